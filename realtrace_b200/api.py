@@ -1,0 +1,269 @@
+"""ctypes binding of the C ABI (include/realtrace_b200.h) for the Python harness.
+
+There is no fallback of any kind here: if the CUDA library has not been built, or no CUDA
+device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librealtrace_b200.so")
+
+FLAG_BRUTE_FORCE, FLAG_COUNT_WORK, FLAG_PACKED_TILES = 1, 2, 4
+COMMIT_BUILD, COMMIT_REFIT = 0, 1
+
+
+class RtMaterial(C.Structure):
+    _fields_ = [("color", C.c_float * 3), ("ka", C.c_float), ("kd", C.c_float), ("ks", C.c_float),
+                ("kr", C.c_float), ("kt", C.c_float), ("eta", C.c_float), ("flags", C.c_uint32)]
+
+
+class RtCamera(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("u", C.c_float * 3), ("v", C.c_float * 3), ("w", C.c_float * 3),
+                ("focal_distance", C.c_float), ("aspect", C.c_float), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class RtRenderParams(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("rank", C.c_int32),
+                ("world_size", C.c_int32), ("flags", C.c_uint32)]
+
+
+class RtAuxOut(C.Structure):
+    _fields_ = [("prim_id", C.c_void_p), ("t", C.c_void_p)]
+
+
+class RtFrameStats(C.Structure):
+    _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_secondary", C.c_uint64),
+                ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("waves", C.c_uint32), ("tiles", C.c_uint32),
+                ("kernel_launches", C.c_uint32), ("max_queue", C.c_uint32), ("ms_device", C.c_float),
+                ("ms_trace", C.c_float), ("ms_shade", C.c_float), ("ms_secondary", C.c_float),
+                ("ms_resolve", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class RtBuildStats(C.Structure):
+    _fields_ = [("n_triangles", C.c_uint32), ("n_large_triangles", C.c_uint32), ("n_nodes", C.c_uint32),
+                ("sort_passes", C.c_uint32), ("ms_build", C.c_float), ("ms_refit", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+ABI_SYMBOLS = [
+    "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_scene_set_triangles", "rt_scene_set_spheres",
+    "rt_scene_set_planes", "rt_scene_set_cylinders", "rt_scene_set_materials", "rt_scene_set_lights",
+    "rt_scene_set_environment", "rt_scene_commit", "rt_scene_update_vertices", "rt_scene_build_stats", "rt_render",
+    "rt_render_device", "rt_tile_layout", "rt_assemble_tiles", "rt_trace_rays", "rt_shade_rays", "rt_bvh_download",
+    "rt_debug_sort_pairs",
+]
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                           "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32p, fp = C.c_void_p, C.c_void_p, C.c_void_p
+    lib.rt_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.rt_destroy.argtypes = [vp]
+    lib.rt_last_error.argtypes = [vp]
+    lib.rt_last_error.restype = C.c_char_p
+    lib.rt_set_stream.argtypes = [vp, vp]
+    lib.rt_scene_set_triangles.argtypes = [vp, fp, u32p, fp, u32p, C.c_uint32]
+    for n in ("rt_scene_set_spheres", "rt_scene_set_planes", "rt_scene_set_cylinders"):
+        getattr(lib, n).argtypes = [vp, fp, u32p, u32p, C.c_uint32]
+    lib.rt_scene_set_materials.argtypes = [vp, vp, C.c_uint32]
+    lib.rt_scene_set_lights.argtypes = [vp, fp, C.c_uint32]
+    lib.rt_scene_set_environment.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.rt_scene_commit.argtypes = [vp, C.c_int]
+    lib.rt_scene_update_vertices.argtypes = [vp, fp, C.c_uint32]
+    lib.rt_scene_build_stats.argtypes = [vp, C.POINTER(RtBuildStats)]
+    lib.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp, C.POINTER(RtAuxOut),
+                              C.POINTER(RtFrameStats)]
+    lib.rt_render_device.argtypes = lib.rt_render.argtypes
+    lib.rt_tile_layout.argtypes = [C.c_int32] * 6 + [C.POINTER(C.c_uint32)] * 3
+    lib.rt_assemble_tiles.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.rt_trace_rays.argtypes = [vp, fp, C.c_uint32, C.c_uint32, vp, vp]
+    lib.rt_shade_rays.argtypes = [vp, fp, C.c_uint32, C.c_int32, C.c_uint32, vp]
+    lib.rt_bvh_download.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.rt_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint32]
+    for n in ABI_SYMBOLS:
+        if n != "rt_last_error":
+            getattr(lib, n).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+class RtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"realtrace_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None and a.size else None
+
+
+def camera_struct(cam) -> RtCamera:
+    """Flatten a scene.Camera exactly like Camera's constructor does (camera.cpp:4-25)."""
+    u, v, w, focal, aspect = cam.basis()
+    c = RtCamera()
+    c.pos = (C.c_float * 3)(*[float(x) for x in cam.pos])
+    c.u = (C.c_float * 3)(*[float(x) for x in u])
+    c.v = (C.c_float * 3)(*[float(x) for x in v])
+    c.w = (C.c_float * 3)(*[float(x) for x in w])
+    c.focal_distance = float(focal)
+    c.aspect = float(aspect)
+    c.width, c.height = int(cam.width), int(cam.height)
+    return c
+
+
+def tile_layout(width, height, tile_w=0, tile_h=0, rank=0, world=1):
+    lib = load_library()
+    a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = lib.rt_tile_layout(width, height, tile_w, tile_h, rank, world, C.byref(a), C.byref(b), C.byref(c))
+    if rc != 0:
+        raise RtError(rc, "rt_tile_layout: bad arguments")
+    return a.value, b.value, c.value
+
+
+class Context:
+    """One GPU context (rt_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.rt_create(C.byref(h), device)
+        if rc != 0:
+            raise RtError(rc, self.lib.rt_last_error(None).decode())
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RtError(rc, self.lib.rt_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.rt_set_stream(self.h, cuda_stream_ptr))
+
+    # ---- scene
+    def set_scene(self, s):
+        lib, h = self.lib, self.h
+        self._check(lib.rt_scene_set_triangles(h, _ptr(s.tri_v), _ptr(s.tri_material), _ptr(s.tri_rgb),
+                                               _ptr(s.tri_object_id), len(s.tri_v)))
+        self._check(lib.rt_scene_set_spheres(h, _ptr(s.sph), _ptr(s.sph_material), _ptr(s.sph_object_id), len(s.sph)))
+        self._check(lib.rt_scene_set_planes(h, _ptr(s.pln), _ptr(s.pln_material), _ptr(s.pln_object_id), len(s.pln)))
+        self._check(lib.rt_scene_set_cylinders(h, _ptr(s.cyl), _ptr(s.cyl_material), _ptr(s.cyl_object_id), len(s.cyl)))
+        mats = np.ascontiguousarray(s.materials)
+        assert mats.dtype.itemsize == C.sizeof(RtMaterial)
+        self._check(lib.rt_scene_set_materials(h, mats.ctypes.data, len(mats)))
+        self._check(lib.rt_scene_set_lights(h, _ptr(s.lights), len(s.lights)))
+        amb = (C.c_float * 3)(*s.ambient)
+        bg = (C.c_float * 3)(*s.background)
+        self._check(lib.rt_scene_set_environment(h, amb, bg))
+
+    def commit(self, mode=COMMIT_BUILD):
+        self._check(self.lib.rt_scene_commit(self.h, mode))
+        return self.build_stats()
+
+    def update_vertices(self, tri_v):
+        v = np.ascontiguousarray(tri_v, np.float32).reshape(-1, 9)
+        self._check(self.lib.rt_scene_update_vertices(self.h, v.ctypes.data, len(v)))
+
+    def build_stats(self):
+        st = RtBuildStats()
+        self._check(self.lib.rt_scene_build_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    # ---- rendering
+    @staticmethod
+    def _params(max_depth, tile=(0, 0), rank=0, world=1, flags=0):
+        p = RtRenderParams()
+        p.max_depth, p.tile_w, p.tile_h, p.rank, p.world_size, p.flags = max_depth, tile[0], tile[1], rank, world, flags
+        return p
+
+    def render(self, cam, max_depth, aux=False, tile=(0, 0), rank=0, world=1, flags=0, out=None):
+        """Host-buffer frame (rt_render).  Returns (rgb[H,W,3] u8, prim[H,W] i32|None, t[H,W] f32|None, stats)."""
+        c = camera_struct(cam)
+        p = self._params(max_depth, tile, rank, world, flags)
+        W, H = cam.width, cam.height
+        if flags & FLAG_PACKED_TILES:
+            _, owned, tb = tile_layout(W, H, tile[0], tile[1], rank, world)
+            rgb = np.zeros(owned * tb, np.uint8) if out is None else out
+        else:
+            rgb = np.zeros((H, W, 3), np.uint8) if out is None else out
+        prim = t = None
+        a = None
+        if aux:
+            prim = np.full((H, W), -1, np.int32)
+            t = np.zeros((H, W), np.float32)
+            a = RtAuxOut(prim.ctypes.data, t.ctypes.data)
+        st = RtFrameStats()
+        self._check(self.lib.rt_render(self.h, C.byref(c), C.byref(p), rgb.ctypes.data,
+                                       C.byref(a) if a is not None else None, C.byref(st)))
+        return rgb, prim, t, st.as_dict()
+
+    def render_device(self, cam, max_depth, rgb_dev_ptr, tile=(0, 0), rank=0, world=1, flags=0, want_stats=True):
+        """Device-buffer frame (rt_render_device); rgb_dev_ptr is a CUDA device pointer (int)."""
+        c = camera_struct(cam)
+        p = self._params(max_depth, tile, rank, world, flags)
+        st = RtFrameStats()
+        self._check(self.lib.rt_render_device(self.h, C.byref(c), C.byref(p), rgb_dev_ptr, None,
+                                              C.byref(st) if want_stats else None))
+        return st.as_dict()
+
+    def assemble_tiles(self, packed_dev_ptr, src_rank, world, width, height, frame_dev_ptr, tile=(0, 0)):
+        self._check(self.lib.rt_assemble_tiles(self.h, packed_dev_ptr, src_rank, world, width, height, tile[0], tile[1],
+                                               frame_dev_ptr))
+
+    # ---- per-ray queries
+    def trace_rays(self, rays, flags=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        prim = np.zeros(len(rays), np.int32)
+        t = np.zeros(len(rays), np.float32)
+        self._check(self.lib.rt_trace_rays(self.h, rays.ctypes.data, len(rays), flags, prim.ctypes.data, t.ctypes.data))
+        return prim, t
+
+    def shade_rays(self, rays, max_depth, flags=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        out = np.zeros((len(rays), 3), np.float32)
+        self._check(self.lib.rt_shade_rays(self.h, rays.ctypes.data, len(rays), max_depth, flags, out.ctypes.data))
+        return out
+
+    # ---- introspection
+    def bvh_download(self):
+        nn, nb = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.rt_bvh_download(self.h, None, None, None, C.byref(nn), C.byref(nb)))
+        nodes = np.zeros((nn.value, 16), np.float32)
+        order = np.zeros(nb.value, np.uint32)
+        keys = np.zeros(nb.value, np.uint64)
+        self._check(self.lib.rt_bvh_download(self.h, _ptr(nodes), _ptr(order), _ptr(keys), C.byref(nn), C.byref(nb)))
+        return nodes, order, keys
+
+    def sort_pairs(self, keys, values):
+        keys = np.ascontiguousarray(keys, np.uint64).copy()
+        values = np.ascontiguousarray(values, np.uint32).copy()
+        self._check(self.lib.rt_debug_sort_pairs(self.h, _ptr(keys), _ptr(values), len(keys)))
+        return keys, values

@@ -1,0 +1,371 @@
+// api.cu — the extern "C" boundary (include/realtrace_b200.h).  No exception crosses it: every
+// entry point converts failures into a negative rt_status and records the text for rt_last_error.
+#include <cmath>
+#include <cstring>
+
+#include "rt_context.h"
+
+static thread_local std::string g_create_error;
+
+template <class F>
+static int guarded(rt_ctx* ctx, F&& body) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    try {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) throw RtError{RT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+        body();
+        return RT_OK;
+    } catch (const RtError& e) {
+        ctx->err = e.msg;
+        cudaGetLastError();   // clear a sticky-less error so the next call starts clean
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        ctx->err = "host allocation failed";
+        return RT_ERR_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        ctx->err = e.what();
+        return RT_ERR_INVALID_ARGUMENT;
+    }
+}
+
+static void need(bool ok, const char* what) {
+    if (!ok) throw RtError{RT_ERR_INVALID_ARGUMENT, what};
+}
+
+extern "C" {
+
+int rt_create(rt_ctx** out, int device) {
+    if (!out) return RT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                         "); realtrace_b200 has no CPU fallback";
+        cudaGetLastError();
+        return RT_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "device ordinal out of range";
+        return RT_ERR_INVALID_ARGUMENT;
+    }
+    rt_ctx* c = nullptr;
+    try {
+        c = new rt_ctx;
+        c->device = device;
+        RT_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        RT_CUDA(cudaGetDeviceProperties(&prop, device));
+        c->sm_count = prop.multiProcessorCount;
+        RT_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        for (auto& ev : c->ev) RT_CUDA(cudaEventCreate(&ev));
+        const char* ls = getenv("RT_LEAF_SIZE");
+        if (ls) {
+            int v = atoi(ls);
+            if (v >= 1 && v <= RT_LEAF_MAX) c->leaf_size = v;
+        }
+        rt_render_init(c);
+    } catch (const RtError& err) {
+        g_create_error = err.msg;
+        delete c;
+        cudaGetLastError();
+        return err.code;
+    }
+    *out = c;
+    return RT_OK;
+}
+
+int rt_destroy(rt_ctx* ctx) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->h_waves) cudaFreeHost(ctx->h_waves);
+    if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return RT_OK;
+}
+
+const char* rt_last_error(rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rt_set_stream(rt_ctx* ctx, void* cuda_stream) {
+    return guarded(ctx, [&] { ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream; });
+}
+
+int rt_scene_set_triangles(rt_ctx* ctx, const float* v, const uint32_t* material_id, const float* vertex_rgb,
+                           const uint32_t* object_id, uint32_t n) {
+    return guarded(ctx, [&] {
+        need(n == 0 || (v && material_id), "rt_scene_set_triangles: v and material_id are required");
+        need(n < (1u << 28), "rt_scene_set_triangles: at most 2^28 - 1 triangles");
+        ctx->h_tri_v.assign(v, v + 9 * (size_t)n);
+        ctx->h_tri_mat.assign(material_id, material_id + n);
+        ctx->h_tri_obj.resize(n);
+        for (uint32_t i = 0; i < n; i++) ctx->h_tri_obj[i] = object_id ? object_id[i] : i;
+        if (vertex_rgb) ctx->h_tri_rgb.assign(vertex_rgb, vertex_rgb + 9 * (size_t)n);
+        else ctx->h_tri_rgb.clear();
+        ctx->committed = false;
+    });
+}
+
+static void fill_ids(std::vector<AnalyticPrim>& dst, uint32_t kind, const uint32_t* material_id, const uint32_t* object_id,
+                     uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) {
+        dst[i].kind = kind;
+        dst[i].material = material_id[i];
+        dst[i].object_id = object_id ? object_id[i] : 0xffffffffu;   // resolved at commit
+        dst[i].tri_index = 0;
+    }
+}
+
+int rt_scene_set_spheres(rt_ctx* ctx, const float* p, const uint32_t* material_id, const uint32_t* object_id, uint32_t n) {
+    return guarded(ctx, [&] {
+        need(n == 0 || (p && material_id), "rt_scene_set_spheres: packed and material_id are required");
+        ctx->h_spheres.assign(n, AnalyticPrim{});
+        fill_ids(ctx->h_spheres, RT_KIND_SPHERE, material_id, object_id, n);
+        for (uint32_t i = 0; i < n; i++) {
+            const float* q = p + 4 * (size_t)i;
+            ctx->h_spheres[i].a = make_float4(q[0], q[1], q[2], q[3]);
+        }
+        ctx->committed = false;
+    });
+}
+
+int rt_scene_set_planes(rt_ctx* ctx, const float* p, const uint32_t* material_id, const uint32_t* object_id, uint32_t n) {
+    return guarded(ctx, [&] {
+        need(n == 0 || (p && material_id), "rt_scene_set_planes: packed and material_id are required");
+        ctx->h_planes.assign(n, AnalyticPrim{});
+        fill_ids(ctx->h_planes, RT_KIND_PLANE, material_id, object_id, n);
+        for (uint32_t i = 0; i < n; i++) {
+            const float* q = p + 12 * (size_t)i;
+            ctx->h_planes[i].a = make_float4(q[0], q[1], q[2], 0);
+            ctx->h_planes[i].b = make_float4(q[3], q[4], q[5], 0);
+            ctx->h_planes[i].c = make_float4(q[6], q[7], q[8], 0);
+            ctx->h_planes[i].d = make_float4(q[9], q[10], q[11], 0);
+        }
+        ctx->committed = false;
+    });
+}
+
+int rt_scene_set_cylinders(rt_ctx* ctx, const float* p, const uint32_t* material_id, const uint32_t* object_id, uint32_t n) {
+    return guarded(ctx, [&] {
+        need(n == 0 || (p && material_id), "rt_scene_set_cylinders: packed and material_id are required");
+        ctx->h_cylinders.assign(n, AnalyticPrim{});
+        fill_ids(ctx->h_cylinders, RT_KIND_CYLINDER, material_id, object_id, n);
+        for (uint32_t i = 0; i < n; i++) {
+            const float* q = p + 7 * (size_t)i;
+            ctx->h_cylinders[i].a = make_float4(q[0], q[1], q[2], q[3]);
+            ctx->h_cylinders[i].b = make_float4(q[4], q[5], q[6], 0);
+        }
+        ctx->committed = false;
+    });
+}
+
+int rt_scene_set_materials(rt_ctx* ctx, const rt_material* m, uint32_t n) {
+    return guarded(ctx, [&] {
+        need(n > 0 && m, "rt_scene_set_materials: at least one material is required");
+        ctx->h_materials.assign(m, m + n);
+        ctx->committed = false;
+    });
+}
+
+int rt_scene_set_lights(rt_ctx* ctx, const float* pos_rgb, uint32_t n) {
+    return guarded(ctx, [&] {
+        need(n == 0 || pos_rgb, "rt_scene_set_lights: pos_rgb is required");
+        ctx->h_lights.assign(pos_rgb, pos_rgb + 6 * (size_t)n);
+        ctx->committed = false;
+    });
+}
+
+int rt_scene_set_environment(rt_ctx* ctx, const float ambient[3], const float background[3]) {
+    return guarded(ctx, [&] {
+        need(ambient && background, "rt_scene_set_environment: both colours are required");
+        for (int k = 0; k < 3; k++) { ctx->ambient[k] = ambient[k]; ctx->background[k] = background[k]; }
+        if (ctx->committed) for (int k = 0; k < 3; k++) { ctx->scene.ambient[k] = ambient[k]; ctx->scene.background[k] = background[k]; }
+    });
+}
+
+int rt_scene_commit(rt_ctx* ctx, int mode) {
+    return guarded(ctx, [&] {
+        need(mode == RT_COMMIT_BUILD || mode == RT_COMMIT_REFIT, "rt_scene_commit: unknown mode");
+        if (mode == RT_COMMIT_REFIT) {
+            if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "rt_scene_commit(REFIT) before a BUILD commit"};
+            rt_build_bvh(ctx, true);
+            return;
+        }
+        need(!ctx->h_materials.empty(), "rt_scene_commit: no materials set");
+        uint32_t nm = (uint32_t)ctx->h_materials.size();
+        for (uint32_t m : ctx->h_tri_mat) need(m < nm, "rt_scene_commit: triangle material id out of range");
+        bool any_bary = false;
+        for (const auto& m : ctx->h_materials) any_bary |= (m.flags & RT_MATERIAL_BARYCENTRIC) != 0;
+        if (any_bary)
+            for (uint32_t m : ctx->h_tri_mat)
+                if (ctx->h_materials[m].flags & RT_MATERIAL_BARYCENTRIC)
+                    need(!ctx->h_tri_rgb.empty(), "rt_scene_commit: barycentric material without vertex_rgb");
+        // default object ids of the analytic kinds: after the triangles, in the order spheres, planes, cylinders
+        uint32_t next = (uint32_t)(ctx->h_tri_v.size() / 9);
+        for (auto* list : {&ctx->h_spheres, &ctx->h_planes, &ctx->h_cylinders})
+            for (auto& p : *list) {
+                need(p.material < nm, "rt_scene_commit: analytic material id out of range");
+                need(!(ctx->h_materials[p.material].flags & RT_MATERIAL_BARYCENTRIC),
+                     "rt_scene_commit: barycentric materials are for triangles only");
+                if (p.object_id == 0xffffffffu) p.object_id = next;
+                next++;
+            }
+        rt_build_bvh(ctx, false);
+        ctx->committed = true;
+    });
+}
+
+int rt_scene_update_vertices(rt_ctx* ctx, const float* v, uint32_t n) {
+    return guarded(ctx, [&] {
+        if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "rt_scene_update_vertices before commit"};
+        need(v && n == ctx->n_tri, "rt_scene_update_vertices: vertex count must equal the committed triangle count");
+        ctx->h_tri_v.assign(v, v + 9 * (size_t)n);
+        RT_CUDA(cudaMemcpyAsync(ctx->d_tri_v.p, ctx->h_tri_v.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int rt_scene_build_stats(rt_ctx* ctx, rt_build_stats* out) {
+    return guarded(ctx, [&] {
+        need(out != nullptr, "rt_scene_build_stats: out is NULL");
+        *out = ctx->build_stats;
+    });
+}
+
+static void check_render_args(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p) {
+    if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "render before rt_scene_commit"};
+    need(cam && p, "render: camera and params are required");
+    need(cam->width > 0 && cam->height > 0 && (int64_t)cam->width * cam->height < (1ll << 31), "render: bad frame size");
+}
+
+int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, void* rgb_out_dev,
+                     const rt_aux_out* aux_dev, rt_frame_stats* stats) {
+    return guarded(ctx, [&] {
+        check_render_args(ctx, cam, p);
+        rt_render_frame(ctx, cam, p, rgb_out_dev, aux_dev, stats);
+    });
+}
+
+int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint8_t* rgb_out, const rt_aux_out* aux,
+              rt_frame_stats* stats) {
+    return guarded(ctx, [&] {
+        check_render_args(ctx, cam, p);
+        need(rgb_out != nullptr, "rt_render: rgb_out is NULL");
+        size_t npix = (size_t)cam->width * cam->height;
+        bool packed = (p->flags & RT_FLAG_PACKED_TILES) != 0;
+        size_t bytes = npix * 3;
+        if (packed) {
+            uint32_t total, owned, tb;
+            rt_tile_layout(cam->width, cam->height, p->tile_w, p->tile_h, p->world_size > 1 ? p->rank : 0,
+                           p->world_size > 1 ? p->world_size : 1, &total, &owned, &tb);
+            bytes = (size_t)owned * tb;
+        }
+        ctx->d_rgb.reserve(bytes ? bytes : 1);
+        rt_aux_out aux_dev{nullptr, nullptr};
+        if (aux && (aux->prim_id || aux->t)) {
+            ctx->d_aux_prim.reserve(npix);
+            ctx->d_aux_t.reserve(npix);
+            aux_dev.prim_id = ctx->d_aux_prim.p;
+            aux_dev.t = ctx->d_aux_t.p;
+            // pixels of tiles this rank does not own stay "miss"
+            RT_CUDA(cudaMemsetAsync(ctx->d_aux_prim.p, 0xff, npix * sizeof(int32_t), ctx->stream));
+            RT_CUDA(cudaMemsetAsync(ctx->d_aux_t.p, 0, npix * sizeof(float), ctx->stream));
+        }
+        if (!packed && p->world_size > 1) RT_CUDA(cudaMemsetAsync(ctx->d_rgb.p, 0, bytes, ctx->stream));
+        RtError deferred{RT_OK, ""};
+        try {
+            rt_render_frame(ctx, cam, p, ctx->d_rgb.p, (aux_dev.prim_id ? &aux_dev : nullptr), stats);
+        } catch (const RtError& e) {
+            if (e.code != RT_ERR_QUEUE_OVERFLOW) throw;
+            deferred = e;
+        }
+        RT_CUDA(cudaMemcpyAsync(rgb_out, ctx->d_rgb.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (aux && aux->prim_id)
+            RT_CUDA(cudaMemcpyAsync(aux->prim_id, ctx->d_aux_prim.p, npix * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (aux && aux->t)
+            RT_CUDA(cudaMemcpyAsync(aux->t, ctx->d_aux_t.p, npix * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (deferred.code != RT_OK) throw deferred;
+    });
+}
+
+int rt_tile_layout(int32_t width, int32_t height, int32_t tile_w, int32_t tile_h, int32_t rank, int32_t world_size,
+                   uint32_t* tiles_total, uint32_t* tiles_owned, uint32_t* tile_bytes) {
+    if (tile_w <= 0) tile_w = 64;
+    if (tile_h <= 0) tile_h = 32;
+    if (width <= 0 || height <= 0 || world_size < 1 || rank < 0 || rank >= world_size) return RT_ERR_INVALID_ARGUMENT;
+    uint32_t tx = (uint32_t)((width + tile_w - 1) / tile_w), ty = (uint32_t)((height + tile_h - 1) / tile_h);
+    uint32_t total = tx * ty;
+    if (tiles_total) *tiles_total = total;
+    if (tiles_owned) *tiles_owned = total > (uint32_t)rank ? (total - (uint32_t)rank + (uint32_t)world_size - 1) / (uint32_t)world_size : 0u;
+    if (tile_bytes) *tile_bytes = (uint32_t)(tile_w * tile_h * 3);
+    return RT_OK;
+}
+
+int rt_assemble_tiles(rt_ctx* ctx, const void* packed_dev, int32_t src_rank, int32_t world_size, int32_t width,
+                      int32_t height, int32_t tile_w, int32_t tile_h, void* frame_dev) {
+    return guarded(ctx, [&] {
+        need(packed_dev && frame_dev, "rt_assemble_tiles: NULL buffer");
+        if (tile_w <= 0) tile_w = 64;
+        if (tile_h <= 0) tile_h = 32;
+        need(world_size >= 1 && src_rank >= 0 && src_rank < world_size && width > 0 && height > 0, "rt_assemble_tiles: bad layout");
+        rt_assemble(ctx, packed_dev, src_rank, world_size, width, height, tile_w, tile_h, frame_dev);
+    });
+}
+
+int rt_trace_rays(rt_ctx* ctx, const float* rays, uint32_t n, uint32_t flags, int32_t* prim_id, float* t) {
+    return guarded(ctx, [&] {
+        if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "rt_trace_rays before rt_scene_commit"};
+        need(n == 0 || rays, "rt_trace_rays: rays is NULL");
+        rt_query_rays(ctx, rays, n, 0, flags, false, prim_id, t, nullptr);
+    });
+}
+
+int rt_shade_rays(rt_ctx* ctx, const float* rays, uint32_t n, int32_t max_depth, uint32_t flags, float* rgb_out) {
+    return guarded(ctx, [&] {
+        if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "rt_shade_rays before rt_scene_commit"};
+        need(n == 0 || (rays && rgb_out), "rt_shade_rays: NULL buffer");
+        rt_query_rays(ctx, rays, n, max_depth, flags, true, nullptr, nullptr, rgb_out);
+    });
+}
+
+int rt_bvh_download(rt_ctx* ctx, float* nodes, uint32_t* tri_order, uint64_t* keys, uint32_t* n_nodes,
+                    uint32_t* n_bvh_triangles) {
+    return guarded(ctx, [&] {
+        if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "rt_bvh_download before rt_scene_commit"};
+        uint32_t nn = (uint32_t)ctx->scene.n_nodes, nb = ctx->n_bvh;
+        if (n_nodes) *n_nodes = nn;
+        if (n_bvh_triangles) *n_bvh_triangles = nb;
+        cudaStream_t st = ctx->stream;
+        if (nodes && nn) RT_CUDA(cudaMemcpyAsync(nodes, ctx->d_nodes.p, (size_t)nn * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (tri_order && nb) RT_CUDA(cudaMemcpyAsync(tri_order, ctx->d_vals[ctx->sorted_buf].p, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (keys && nb) RT_CUDA(cudaMemcpyAsync(keys, ctx->d_keys[ctx->sorted_buf].p, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int rt_debug_sort_pairs(rt_ctx* ctx, uint64_t* keys, uint32_t* values, uint32_t n) {
+    return guarded(ctx, [&] {
+        need(n == 0 || (keys && values), "rt_debug_sort_pairs: NULL buffer");
+        if (n == 0) return;
+        // the scene's sort buffers are reused: a later commit rebuilds them, but an already
+        // committed hierarchy keeps pointing at d_vals[sorted_buf], so refuse in that state
+        need(!ctx->committed, "rt_debug_sort_pairs: use a context without a committed scene");
+        cudaStream_t st = ctx->stream;
+        ctx->d_keys[0].reserve(n);
+        ctx->d_vals[0].reserve(n);
+        RT_CUDA(cudaMemcpyAsync(ctx->d_keys[0].p, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        RT_CUDA(cudaMemcpyAsync(ctx->d_vals[0].p, values, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        int passes = 0;
+        rt_sort_pairs_device(ctx, n, &passes);
+        RT_CUDA(cudaMemcpyAsync(keys, ctx->d_keys[ctx->sorted_buf].p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaMemcpyAsync(values, ctx->d_vals[ctx->sorted_buf].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+}  // extern "C"

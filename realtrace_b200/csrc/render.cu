@@ -1,0 +1,677 @@
+// render.cu — the wavefront pipeline: primary raygen + persistent-thread nearest-hit traversal,
+// shadow any-hit + shading + bounce spawning, RGB8 resolve.
+//
+// Replaces the reference's frame loop RenderEngine::renderLoop -> trace -> World::shade_ray
+// (/root/reference/Serial/renderengine.cpp:3-26, world.cpp:32-111) and its display conversion
+// Camera::drawPixel (camera.cpp:46-52).  One "wave" is one generation of rays:
+//   k_trace   persistent warps pull 32 rays at a time from a global cursor; wave 0 generates its
+//             rays in registers from the pixel index (tile-ordered, 8x4 pixels per warp), later
+//             waves read 48-byte SoA ray records.  Hits are compacted into a hit queue with one
+//             warp-aggregated atomic (ballot + popc); misses add throughput*background at once.
+//   k_shade   persistent warps pull hit-queue entries: per light one any-hit shadow query
+//             (world.cpp:44-51), the local Phong-like term (:126-137), then the mirror /
+//             dielectric children (:77-107) appended to the next wave's ray queue, again with one
+//             atomic per warp (shfl prefix sum).
+//   k_resolve 32.32 fixed-point accumulators -> clamp -> (uint8)(255 c) (color.cpp:19-28,
+//             camera.cpp:49-51) into the frame or into this rank's packed tile buffer.
+// Pixel sums use integer atomics, so the frame is bit-identical for any tile split, queue order
+// or GPU count.
+#include <cstring>
+
+#include "rt_context.h"
+#include "rt_shade.h"
+
+namespace {
+
+constexpr int TRACE_TPB = 128;
+constexpr int SHADE_TPB = 128;
+
+struct CamDev {
+    double pos[3], u[3], v[3], w[3];
+    double focal, aspect;
+    int W, H;
+};
+
+struct FrameDev {
+    int W, H, tile_w, tile_h, tiles_x, tile_pix;
+    uint32_t n_tiles_owned, n_local_pix;
+    const uint32_t* tile_ids;
+};
+
+// local pixel index -> frame pixel.  A tile is cut into 8x4 blocks (one warp each); lane = x%8 + 8*(y%4).
+__device__ __forceinline__ bool local_to_pixel(const FrameDev& f, uint32_t lp, int& i, int& j) {
+    uint32_t tl = lp / (uint32_t)f.tile_pix, p = lp % (uint32_t)f.tile_pix;
+    uint32_t tile = __ldg(f.tile_ids + tl);
+    int tx = (int)(tile % (uint32_t)f.tiles_x), ty = (int)(tile / (uint32_t)f.tiles_x);
+    int b = (int)(p >> 5), l = (int)(p & 31);
+    int bpr = f.tile_w >> 3;
+    i = tx * f.tile_w + (b % bpr) * 8 + (l & 7);
+    j = ty * f.tile_h + (b / bpr) * 4 + (l >> 3);
+    return i < f.W && j < f.H;
+}
+__device__ __forceinline__ uint32_t pixel_in_tile_to_local(const FrameDev& f, uint32_t tl, int x, int y) {
+    int bpr = f.tile_w >> 3;
+    int b = (y >> 2) * bpr + (x >> 3);
+    int l = (y & 3) * 8 + (x & 7);
+    return tl * (uint32_t)f.tile_pix + (uint32_t)(b * 32 + l);
+}
+
+// Camera::get_ray_direction (camera.cpp:33-44) + the Ray constructor's normalisation (ray.h:25-29),
+// evaluated in FP64 like the reference and rounded once to FP32.
+__device__ __forceinline__ void primary_ray(const CamDev& c, int i, int j, f3& o, f3& d) {
+    float xw = (float)(c.aspect * (i - c.W / 2.0 + 0.5) / c.W);
+    float yw = (float)((j - c.H / 2.0 + 0.5) / c.H);
+    double dx = -c.w[0] * c.focal + c.u[0] * (double)xw + c.v[0] * (double)yw;
+    double dy = -c.w[1] * c.focal + c.u[1] * (double)xw + c.v[1] * (double)yw;
+    double dz = -c.w[2] * c.focal + c.u[2] * (double)xw + c.v[2] * (double)yw;
+    double l = sqrt(dx * dx + dy * dy + dz * dz);
+    // get_ray_direction normalises, then Ray's constructor normalises again
+    dx /= l; dy /= l; dz /= l;
+    l = sqrt(dx * dx + dy * dy + dz * dz);
+    d = mk3((float)(dx / l), (float)(dy / l), (float)(dz / l));
+    o = mk3((float)c.pos[0], (float)c.pos[1], (float)c.pos[2]);
+}
+
+__device__ __forceinline__ void accumulate(long long* accum, uint32_t pix, f3 c) {
+    const float scale = 4294967296.0f, lim = 1048576.0f;
+    float v[3] = {c.x, c.y, c.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float x = v[k];
+        if (!(x == x)) x = 0.0f;                       // NaN -> 0
+        x = fminf(fmaxf(x, -lim), lim);
+        long long q = __float2ll_rn(x * scale);
+        if (q) atomicAdd((unsigned long long*)(accum + 3 * (size_t)pix + k), (unsigned long long)q);
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct TraceArgs {
+    SceneDev s;
+    CamDev cam;
+    FrameDev f;
+    RayQueue q;
+    float4* hits;
+    uint32_t* hitq;
+    WaveCounters* wave;
+    long long* accum;
+    FrameCounters* fc;
+    int32_t* aux_prim;
+    float* aux_t;
+    uint32_t brute;
+    uint32_t cap;       // ray-queue capacity (bounds n_rays after an overflow)
+};
+
+template <bool PRIMARY, bool COUNT>
+__global__ void __launch_bounds__(TRACE_TPB) k_trace(const __grid_constant__ TraceArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = PRIMARY ? a.f.n_local_pix : min(a.wave->n_rays, a.cap);
+    const f3 bg = mk3(a.s.background[0], a.s.background[1], a.s.background[2]);
+    WorkCount wc;
+    wc.nodes = wc.tris = 0;
+    bool overflow = false;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&a.wave->fetch_trace, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t idx = base + lane;
+        bool valid = idx < n;
+        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), w = mk3(1, 1, 1);
+        uint32_t pix = idx;
+        int pi = 0, pj = 0;
+        if (valid) {
+            if (PRIMARY) {
+                valid = local_to_pixel(a.f, idx, pi, pj);
+                if (valid) primary_ray(a.cam, pi, pj, o, d);
+            } else {
+                float4 ro = a.q.o_pix[idx], rd = a.q.d_lvl[idx], rw = a.q.w[idx];
+                o = mk3(ro); d = mk3(rd); w = mk3(rw);
+                pix = __float_as_uint(ro.w);
+            }
+        }
+        HitRec h;
+        h.t = RT_FLT_MAX; h.prim = RT_MISS; h.beta = h.gamma = 0.0f;
+        bool found = false;
+        if (valid) found = trace_ray<false>(a.s, o, d, a.brute != 0, h, COUNT ? &wc : nullptr, &overflow);
+        if (valid && a.aux_prim) {
+            size_t at = PRIMARY ? (size_t)pi + (size_t)pj * a.f.W : (size_t)pix;
+            int id = -1;
+            if (found) {
+                if (h.prim >= 0) id = (int)__float_as_uint(__ldg(a.s.tris + 3 * (size_t)h.prim).w);
+                else id = (int)a.s.analytic[rt_analytic_index(h.prim)].object_id;
+            }
+            a.aux_prim[at] = id;
+            if (a.aux_t) a.aux_t[at] = found ? h.t : RT_FLT_MAX;
+        }
+        // misses resolve to throughput * background right here (world.cpp:110)
+        if (valid && !found) accumulate(a.accum, pix, w * bg);
+        // hits: one atomic per warp reserves a run of the hit queue
+        uint32_t mask = __ballot_sync(0xffffffffu, found);
+        if (mask) {
+            uint32_t qbase = 0;
+            int leader = __ffs(mask) - 1;
+            if (lane == leader) qbase = atomicAdd(&a.wave->n_hits, (uint32_t)__popc(mask));
+            qbase = __shfl_sync(0xffffffffu, qbase, leader);
+            if (found) {
+                uint32_t pos = qbase + __popc(mask & ((1u << lane) - 1u));
+                a.hitq[pos] = idx;
+                a.hits[pos] = make_float4(h.t, __int_as_float(h.prim), h.beta, h.gamma);
+            }
+        }
+    }
+    if (COUNT) {
+        uint32_t nn = warp_sum(wc.nodes), nt = warp_sum(wc.tris);
+        if (lane == 0) {
+            atomicAdd(&a.fc->node_visits, (unsigned long long)nn);
+            atomicAdd(&a.fc->tri_tests, (unsigned long long)nt);
+        }
+    }
+    if (__any_sync(0xffffffffu, overflow) && lane == 0) atomicOr(&a.wave->flags, 2u);
+}
+
+struct ShadeArgs {
+    SceneDev s;
+    CamDev cam;
+    FrameDev f;
+    RayQueue qin, qout;
+    const float4* hits;
+    const uint32_t* hitq;
+    WaveCounters* wave;
+    WaveCounters* next;
+    long long* accum;
+    FrameCounters* fc;
+    uint32_t cap;
+    int max_depth;
+    uint32_t brute;
+};
+
+template <bool PRIMARY, bool COUNT>
+__global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ ShadeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = a.wave->n_hits;
+    const f3 bg = mk3(a.s.background[0], a.s.background[1], a.s.background[2]);
+    WorkCount wc;
+    wc.nodes = wc.tris = 0;
+    uint32_t shadow_rays = 0;
+    bool overflow = false, qfull = false;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&a.wave->fetch_shade, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t pos = base + lane;
+        bool valid = pos < n;
+        ShadeOut out;
+        out.n_children = 0;
+        f3 w = mk3(1, 1, 1);
+        uint32_t pix = 0;
+        if (valid) {
+            uint32_t idx = a.hitq[pos];
+            float4 hr = a.hits[pos];
+            HitRec h;
+            h.t = hr.x; h.prim = __float_as_int(hr.y); h.beta = hr.z; h.gamma = hr.w;
+            f3 o, d;
+            int level = 0;
+            if (PRIMARY) {
+                int pi, pj;
+                local_to_pixel(a.f, idx, pi, pj);
+                primary_ray(a.cam, pi, pj, o, d);
+                pix = idx;
+            } else {
+                float4 ro = a.qin.o_pix[idx], rd = a.qin.d_lvl[idx], rw = a.qin.w[idx];
+                o = mk3(ro); d = mk3(rd); w = mk3(rw);
+                pix = __float_as_uint(ro.w);
+                level = __float_as_int(rd.w);
+            }
+            auto any_hit = [&](f3 so, f3 sd) -> bool {
+                HitRec sh;
+                return trace_ray<true>(a.s, so, sd, a.brute != 0, sh, COUNT ? &wc : nullptr, &overflow);
+            };
+            shade_hit(a.s, o, d, level, h, a.max_depth, any_hit, out);
+            shadow_rays += (uint32_t)out.shadow_rays;
+            accumulate(a.accum, pix, w * (out.local + out.bg_weight * bg));
+        }
+        // append children: exclusive prefix over the warp, one atomic
+        uint32_t k = valid ? (uint32_t)out.n_children : 0u;
+        uint32_t incl = k;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o2);
+            if (lane >= o2) incl += t;
+        }
+        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            uint32_t qbase = 0;
+            if (lane == 31) qbase = atomicAdd(&a.next->n_rays, total);
+            qbase = __shfl_sync(0xffffffffu, qbase, 31);
+            uint32_t at = qbase + incl - k;
+            for (uint32_t c = 0; c < k; c++) {
+                if (at + c >= a.cap) { qfull = true; break; }
+                const ShadeChild& ch = out.child[c];
+                f3 cw = w * ch.w;
+                a.qout.o_pix[at + c] = make_float4(ch.o.x, ch.o.y, ch.o.z, __uint_as_float(pix));
+                a.qout.d_lvl[at + c] = make_float4(ch.d.x, ch.d.y, ch.d.z, __int_as_float(ch.level));
+                a.qout.w[at + c] = make_float4(cw.x, cw.y, cw.z, 0.0f);
+            }
+        }
+    }
+    uint32_t ns = warp_sum(shadow_rays);
+    if (lane == 0 && ns) atomicAdd(&a.fc->rays_shadow, (unsigned long long)ns);
+    if (COUNT) {
+        uint32_t nn = warp_sum(wc.nodes), nt = warp_sum(wc.tris);
+        if (lane == 0) {
+            atomicAdd(&a.fc->node_visits, (unsigned long long)nn);
+            atomicAdd(&a.fc->tri_tests, (unsigned long long)nt);
+        }
+    }
+    uint32_t fl = (__any_sync(0xffffffffu, overflow) ? 2u : 0u) | (__any_sync(0xffffffffu, qfull) ? 1u : 0u);
+    if (fl && lane == 0) atomicOr(&a.wave->flags, fl);
+}
+
+// Color::clamp + Camera::drawPixel (color.cpp:19-28, camera.cpp:46-52): truncating 8-bit conversion.
+__device__ __forceinline__ uint32_t to_u8(long long q) {
+    double c = (double)q * (1.0 / 4294967296.0);
+    if (c > 1.0) c = 1.0;
+    if (c < 0.0) c = 0.0;
+    return (uint32_t)(255.0 * c);
+}
+
+// One thread per 4 horizontally adjacent pixels of an owned tile.
+__global__ void __launch_bounds__(256) k_resolve(FrameDev f, const long long* __restrict__ accum,
+                                                uint8_t* __restrict__ out, int packed) {
+    uint32_t quads_per_row = (uint32_t)f.tile_w >> 2;
+    uint32_t quads_per_tile = quads_per_row * (uint32_t)f.tile_h;
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= f.n_tiles_owned * quads_per_tile) return;
+    uint32_t tl = q / quads_per_tile, r = q % quads_per_tile;
+    int y = (int)(r / quads_per_row), x0 = (int)(r % quads_per_row) * 4;
+    uint32_t tile = __ldg(f.tile_ids + tl);
+    int tx = (int)(tile % (uint32_t)f.tiles_x), ty = (int)(tile / (uint32_t)f.tiles_x);
+    int j = ty * f.tile_h + y, i0 = tx * f.tile_w + x0;
+    if (j >= f.H || i0 >= f.W) return;
+    uint32_t lp0 = pixel_in_tile_to_local(f, tl, x0, y);
+    uint32_t px[12];
+    int npx = min(4, f.W - i0);
+    for (int k = 0; k < 4; k++) {
+        const long long* a = accum + 3 * (size_t)(lp0 + k);
+        bool in = k < npx;
+        px[3 * k + 0] = in ? to_u8(a[0]) : 0u;
+        px[3 * k + 1] = in ? to_u8(a[1]) : 0u;
+        px[3 * k + 2] = in ? to_u8(a[2]) : 0u;
+    }
+    size_t byte0 = packed ? ((size_t)tl * f.tile_pix + (size_t)y * f.tile_w + x0) * 3
+                          : ((size_t)i0 + (size_t)j * f.W) * 3;
+    if (npx == 4 && (byte0 & 3) == 0) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out + byte0);
+        o32[0] = px[0] | px[1] << 8 | px[2] << 16 | px[3] << 24;
+        o32[1] = px[4] | px[5] << 8 | px[6] << 16 | px[7] << 24;
+        o32[2] = px[8] | px[9] << 8 | px[10] << 16 | px[11] << 24;
+    } else {
+        for (int k = 0; k < 3 * npx; k++) out[byte0 + k] = (uint8_t)px[k];
+    }
+}
+
+__global__ void k_resolve_float(const long long* __restrict__ accum, uint32_t n3, float* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) out[i] = (float)((double)accum[i] * (1.0 / 4294967296.0));
+}
+
+// Tiles of rank `src` (packed) -> full frame.
+__global__ void __launch_bounds__(256) k_assemble(const uint8_t* __restrict__ packed, uint8_t* __restrict__ frame,
+                                                 int W, int H, int tile_w, int tile_h, int tiles_x,
+                                                 uint32_t tiles_total, int src, int world) {
+    uint32_t quads_per_row = (uint32_t)tile_w >> 2, quads_per_tile = quads_per_row * (uint32_t)tile_h;
+    uint32_t n_owned = tiles_total > (uint32_t)src ? (tiles_total - (uint32_t)src + (uint32_t)world - 1) / (uint32_t)world : 0u;
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_owned * quads_per_tile) return;
+    uint32_t tl = q / quads_per_tile, r = q % quads_per_tile;
+    uint32_t tile = (uint32_t)src + tl * (uint32_t)world;
+    int y = (int)(r / quads_per_row), x0 = (int)(r % quads_per_row) * 4;
+    int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
+    int j = ty * tile_h + y, i0 = tx * tile_w + x0;
+    if (j >= H || i0 >= W) return;
+    int npx = min(4, W - i0);
+    size_t src0 = ((size_t)tl * tile_w * tile_h + (size_t)y * tile_w + x0) * 3;
+    size_t dst0 = ((size_t)i0 + (size_t)j * W) * 3;
+    if (npx == 4 && (dst0 & 3) == 0 && (src0 & 3) == 0) {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(packed + src0);
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(frame + dst0);
+        d32[0] = s32[0]; d32[1] = s32[1]; d32[2] = s32[2];
+    } else {
+        for (int k = 0; k < 3 * npx; k++) frame[dst0 + k] = packed[src0 + k];
+    }
+}
+
+CamDev make_cam(const rt_camera* c) {
+    CamDev d;
+    for (int k = 0; k < 3; k++) { d.pos[k] = c->pos[k]; d.u[k] = c->u[k]; d.v[k] = c->v[k]; d.w[k] = c->w[k]; }
+    d.focal = c->focal_distance;
+    d.aspect = c->aspect;
+    d.W = c->width;
+    d.H = c->height;
+    return d;
+}
+
+template <typename K>
+int persistent_blocks(K kernel, int tpb, int sm_count) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tpb, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return per_sm * sm_count;
+}
+
+void setup_layout(rt_ctx* c, const rt_camera* cam, const rt_render_params* p) {
+    TileLayout L;
+    L.width = cam->width; L.height = cam->height;
+    L.tile_w = p->tile_w > 0 ? p->tile_w : 64;
+    L.tile_h = p->tile_h > 0 ? p->tile_h : 32;
+    L.rank = p->world_size > 1 ? p->rank : 0;
+    L.world = p->world_size > 1 ? p->world_size : 1;
+    if (L.tile_w % 8 || L.tile_h % 4) throw RtError{RT_ERR_INVALID_ARGUMENT, "tile_w must be a multiple of 8 and tile_h of 4"};
+    if (L.rank < 0 || L.rank >= L.world) throw RtError{RT_ERR_INVALID_ARGUMENT, "rank outside [0, world_size)"};
+    L.tiles_x = (L.width + L.tile_w - 1) / L.tile_w;
+    L.tiles_y = (L.height + L.tile_h - 1) / L.tile_h;
+    if (L == c->layout && c->d_tile_ids.p) return;
+    std::vector<uint32_t> ids;
+    uint32_t total = (uint32_t)L.tiles_x * (uint32_t)L.tiles_y;
+    for (uint32_t t = (uint32_t)L.rank; t < total; t += (uint32_t)L.world) ids.push_back(t);
+    L.n_tiles_owned = (uint32_t)ids.size();
+    c->d_tile_ids.reserve(ids.size() ? ids.size() : 1);
+    if (!ids.empty())
+        RT_CUDA(cudaMemcpyAsync(c->d_tile_ids.p, ids.data(), ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    c->layout = L;
+}
+
+FrameDev frame_dev(const rt_ctx* c) {
+    const TileLayout& L = c->layout;
+    FrameDev f;
+    f.W = L.width; f.H = L.height; f.tile_w = L.tile_w; f.tile_h = L.tile_h; f.tiles_x = L.tiles_x;
+    f.tile_pix = L.tile_w * L.tile_h;
+    f.n_tiles_owned = L.n_tiles_owned;
+    f.n_local_pix = L.n_tiles_owned * (uint32_t)f.tile_pix;
+    f.tile_ids = c->d_tile_ids.p;
+    return f;
+}
+
+void ensure_queues(rt_ctx* c, size_t n_rays0, bool need_bounce) {
+    size_t hits_cap = n_rays0 ? n_rays0 : 1;
+    size_t cap = 0;
+    if (need_bounce) cap = (c->has_dielectric ? 2 : 1) * hits_cap;
+    if (cap > hits_cap) hits_cap = cap;
+    c->d_hits.reserve(hits_cap);
+    c->d_hitq.reserve(hits_cap);
+    if (cap) {
+        for (int b = 0; b < 2; b++)
+            for (int k = 0; k < 3; k++) c->d_q[b][k].reserve(cap);
+    }
+    c->queue_cap = cap;
+}
+
+RayQueue queue_of(rt_ctx* c, int b) {
+    RayQueue q;
+    q.o_pix = c->d_q[b][0].p; q.d_lvl = c->d_q[b][1].p; q.w = c->d_q[b][2].p;
+    return q;
+}
+
+template <bool PRIMARY>
+void launch_trace(rt_ctx* c, const TraceArgs& a, bool count) {
+    if (count) k_trace<PRIMARY, true><<<c->trace_blocks, TRACE_TPB, 0, c->stream>>>(a);
+    else k_trace<PRIMARY, false><<<c->trace_blocks, TRACE_TPB, 0, c->stream>>>(a);
+    RT_CUDA(cudaGetLastError());
+}
+template <bool PRIMARY>
+void launch_shade(rt_ctx* c, const ShadeArgs& a, bool count) {
+    if (count) k_shade<PRIMARY, true><<<c->shade_blocks, SHADE_TPB, 0, c->stream>>>(a);
+    else k_shade<PRIMARY, false><<<c->shade_blocks, SHADE_TPB, 0, c->stream>>>(a);
+    RT_CUDA(cudaGetLastError());
+}
+
+// Runs waves 1.. over rays already sitting in queue `cur` with population d_waves[1].n_rays (or
+// h_n1 if known).  Returns number of waves executed; accumulates launches.
+struct WaveResult {
+    uint32_t waves = 0, launches = 0, max_queue = 0, flags = 0;
+    uint64_t secondary = 0;
+};
+
+WaveResult run_bounce_waves(rt_ctx* c, TraceArgs ta, ShadeArgs sa, int first_wave, int cur, int max_depth, bool count,
+                            bool primary_in_wave0) {
+    WaveResult r;
+    cudaStream_t st = c->stream;
+    bool poll = c->has_dielectric || max_depth > 16 || !primary_in_wave0;
+    for (int w = first_wave;; w++) {
+        int slot_in = w % RT_WAVE_SLOTS, slot_out = (w + 1) % RT_WAVE_SLOTS;
+        if (poll) {
+            RT_CUDA(cudaMemcpyAsync(&c->h_waves[slot_in], c->d_waves.p + slot_in, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+            RT_CUDA(cudaStreamSynchronize(st));
+            uint32_t n = c->h_waves[slot_in].n_rays;
+            if (n == 0) break;
+            if (n > c->queue_cap) n = (uint32_t)c->queue_cap;
+            r.secondary += n;
+            if (n > r.max_queue) r.max_queue = n;
+        } else if (w > max_depth) {
+            break;
+        }
+        if (w + 1 >= RT_WAVE_SLOTS) RT_CUDA(cudaMemsetAsync(c->d_waves.p + slot_out, 0, sizeof(WaveCounters), st));
+        ta.q = queue_of(c, cur);
+        ta.wave = c->d_waves.p + slot_in;
+        launch_trace<false>(c, ta, count);
+        sa.qin = queue_of(c, cur);
+        sa.qout = queue_of(c, cur ^ 1);
+        sa.wave = c->d_waves.p + slot_in;
+        sa.next = c->d_waves.p + slot_out;
+        launch_shade<false>(c, sa, count);
+        r.launches += 2;
+        r.waves++;
+        cur ^= 1;
+    }
+    return r;
+}
+
+}  // namespace
+
+void rt_render_init(rt_ctx* c) {
+    c->trace_blocks = persistent_blocks(k_trace<true, false>, TRACE_TPB, c->sm_count);
+    int tb2 = persistent_blocks(k_trace<false, false>, TRACE_TPB, c->sm_count);
+    if (tb2 < c->trace_blocks) c->trace_blocks = tb2;
+    c->shade_blocks = persistent_blocks(k_shade<true, false>, SHADE_TPB, c->sm_count);
+    int sb2 = persistent_blocks(k_shade<false, false>, SHADE_TPB, c->sm_count);
+    if (sb2 < c->shade_blocks) c->shade_blocks = sb2;
+    c->d_waves.reserve(RT_WAVE_SLOTS);
+    c->d_frame.reserve(1);
+    RT_CUDA(cudaMallocHost((void**)&c->h_waves, RT_WAVE_SLOTS * sizeof(WaveCounters)));
+    RT_CUDA(cudaMallocHost((void**)&c->h_frame, sizeof(FrameCounters)));
+}
+
+void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p, void* rgb_dev,
+                     const rt_aux_out* aux_dev, rt_frame_stats* stats) {
+    cudaStream_t st = c->stream;
+    setup_layout(c, cam, p);
+    FrameDev f = frame_dev(c);
+    const bool count = (p->flags & RT_FLAG_COUNT_WORK) != 0;
+    const bool bounce = c->has_reflective && p->max_depth >= 1;
+    ensure_queues(c, f.n_local_pix, bounce);
+    c->d_accum.reserve(3 * (size_t)(f.n_local_pix ? f.n_local_pix : 1));
+
+    RT_CUDA(cudaEventRecord(c->ev[0], st));
+    RT_CUDA(cudaMemsetAsync(c->d_waves.p, 0, RT_WAVE_SLOTS * sizeof(WaveCounters), st));
+    RT_CUDA(cudaMemsetAsync(c->d_frame.p, 0, sizeof(FrameCounters), st));
+    RT_CUDA(cudaMemsetAsync(c->d_accum.p, 0, 3 * (size_t)f.n_local_pix * sizeof(long long), st));
+
+    TraceArgs ta;
+    ta.s = c->scene; ta.cam = make_cam(cam); ta.f = f; ta.q = queue_of(c, 0);
+    ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p; ta.wave = c->d_waves.p; ta.accum = c->d_accum.p;
+    ta.fc = c->d_frame.p;
+    ta.aux_prim = aux_dev ? aux_dev->prim_id : nullptr;
+    ta.aux_t = aux_dev ? aux_dev->t : nullptr;
+    ta.brute = (p->flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
+    ta.cap = (uint32_t)c->queue_cap;
+    uint32_t launches = 0;
+    if (f.n_local_pix) { launch_trace<true>(c, ta, count); launches++; }
+    RT_CUDA(cudaEventRecord(c->ev[1], st));
+
+    ShadeArgs sa;
+    sa.s = c->scene; sa.cam = ta.cam; sa.f = f; sa.qin = queue_of(c, 0); sa.qout = queue_of(c, 0);
+    sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.wave = c->d_waves.p; sa.next = c->d_waves.p + 1;
+    sa.accum = c->d_accum.p; sa.fc = c->d_frame.p; sa.cap = (uint32_t)c->queue_cap;
+    sa.max_depth = p->max_depth;
+    sa.brute = ta.brute;
+    if (f.n_local_pix) { launch_shade<true>(c, sa, count); launches++; }
+    RT_CUDA(cudaEventRecord(c->ev[2], st));
+
+    WaveResult wr;
+    if (bounce && f.n_local_pix) {
+        ta.aux_prim = nullptr; ta.aux_t = nullptr;
+        wr = run_bounce_waves(c, ta, sa, 1, 0, p->max_depth, count, true);
+        launches += wr.launches;
+    }
+    RT_CUDA(cudaEventRecord(c->ev[3], st));
+
+    if (f.n_local_pix && rgb_dev) {
+        uint32_t quads = f.n_tiles_owned * (uint32_t)(f.tile_pix / 4);
+        k_resolve<<<(quads + 255) / 256, 256, 0, st>>>(f, c->d_accum.p, (uint8_t*)rgb_dev,
+                                                       (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0);
+        RT_CUDA(cudaGetLastError());
+        launches++;
+    }
+    RT_CUDA(cudaEventRecord(c->ev[6], st));
+
+    // statistics + error flags (one small D2H; also the frame's completion point)
+    RT_CUDA(cudaMemcpyAsync(c->h_waves, c->d_waves.p, RT_WAVE_SLOTS * sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaMemcpyAsync(c->h_frame, c->d_frame.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    uint32_t flags = 0;
+    for (int w = 0; w < RT_WAVE_SLOTS; w++) flags |= c->h_waves[w].flags;
+    uint64_t secondary = wr.secondary;
+    uint32_t max_queue = wr.max_queue;
+    if (bounce && !c->has_dielectric && p->max_depth <= 16) {   // blind mode: read populations now
+        for (int w = 1; w <= p->max_depth && w < RT_WAVE_SLOTS; w++) {
+            secondary += c->h_waves[w].n_rays;
+            if (c->h_waves[w].n_rays > max_queue) max_queue = c->h_waves[w].n_rays;
+        }
+    }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->rays_primary = (uint64_t)cam->width * (uint64_t)cam->height;
+        if (c->layout.world > 1) {   // in-frame pixels of the owned tiles
+            uint64_t np = 0;
+            const TileLayout& L = c->layout;
+            uint32_t total = (uint32_t)L.tiles_x * (uint32_t)L.tiles_y;
+            for (uint32_t t = (uint32_t)L.rank; t < total; t += (uint32_t)L.world) {
+                int tx = (int)(t % (uint32_t)L.tiles_x), ty = (int)(t / (uint32_t)L.tiles_x);
+                int w = L.width - tx * L.tile_w, h = L.height - ty * L.tile_h;
+                if (w > L.tile_w) w = L.tile_w;
+                if (h > L.tile_h) h = L.tile_h;
+                np += (uint64_t)w * (uint64_t)h;
+            }
+            stats->rays_primary = np;
+        }
+        stats->rays_shadow = c->h_frame->rays_shadow;
+        stats->rays_secondary = secondary;
+        stats->node_visits = c->h_frame->node_visits;
+        stats->tri_tests = c->h_frame->tri_tests;
+        stats->waves = 1 + wr.waves;
+        stats->tiles = c->layout.n_tiles_owned;
+        stats->kernel_launches = launches;
+        stats->max_queue = max_queue > c->h_waves[0].n_hits ? max_queue : c->h_waves[0].n_hits;
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_device, c->ev[0], c->ev[6]));
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_trace, c->ev[0], c->ev[1]));
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_shade, c->ev[1], c->ev[2]));
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_secondary, c->ev[2], c->ev[3]));
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_resolve, c->ev[3], c->ev[6]));
+    }
+    if (flags & 1u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow: a wave spawned more rays than the queue holds"};
+    if (flags & 2u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow (BVH deeper than RT_STACK_SIZE)"};
+}
+
+void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth, uint32_t flags, bool shade,
+                   int32_t* prim_out, float* t_out, float* rgb_out) {
+    cudaStream_t st = c->stream;
+    if (n == 0) return;
+    const bool count = false;
+    const bool bounce = shade && c->has_reflective && max_depth >= 1;
+    ensure_queues(c, n, true);
+    size_t cap = c->queue_cap;
+    c->d_accum.reserve(3 * (size_t)n);
+    c->d_aux_prim.reserve(n);
+    c->d_aux_t.reserve(n);
+    // Ray's constructor normalises the direction in FP64 (ray.h:25-29)
+    std::vector<float4> o(n), d(n), w(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const float* r = rays_host + 6 * (size_t)i;
+        double x = r[3], y = r[4], z = r[5];
+        double l = std::sqrt(x * x + y * y + z * z);
+        uint32_t pix = i;
+        float pf;
+        memcpy(&pf, &pix, 4);
+        o[i] = make_float4(r[0], r[1], r[2], pf);
+        d[i] = make_float4((float)(x / l), (float)(y / l), (float)(z / l), 0.0f);   // level 0 (bit pattern 0)
+        w[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    }
+    RT_CUDA(cudaMemcpyAsync(c->d_q[0][0].p, o.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    RT_CUDA(cudaMemcpyAsync(c->d_q[0][1].p, d.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    RT_CUDA(cudaMemcpyAsync(c->d_q[0][2].p, w.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    RT_CUDA(cudaMemsetAsync(c->d_waves.p, 0, RT_WAVE_SLOTS * sizeof(WaveCounters), st));
+    RT_CUDA(cudaMemsetAsync(c->d_frame.p, 0, sizeof(FrameCounters), st));
+    RT_CUDA(cudaMemsetAsync(c->d_accum.p, 0, 3 * (size_t)n * sizeof(long long), st));
+    WaveCounters w0;
+    memset(&w0, 0, sizeof w0);
+    w0.n_rays = n;
+    RT_CUDA(cudaMemcpyAsync(c->d_waves.p, &w0, sizeof w0, cudaMemcpyHostToDevice, st));
+
+    TraceArgs ta;
+    memset(&ta, 0, sizeof ta);
+    ta.s = c->scene; ta.q = queue_of(c, 0); ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p;
+    ta.wave = c->d_waves.p; ta.accum = c->d_accum.p; ta.fc = c->d_frame.p;
+    ta.aux_prim = c->d_aux_prim.p; ta.aux_t = c->d_aux_t.p;
+    ta.brute = (flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
+    ta.cap = (uint32_t)cap;
+    ShadeArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.s = c->scene; sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.accum = c->d_accum.p; sa.fc = c->d_frame.p;
+    sa.cap = (uint32_t)cap; sa.max_depth = max_depth; sa.brute = ta.brute;
+    if (!shade) {
+        launch_trace<false>(c, ta, count);
+    } else {
+        // wave 0 runs through the generic (queue-fed) kernels
+        launch_trace<false>(c, ta, count);
+        sa.qin = queue_of(c, 0); sa.qout = queue_of(c, 1);
+        sa.wave = c->d_waves.p; sa.next = c->d_waves.p + 1;
+        launch_shade<false>(c, sa, count);
+        if (bounce) {
+            ta.aux_prim = nullptr; ta.aux_t = nullptr;
+            run_bounce_waves(c, ta, sa, 1, 1, max_depth, count, false);
+        }
+    }
+    if (prim_out) RT_CUDA(cudaMemcpyAsync(prim_out, c->d_aux_prim.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (t_out) RT_CUDA(cudaMemcpyAsync(t_out, c->d_aux_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (shade && rgb_out) {
+        c->d_rgbf_out.reserve(3 * (size_t)n);
+        k_resolve_float<<<(3 * n + 255) / 256, 256, 0, st>>>(c->d_accum.p, 3 * n, c->d_rgbf_out.p);
+        RT_CUDA(cudaGetLastError());
+        RT_CUDA(cudaMemcpyAsync(rgb_out, c->d_rgbf_out.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    RT_CUDA(cudaMemcpyAsync(c->h_waves, c->d_waves.p, RT_WAVE_SLOTS * sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    uint32_t fl = 0;
+    for (int k = 0; k < RT_WAVE_SLOTS; k++) fl |= c->h_waves[k].flags;
+    if (fl & 1u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow in rt_shade_rays"};
+    if (fl & 2u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow"};
+}
+
+void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int width, int height, int tile_w,
+                 int tile_h, void* frame) {
+    int tiles_x = (width + tile_w - 1) / tile_w, tiles_y = (height + tile_h - 1) / tile_h;
+    uint32_t total = (uint32_t)tiles_x * (uint32_t)tiles_y;
+    uint32_t n_owned = total > (uint32_t)src_rank ? (total - (uint32_t)src_rank + (uint32_t)world - 1) / (uint32_t)world : 0u;
+    if (!n_owned) return;
+    uint32_t quads = n_owned * (uint32_t)(tile_w * tile_h / 4);
+    k_assemble<<<(quads + 255) / 256, 256, 0, c->stream>>>((const uint8_t*)packed, (uint8_t*)frame, width, height,
+                                                           tile_w, tile_h, tiles_x, total, src_rank, world);
+    RT_CUDA(cudaGetLastError());
+}

@@ -1,0 +1,158 @@
+// rt_context.h — host-side state behind an rt_ctx (internal; not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/realtrace_b200.h"
+#include "rt_bvh.h"
+#include "rt_scene.h"
+
+// ---- error plumbing ---------------------------------------------------------------------------
+struct RtError {
+    int code;
+    std::string msg;
+};
+
+#define RT_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char buf__[512];                                                                       \
+            snprintf(buf__, sizeof buf__, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,     \
+                     cudaGetErrorString(e__));                                                     \
+            throw RtError{RT_ERR_CUDA, buf__};                                                     \
+        }                                                                                          \
+    } while (0)
+
+// ---- a growable device buffer -----------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        release();
+        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            char buf[256];
+            snprintf(buf, sizeof buf, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+            throw RtError{RT_ERR_OUT_OF_MEMORY, buf};
+        }
+        cap = n;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// ---- per-wave device counters -------------------------------------------------------------------
+struct WaveCounters {
+    uint32_t n_rays;        // population of this wave (written by the previous wave's shade kernel)
+    uint32_t fetch_trace;   // persistent-thread work cursor of the trace kernel
+    uint32_t n_hits;        // hit-queue length
+    uint32_t fetch_shade;   // work cursor of the shade kernel
+    uint32_t n_next;        // rays appended for the next wave
+    uint32_t flags;         // bit0: ray-queue overflow, bit1: traversal stack overflow
+    uint32_t pad[2];
+};
+#define RT_WAVE_SLOTS 64
+
+struct FrameCounters {
+    unsigned long long rays_shadow, rays_secondary, node_visits, tri_tests;
+};
+
+// Ray queue in SoA float4 records (48 B per ray).
+struct RayQueue {
+    float4* o_pix;   // origin.xyz, as_float(local pixel index)
+    float4* d_lvl;   // direction.xyz, as_float(level)
+    float4* w;       // throughput rgb, unused
+};
+
+struct TileLayout {
+    int width = 0, height = 0, tile_w = 0, tile_h = 0, rank = 0, world = 1;
+    int tiles_x = 0, tiles_y = 0;
+    uint32_t n_tiles_owned = 0;
+    bool operator==(const TileLayout& o) const {
+        return width == o.width && height == o.height && tile_w == o.tile_w && tile_h == o.tile_h && rank == o.rank &&
+               world == o.world;
+    }
+};
+
+struct rt_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int sm_count = 148;
+
+    // ---- host staging of the scene (copied by the rt_scene_set_* calls)
+    std::vector<float> h_tri_v;            // 9 per triangle
+    std::vector<uint32_t> h_tri_mat, h_tri_obj;
+    std::vector<float> h_tri_rgb;          // 9 per triangle or empty
+    std::vector<AnalyticPrim> h_spheres, h_planes, h_cylinders;
+    std::vector<rt_material> h_materials;
+    std::vector<float> h_lights;           // 6 per light
+    float ambient[3] = {0, 0, 0}, background[3] = {0, 0, 0};
+    bool has_reflective = false, has_dielectric = false;
+    bool committed = false;
+
+    // ---- device scene
+    uint32_t n_tri = 0, n_bvh = 0, n_large = 0, n_fixed_analytic = 0;
+    DevBuf<float> d_tri_v;
+    DevBuf<uint32_t> d_tri_mat, d_tri_obj;
+    DevBuf<float4> d_tri_rgb, d_tris, d_nodes, d_box_lo, d_box_hi, d_materials, d_lights;
+    DevBuf<AnalyticPrim> d_analytic;
+    DevBuf<uint64_t> d_keys[2];
+    DevBuf<uint32_t> d_vals[2];
+    int sorted_buf = 0;                    // which of d_keys/d_vals holds the sorted result
+    DevBuf<uint32_t> d_hist, d_digit_hist, d_bounds, d_misc;
+    DevBuf<KarrasNode> d_karras;
+    DevBuf<int> d_leaf_parent, d_node_parent;
+    DevBuf<uint32_t> d_visit;
+    SceneDev scene{};
+    rt_build_stats build_stats{};
+    int leaf_size = 4;
+    float scene_abs_max = 1.0f;
+
+    // ---- render state
+    TileLayout layout;
+    DevBuf<uint32_t> d_tile_ids;
+    DevBuf<long long> d_accum;             // 3 per local pixel, 32.32 fixed point
+    DevBuf<float4> d_q[2][3];              // two ray queues x (o_pix, d_lvl, w)
+    DevBuf<float4> d_hits;                 // HitRec per ray slot
+    DevBuf<uint32_t> d_hitq;
+    size_t queue_cap = 0;
+    DevBuf<WaveCounters> d_waves;
+    DevBuf<FrameCounters> d_frame;
+    DevBuf<uint8_t> d_rgb;
+    DevBuf<int32_t> d_aux_prim;
+    DevBuf<float> d_aux_t;
+    DevBuf<float> d_rays_in;               // rt_trace_rays / rt_shade_rays staging
+    DevBuf<float> d_rgbf_out;
+    WaveCounters* h_waves = nullptr;       // pinned
+    FrameCounters* h_frame = nullptr;      // pinned
+    cudaEvent_t ev[8] = {};
+    int trace_blocks = 0, shade_blocks = 0;
+};
+
+// ---- entry points implemented across the .cu files ------------------------------------------------
+void rt_build_bvh(rt_ctx* c, bool refit_only);                      // bvh_build.cu
+void rt_sort_pairs_device(rt_ctx* c, uint32_t n, int* sort_passes); // radix_sort.cu: d_keys[0]/d_vals[0] -> sorted_buf
+void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p, void* rgb_dev,
+                     const rt_aux_out* aux_dev, rt_frame_stats* stats);   // render.cu
+void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth, uint32_t flags, bool shade,
+                   int32_t* prim_out, float* t_out, float* rgb_out);      // render.cu
+void rt_render_init(rt_ctx* c);                                     // render.cu
+void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int width, int height, int tile_w,
+                 int tile_h, void* frame);                          // render.cu

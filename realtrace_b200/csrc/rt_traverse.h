@@ -1,0 +1,141 @@
+// rt_traverse.h — nearest-hit / any-hit queries: stack-based walk of the two-child-AABB LBVH,
+// then the (few) analytic primitives linearly.
+//
+// Replaces World::firstIntersection -> UniformGrid::intersect -> Voxel::intersect
+// (/root/reference/Serial/world.cpp:5-17, uniform-grid.cpp:149-256, :9-31).  Unlike the grid walk,
+// which stops at the first voxel that reported any accepted hit (:251), this returns the true
+// nearest accepted hit; SURVEY Appendix A Q13 measures that difference (<= 0.05 % of hit pixels).
+// Any-hit mode reproduces the shadow test of world.cpp:44-51: no maximum distance, any accepted
+// hit (t > SMALLEST_DIST) along the ray counts, even beyond the light.
+#pragma once
+
+#include "rt_intersect.h"
+
+#define RT_STACK_SIZE 64
+
+struct RayPrep {
+    f3 o, d;
+    f3 idir;   // 1 / d, with |d| clamped away from 0 so that products stay finite
+    f3 ood;    // o * idir
+};
+
+RT_HD float safe_rcp(float v) {
+    const float tiny = 8.271806e-25f;   // 2^-80 (Aila & Laine's guard); keeps lo*idir - o*idir finite
+    float a = fabsf(v) > tiny ? v : copysignf(tiny, v);
+    return 1.0f / a;
+}
+
+RT_HD RayPrep prep_ray(f3 o, f3 d) {
+    RayPrep r;
+    r.o = o; r.d = d;
+    r.idir = mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+    r.ood = o * r.idir;
+    return r;
+}
+
+// Slab test of one child box against [0, tmax]; returns entry distance in tnear.
+RT_HD bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, const RayPrep& r, float tmax,
+                float& tnear) {
+    float x0 = fmaf(lox, r.idir.x, -r.ood.x), x1 = fmaf(hix, r.idir.x, -r.ood.x);
+    float y0 = fmaf(loy, r.idir.y, -r.ood.y), y1 = fmaf(hiy, r.idir.y, -r.ood.y);
+    float z0 = fmaf(loz, r.idir.z, -r.ood.z), z1 = fmaf(hiz, r.idir.z, -r.ood.z);
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    tnear = tn;
+    return tn <= tf;
+}
+
+RT_HD bool leaf_test(const SceneDev& s, int code, const RayPrep& r, HitRec& hit, bool any_hit, WorkCount* wc) {
+    uint32_t first = rt_leaf_first(code), count = rt_leaf_count(code);
+    bool found = false;
+    for (uint32_t k = 0; k < count; k++) {
+        const float4* rec = s.tris + 3 * (size_t)(first + k);
+        float4 r0 = ldg(rec), r1 = ldg(rec + 1), r2 = ldg(rec + 2);
+        if (wc) wc->tris++;
+        if (tri_test(mk3(r0), mk3(r1), mk3(r2), r.o, r.d, hit.t, hit.beta, hit.gamma) == 2) {
+            hit.prim = (int)(first + k);
+            found = true;
+            if (any_hit) return true;
+        }
+    }
+    return found;
+}
+
+// hit.t must hold the current upper bound (RT_FLT_MAX for a fresh ray), hit.prim = RT_MISS.
+template <bool ANY_HIT>
+RT_HD bool bvh_walk(const SceneDev& s, const RayPrep& r, HitRec& hit, WorkCount* wc, bool* overflow) {
+    if (s.n_bvh_tris <= 0) return false;
+    int stack[RT_STACK_SIZE];
+    int sp = 0;
+    int node = 0;
+    bool found = false;
+    for (;;) {
+        if (node >= 0) {
+            const float4* n = s.nodes + RT_NODE_FLOAT4S * (size_t)node;
+            float4 n0 = ldg(n), n1 = ldg(n + 1), n2 = ldg(n + 2), n3 = ldg(n + 3);
+            if (wc) wc->nodes++;
+            float t0, t1;
+            bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, r, hit.t, t0);
+            bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, r, hit.t, t1);
+            int c0 = (int)as_uint(n3.x), c1 = (int)as_uint(n3.y);
+            if (h0 && h1) {
+                if (t1 < t0) { int tmp = c0; c0 = c1; c1 = tmp; }
+                if (sp < RT_STACK_SIZE) stack[sp++] = c1;
+                else if (overflow) *overflow = true;
+                node = c0;
+                continue;
+            }
+            if (h0) { node = c0; continue; }
+            if (h1) { node = c1; continue; }
+        } else {
+            if (leaf_test(s, node, r, hit, ANY_HIT, wc)) {
+                found = true;
+                if (ANY_HIT) return true;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return found;
+}
+
+// Linear reference walk used by RT_FLAG_BRUTE_FORCE (and by the structure tests): every triangle.
+template <bool ANY_HIT>
+RT_HD bool brute_walk(const SceneDev& s, const RayPrep& r, HitRec& hit, WorkCount* wc) {
+    bool found = false;
+    for (int i = 0; i < s.n_bvh_tris; i++) {
+        const float4* rec = s.tris + 3 * (size_t)i;
+        float4 r0 = ldg(rec), r1 = ldg(rec + 1), r2 = ldg(rec + 2);
+        if (wc) wc->tris++;
+        if (tri_test(mk3(r0), mk3(r1), mk3(r2), r.o, r.d, hit.t, hit.beta, hit.gamma) == 2) {
+            hit.prim = i;
+            found = true;
+            if (ANY_HIT) return true;
+        }
+    }
+    return found;
+}
+
+// The full query.  Direction NaN (a failed refraction, world.cpp:83/:98) misses everything, like
+// the reference where every comparison against NaN is false.
+template <bool ANY_HIT>
+RT_HD bool trace_ray(const SceneDev& s, f3 o, f3 d, bool brute, HitRec& hit, WorkCount* wc, bool* overflow) {
+    hit.t = RT_FLT_MAX;
+    hit.prim = RT_MISS;
+    hit.beta = 0.0f;
+    hit.gamma = 0.0f;
+    if (!(d.x == d.x && d.y == d.y && d.z == d.z)) return false;
+    RayPrep r = prep_ray(o, d);
+    bool found = brute ? brute_walk<ANY_HIT>(s, r, hit, wc) : bvh_walk<ANY_HIT>(s, r, hit, wc, overflow);
+    if (ANY_HIT && found) return true;
+    for (int k = 0; k < s.n_analytic; k++) {
+        const AnalyticPrim p = s.analytic[k];
+        if (wc) wc->tris++;
+        if (analytic_test(p, o, d, hit.t, hit.beta, hit.gamma)) {
+            hit.prim = rt_analytic_code(k);
+            found = true;
+            if (ANY_HIT) return true;
+        }
+    }
+    return found;
+}

@@ -1,0 +1,274 @@
+// emul.cu — TEST-ONLY host emulation of the GPU pipeline.
+//
+// Compiled by nvcc as HOST code: it runs the very same RT_HD functions the kernels call
+// (rt_intersect.h, rt_traverse.h, rt_shade.h, rt_bvh.h) serially on the CPU, with std::stable_sort
+// standing in for the device radix sort and plain loops for the launch grids.  It exists so that
+// the logic (LBVH construction, traversal, shading, bounce bookkeeping, FP32 parity rates) can be
+// debugged on a machine without a GPU.  It is never linked into, loaded by or shipped with the
+// product library; only tests/test_emulation.py loads it.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/realtrace_b200.h"
+#include "../../oracle/oracle_abi.h"
+#include "../../realtrace_b200/csrc/rt_bvh.h"
+#include "../../realtrace_b200/csrc/rt_shade.h"
+
+namespace {
+
+struct EmulScene {
+    std::vector<float4> nodes, tris, tri_rgb, materials, lights;
+    std::vector<AnalyticPrim> analytic;
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> order;
+    SceneDev dev{};
+    uint32_t n_bvh = 0, n_large = 0;
+};
+
+f3 vtx(const float* v, uint32_t i, int k) { const float* p = v + 9 * (size_t)i + 3 * k; return mk3(p[0], p[1], p[2]); }
+
+void build(const oracle_scene* in, int leaf_size, EmulScene& S) {
+    uint32_t n = in->n_tri;
+    // analytic list: spheres, planes, cylinders (object ids default to after the triangles)
+    uint32_t next = n;
+    for (uint32_t i = 0; i < in->n_sph; i++, next++) {
+        AnalyticPrim p{}; const float* q = in->sph + 4 * (size_t)i;
+        p.kind = RT_KIND_SPHERE; p.material = in->sph_material[i]; p.object_id = in->sph_object_id ? in->sph_object_id[i] : next;
+        p.a = make_float4(q[0], q[1], q[2], q[3]); S.analytic.push_back(p);
+    }
+    for (uint32_t i = 0; i < in->n_pln; i++, next++) {
+        AnalyticPrim p{}; const float* q = in->pln + 12 * (size_t)i;
+        p.kind = RT_KIND_PLANE; p.material = in->pln_material[i]; p.object_id = in->pln_object_id ? in->pln_object_id[i] : next;
+        p.a = make_float4(q[0], q[1], q[2], 0); p.b = make_float4(q[3], q[4], q[5], 0);
+        p.c = make_float4(q[6], q[7], q[8], 0); p.d = make_float4(q[9], q[10], q[11], 0); S.analytic.push_back(p);
+    }
+    for (uint32_t i = 0; i < in->n_cyl; i++, next++) {
+        AnalyticPrim p{}; const float* q = in->cyl + 7 * (size_t)i;
+        p.kind = RT_KIND_CYLINDER; p.material = in->cyl_material[i]; p.object_id = in->cyl_object_id ? in->cyl_object_id[i] : next;
+        p.a = make_float4(q[0], q[1], q[2], q[3]); p.b = make_float4(q[4], q[5], q[6], 0); S.analytic.push_back(p);
+    }
+    for (uint32_t i = 0; i < in->n_materials; i++) {
+        const oracle_material& m = in->materials[i];
+        S.materials.push_back(make_float4(m.color[0], m.color[1], m.color[2], m.ka));
+        S.materials.push_back(make_float4(m.kd, m.ks, m.kr, m.kt));
+        S.materials.push_back(make_float4(m.eta, as_float(m.barycentric ? 1u : 0u), 0, 0));
+    }
+    for (uint32_t i = 0; i < in->n_lights; i++) {
+        const float* p = in->lights + 6 * (size_t)i;
+        S.lights.push_back(make_float4(p[0], p[1], p[2], 0)); S.lights.push_back(make_float4(p[3], p[4], p[5], 0));
+    }
+    if (in->tri_rgb)
+        for (uint32_t i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++) { const float* p = in->tri_rgb + 9 * (size_t)i + 3 * k; S.tri_rgb.push_back(make_float4(p[0], p[1], p[2], 0)); }
+
+    // k_scene_bounds
+    Aabb sb, cb;
+    sb.lo = cb.lo = mk3(RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX);
+    sb.hi = cb.hi = mk3(-RT_FLT_MAX, -RT_FLT_MAX, -RT_FLT_MAX);
+    for (uint32_t i = 0; i < n; i++) {
+        Aabb b = tri_aabb(vtx(in->tri_v, i, 0), vtx(in->tri_v, i, 1), vtx(in->tri_v, i, 2));
+        sb = aabb_union(sb, b);
+        f3 c = (b.lo + b.hi) * 0.5f;
+        Aabb cc; cc.lo = c; cc.hi = c;
+        cb = aabb_union(cb, cc);
+    }
+    float amax = 0;
+    for (float v : {sb.lo.x, sb.lo.y, sb.lo.z, sb.hi.x, sb.hi.y, sb.hi.z}) amax = fmaxf(amax, fabsf(v));
+    float pad_abs = amax * 4.0e-6f;
+    // k_morton (+ oversized-triangle classification)
+    float large_frac = n >= 64 ? 0.25f : RT_FLT_MAX;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        S.keys.assign(n, 0); S.order.resize(n); S.n_large = 0;
+        float scene_ext = fmaxf(sb.hi.x - sb.lo.x, fmaxf(sb.hi.y - sb.lo.y, sb.hi.z - sb.lo.z));
+        f3 ext = cb.hi - cb.lo;
+        f3 inv = mk3(ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f, ext.z > 0 ? 1.0f / ext.z : 0.0f);
+        for (uint32_t i = 0; i < n; i++) {
+            Aabb b = tri_aabb(vtx(in->tri_v, i, 0), vtx(in->tri_v, i, 1), vtx(in->tri_v, i, 2));
+            float te = fmaxf(b.hi.x - b.lo.x, fmaxf(b.hi.y - b.lo.y, b.hi.z - b.lo.z));
+            if (te > large_frac * scene_ext) { S.keys[i] = ~0ull; S.n_large++; }
+            else S.keys[i] = morton63((b.lo + b.hi) * 0.5f, cb.lo, inv);
+            S.order[i] = i;
+        }
+        if (S.n_large <= 16) break;
+        large_frac = RT_FLT_MAX;
+    }
+    // sort (stable, by key)
+    std::stable_sort(S.order.begin(), S.order.end(), [&](uint32_t a, uint32_t b) { return S.keys[a] < S.keys[b]; });
+    std::vector<uint64_t> sk(n);
+    for (uint32_t k = 0; k < n; k++) sk[k] = S.keys[S.order[k]];
+    S.keys.swap(sk);
+    uint32_t nb = S.n_bvh = n - S.n_large;
+    // k_tri_records
+    S.tris.resize(3 * (size_t)n);
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t i = S.order[k];
+        f3 a = vtx(in->tri_v, i, 0), b = vtx(in->tri_v, i, 1), c = vtx(in->tri_v, i, 2);
+        f3 e1 = a - b, e2 = a - c;
+        uint32_t obj = in->tri_object_id ? in->tri_object_id[i] : i;
+        S.tris[3 * k] = make_float4(a.x, a.y, a.z, as_float(obj));
+        S.tris[3 * k + 1] = make_float4(e1.x, e1.y, e1.z, as_float(in->tri_material[i]));
+        S.tris[3 * k + 2] = make_float4(e2.x, e2.y, e2.z, as_float(i));
+    }
+    for (uint32_t k = 0; k < S.n_large; k++) {   // k_emit_large
+        AnalyticPrim p{};
+        const float4* r = &S.tris[3 * (size_t)(nb + k)];
+        p.kind = RT_KIND_TRIANGLE; p.object_id = as_uint(r[0].w); p.material = as_uint(r[1].w); p.tri_index = as_uint(r[2].w);
+        p.a = r[0]; p.b = r[1]; p.c = r[2];
+        S.analytic.push_back(p);
+    }
+    auto padded = [&](Aabb b) { Aabb r = aabb_pad(b); r.lo = r.lo - mk3(pad_abs, pad_abs, pad_abs); r.hi = r.hi + mk3(pad_abs, pad_abs, pad_abs); return r; };
+    if (nb >= 2) {
+        std::vector<KarrasNode> kn(nb - 1);
+        std::vector<int> leaf_parent(nb), node_parent(nb - 1, -1);
+        for (int i = 0; i < (int)nb - 1; i++) {
+            kn[i] = karras_node(S.keys.data(), (int)nb, i);
+            if (kn[i].left < 0) leaf_parent[~kn[i].left] = i; else node_parent[kn[i].left] = i;
+            if (kn[i].right < 0) leaf_parent[~kn[i].right] = i; else node_parent[kn[i].right] = i;
+        }
+        node_parent[0] = -1;
+        std::vector<Aabb> box(2 * (size_t)nb - 1);
+        std::vector<int> visit(nb - 1, 0);
+        S.nodes.assign(4 * (size_t)(nb - 1), make_float4(0, 0, 0, 0));
+        auto code = [&](int child) {
+            if (child < 0) return rt_leaf_code((uint32_t)~child, 1u);
+            int cnt = kn[child].last - kn[child].first + 1;
+            return cnt <= leaf_size ? rt_leaf_code((uint32_t)kn[child].first, (uint32_t)cnt) : child;
+        };
+        for (uint32_t k = 0; k < nb; k++) {
+            uint32_t i = S.order[k];
+            box[(nb - 1) + k] = tri_aabb(vtx(in->tri_v, i, 0), vtx(in->tri_v, i, 1), vtx(in->tri_v, i, 2));
+            int cur = leaf_parent[k];
+            while (cur >= 0) {
+                if (visit[cur]++ == 0) break;
+                const KarrasNode& nd = kn[cur];
+                Aabb L = box[nd.left < 0 ? (nb - 1) + ~nd.left : nd.left], R = box[nd.right < 0 ? (nb - 1) + ~nd.right : nd.right];
+                box[cur] = aabb_union(L, R);
+                Aabb Lp = padded(L), Rp = padded(R);
+                float4* o = &S.nodes[4 * (size_t)cur];
+                o[0] = make_float4(Lp.lo.x, Lp.hi.x, Lp.lo.y, Lp.hi.y);
+                o[1] = make_float4(Rp.lo.x, Rp.hi.x, Rp.lo.y, Rp.hi.y);
+                o[2] = make_float4(Lp.lo.z, Lp.hi.z, Rp.lo.z, Rp.hi.z);
+                o[3] = make_float4(as_float((uint32_t)code(nd.left)), as_float((uint32_t)code(nd.right)), as_float((uint32_t)nd.first), as_float((uint32_t)nd.last));
+                cur = node_parent[cur];
+            }
+        }
+    } else if (nb == 1) {
+        uint32_t i = S.order[0];
+        Aabb p = padded(tri_aabb(vtx(in->tri_v, i, 0), vtx(in->tri_v, i, 1), vtx(in->tri_v, i, 2)));
+        S.nodes = {make_float4(p.lo.x, p.hi.x, p.lo.y, p.hi.y), make_float4(RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX),
+                   make_float4(p.lo.z, p.hi.z, RT_FLT_MAX, RT_FLT_MAX),
+                   make_float4(as_float((uint32_t)rt_leaf_code(0, 1)), as_float((uint32_t)RT_EMPTY_CODE), 0, 0)};
+    }
+    SceneDev& d = S.dev;
+    d.nodes = S.nodes.data(); d.tris = S.tris.data(); d.tri_rgb = S.tri_rgb.empty() ? nullptr : S.tri_rgb.data();
+    d.analytic = S.analytic.data(); d.materials = S.materials.data(); d.lights = S.lights.data();
+    d.n_bvh_tris = (int)nb; d.n_nodes = nb >= 2 ? (int)nb - 1 : (int)nb; d.n_analytic = (int)S.analytic.size();
+    d.n_lights = (int)in->n_lights;
+    for (int k = 0; k < 3; k++) { d.ambient[k] = in->ambient[k]; d.background[k] = in->background[k]; }
+}
+
+struct Pending { f3 o, d, w; int level; };
+
+long long to_fixed(float x) {
+    if (!(x == x)) x = 0.0f;
+    x = fminf(fmaxf(x, -1048576.0f), 1048576.0f);
+    return llrintf(x * 4294967296.0f);
+}
+
+}  // namespace
+
+extern "C" int emul_render(const oracle_scene* in, const rt_camera* cam, int max_depth, int leaf_size, int brute,
+                           uint8_t* rgb, int32_t* prim_id, float* t_hit, uint64_t* counts /*primary, shadow, secondary, nodes, tris*/) {
+    EmulScene S;
+    build(in, leaf_size, S);
+    const SceneDev& s = S.dev;
+    const int W = cam->width, H = cam->height;
+    uint64_t n_shadow = 0, n_secondary = 0;
+    WorkCount wc{0, 0};
+    uint64_t nodes = 0, tris = 0;
+    bool overflow = false;
+    f3 bg = mk3(s.background[0], s.background[1], s.background[2]);
+    std::vector<Pending> stack;
+    for (int j = 0; j < H; j++)
+        for (int i = 0; i < W; i++) {
+            // primary_ray of render.cu
+            float xw = (float)((double)cam->aspect * (i - W / 2.0 + 0.5) / W), yw = (float)((j - H / 2.0 + 0.5) / H);
+            double dd[3];
+            for (int k = 0; k < 3; k++) dd[k] = -(double)cam->w[k] * (double)cam->focal_distance + (double)cam->u[k] * (double)xw + (double)cam->v[k] * (double)yw;
+            double l = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+            for (int k = 0; k < 3; k++) dd[k] /= l;
+            l = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+            Pending r0;
+            r0.d = mk3((float)(dd[0] / l), (float)(dd[1] / l), (float)(dd[2] / l));
+            r0.o = mk3(cam->pos[0], cam->pos[1], cam->pos[2]);
+            r0.w = mk3(1, 1, 1); r0.level = 0;
+            long long acc[3] = {0, 0, 0};
+            stack.clear();
+            stack.push_back(r0);
+            bool first = true;
+            while (!stack.empty()) {
+                Pending r = stack.back();
+                stack.pop_back();
+                if (!first) n_secondary++;
+                HitRec h;
+                wc.nodes = wc.tris = 0;
+                bool found = trace_ray<false>(s, r.o, r.d, brute != 0, h, &wc, &overflow);
+                nodes += wc.nodes; tris += wc.tris;
+                if (first) {
+                    size_t at = (size_t)i + (size_t)j * W;
+                    if (prim_id) prim_id[at] = !found ? -1 : (h.prim >= 0 ? (int)as_uint(s.tris[3 * (size_t)h.prim].w) : (int)s.analytic[rt_analytic_index(h.prim)].object_id);
+                    if (t_hit) t_hit[at] = found ? h.t : RT_FLT_MAX;
+                    first = false;
+                }
+                f3 add;
+                if (!found) add = r.w * bg;
+                else {
+                    ShadeOut out;
+                    auto any_hit = [&](f3 so, f3 sd) { HitRec sh; wc.nodes = wc.tris = 0; bool f = trace_ray<true>(s, so, sd, brute != 0, sh, &wc, &overflow); nodes += wc.nodes; tris += wc.tris; return f; };
+                    shade_hit(s, r.o, r.d, r.level, h, max_depth, any_hit, out);
+                    n_shadow += out.shadow_rays;
+                    add = r.w * (out.local + out.bg_weight * bg);
+                    for (int c = 0; c < out.n_children; c++) stack.push_back({out.child[c].o, out.child[c].d, r.w * out.child[c].w, out.child[c].level});
+                }
+                acc[0] += to_fixed(add.x); acc[1] += to_fixed(add.y); acc[2] += to_fixed(add.z);
+            }
+            for (int k = 0; k < 3; k++) {
+                double c = (double)acc[k] * (1.0 / 4294967296.0);
+                if (c > 1.0) c = 1.0;
+                if (c < 0.0) c = 0.0;
+                rgb[((size_t)i + (size_t)j * W) * 3 + k] = (uint8_t)(255.0 * c);
+            }
+        }
+    if (counts) { counts[0] = (uint64_t)W * H; counts[1] = n_shadow; counts[2] = n_secondary; counts[3] = nodes; counts[4] = tris; }
+    return overflow ? -5 : 0;
+}
+
+extern "C" int emul_trace_rays(const oracle_scene* in, int leaf_size, int brute, const float* rays, uint32_t n, int32_t* prim_id, float* t_hit) {
+    EmulScene S;
+    build(in, leaf_size, S);
+    const SceneDev& s = S.dev;
+    bool overflow = false;
+    for (uint32_t r = 0; r < n; r++) {
+        const float* p = rays + 6 * (size_t)r;
+        double x = p[3], y = p[4], z = p[5], l = std::sqrt(x * x + y * y + z * z);
+        HitRec h;
+        bool found = trace_ray<false>(s, mk3(p[0], p[1], p[2]), mk3((float)(x / l), (float)(y / l), (float)(z / l)), brute != 0, h, nullptr, &overflow);
+        prim_id[r] = !found ? -1 : (h.prim >= 0 ? (int)as_uint(s.tris[3 * (size_t)h.prim].w) : (int)s.analytic[rt_analytic_index(h.prim)].object_id);
+        t_hit[r] = found ? h.t : RT_FLT_MAX;
+    }
+    return overflow ? -5 : 0;
+}
+
+// BVH introspection for structure checks: returns node count; copies nodes (16 floats each) and order.
+extern "C" int emul_bvh(const oracle_scene* in, int leaf_size, float* nodes, uint32_t* order, uint64_t* keys, uint32_t* n_bvh) {
+    EmulScene S;
+    build(in, leaf_size, S);
+    if (nodes) memcpy(nodes, S.nodes.data(), S.nodes.size() * sizeof(float4));
+    if (order) memcpy(order, S.order.data(), S.n_bvh * sizeof(uint32_t));
+    if (keys) memcpy(keys, S.keys.data(), S.n_bvh * sizeof(uint64_t));
+    if (n_bvh) *n_bvh = S.n_bvh;
+    return (int)(S.nodes.size() / 4);
+}

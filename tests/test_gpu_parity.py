@@ -1,0 +1,210 @@
+"""The parity tests proper: the CUDA path, called through the C ABI, against the golden fixtures
+generated from the reference's own Serial sources and against the CPU oracle on fresh inputs.
+
+Bars (tests/parity.py, from BASELINE.json): first-hit primitive id equal on >= 99.9 % of pixels,
+8-bit colour within +-1 LSB on >= 99.9 % of pixels, FP32 hit distance within 1e-4 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import kat
+import parity
+from bvh_checks import check_bvh
+from cases import GOLDEN_CASES, build_case
+from conftest import GOLDEN
+from oracle import binding as ob
+from realtrace_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    import __graft_entry__ as entry
+    entry.build_oracle()
+    return ob.load_port()
+
+
+def make_ctx(scene):
+    ctx = api.Context(0)
+    ctx.set_scene(scene)
+    ctx.commit()
+    return ctx
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_frames_match_golden_and_true_nearest(oracle, name):
+    scene, cam, depth, mode = build_case(name)
+    ctx = make_ctx(scene)
+    rgb, prim, t, st = ctx.render(cam, depth, aux=True)
+    ctx.close()
+    tr = oracle.render(scene, cam, depth, ob.MODE_TRUE_NEAREST)
+    parity.assert_parity(parity.compare(rgb, prim, t, tr[0], tr[1], tr[2]), name + " vs true-nearest oracle")
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m = parity.compare(rgb, prim, t, g["rgb"], g["prim_id"], g["t"])
+    if name == "analytic_close_d5":
+        # camera inside the triangle grid: the shipped grid walk returns non-nearest hits for a patch of
+        # reflections (uniform-grid.cpp:190-251); ids still agree everywhere
+        assert m["id_match"] == 1.0 and m["colour_within_1"] >= 0.998, m
+    else:
+        parity.assert_parity(m, name + " vs golden (reference build, as shipped)")
+    assert st["rays_primary"] == cam.width * cam.height
+
+
+def test_kat_rays_through_the_abi():
+    g = np.load(os.path.join(GOLDEN, "kat_rays.npz"))
+    names, rays = kat.kat_rays()
+    ctx = make_ctx(kat.kat_scene())
+    prim, t = ctx.trace_rays(rays)
+    assert np.array_equal(prim, g["prim_true_nearest"]), list(zip(names, prim, g["prim_true_nearest"]))
+    hit = prim >= 0
+    assert np.allclose(t[hit], g["t_true_nearest"][hit], rtol=1e-5)
+    assert np.all(t[~hit] == np.finfo(np.float32).max)
+    shade = ctx.shade_rays(rays, 3)
+    assert np.allclose(shade, g["shade_true_nearest"], rtol=2e-4, atol=2e-4)
+    ctx.close()
+
+
+def test_random_rays_bvh_vs_brute_force_vs_oracle(oracle):
+    scene = scenes.obj_scene("blub_triangulated.obj")
+    ctx = make_ctx(scene)
+    rng = np.random.default_rng(3)
+    n = 20000
+    o = rng.uniform(-40, 40, (n, 3))
+    target = rng.uniform(-8, 8, (n, 3))
+    rays = np.concatenate([o, target - o], axis=1).astype(np.float32)
+    prim, t = ctx.trace_rays(rays)
+    prim_b, t_b = ctx.trace_rays(rays, flags=api.FLAG_BRUTE_FORCE)
+    ctx.close()
+    assert np.array_equal(prim, prim_b) and np.array_equal(t, t_b)      # same FP32 tests, different walk
+    ref_prim, ref_t = oracle.trace_rays(scene, rays[:4000], ob.MODE_TRUE_NEAREST)
+    same = prim[:4000] == ref_prim
+    assert same.mean() >= 0.999
+    both = same & (ref_prim >= 0)
+    assert both.sum() > 500
+    assert np.max(np.abs(t[:4000][both] - ref_t[both]) / ref_t[both]) <= 1e-4
+
+
+@pytest.mark.parametrize("name,leaf", [("bobtex_d3", 4), ("blubmixed_d5", 4), ("synth_small_d1", 4), ("tetra_d10", 4)])
+def test_bvh_structure(name, leaf):
+    scene, _, _, _ = build_case(name)
+    ctx = make_ctx(scene)
+    nodes, order, keys = ctx.bvh_download()
+    bs = ctx.build_stats()
+    ctx.close()
+    assert bs["n_triangles"] == len(order)
+    info = check_bvh(nodes, order, keys, scene.tri_v, leaf)
+    assert info["depth"] <= 64
+
+
+def test_bvh_equals_the_emulated_build():
+    """Device radix sort + Karras + refit produce exactly the tree the serial emulation builds."""
+    import emul_binding
+    scene, _, _, _ = build_case("blubmixed_d5")
+    ctx = make_ctx(scene)
+    nodes, order, keys = ctx.bvh_download()
+    ctx.close()
+    e_nodes, e_order, e_keys = emul_binding.Emulation().bvh(scene, 4)
+    assert np.array_equal(order, e_order)
+    assert np.array_equal(keys, e_keys)
+    assert np.array_equal(nodes.view(np.uint32), e_nodes.view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 4096, 4097, 100000, 1 << 20])
+def test_device_radix_sort(n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 63, n, dtype=np.uint64)
+    if n > 100:
+        keys[::7] = keys[3]          # duplicates: stability matters
+        keys[n // 2:] &= np.uint64(0xFFFFFFFF)
+    vals = np.arange(n, dtype=np.uint32)
+    ctx = api.Context(0)
+    k, v = ctx.sort_pairs(keys, vals)
+    ctx.close()
+    ref = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[ref])
+    assert np.array_equal(v, vals[ref])
+
+
+def test_refit_is_idempotent_and_tracks_vertices(oracle):
+    scene, cam, depth, _ = build_case("bobtex_d3")
+    ctx = make_ctx(scene)
+    base = ctx.render(cam, depth, aux=True)
+    nodes0, order0, _ = ctx.bvh_download()
+    ctx.commit(api.COMMIT_REFIT)
+    nodes1, order1, _ = ctx.bvh_download()
+    assert np.array_equal(nodes0.view(np.uint32), nodes1.view(np.uint32)) and np.array_equal(order0, order1)
+    again = ctx.render(cam, depth, aux=True)
+    assert np.array_equal(base[0], again[0]) and np.array_equal(base[1], again[1])
+    # move the model: refit must follow (same topology), and match a fresh build of the moved scene
+    moved = scene.tri_v.copy()
+    moved[:, 1::3] += 1.5
+    ctx.update_vertices(moved)
+    ctx.commit(api.COMMIT_REFIT)
+    r = ctx.render(cam, depth, aux=True)
+    ctx.close()
+    scene2, _, _, _ = build_case("bobtex_d3")
+    scene2.tri_v = moved
+    tr = oracle.render(scene2, cam, depth, ob.MODE_TRUE_NEAREST)
+    parity.assert_parity(parity.compare(r[0], r[1], r[2], tr[0], tr[1], tr[2]), "refit after translation")
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_tile_sharding_is_bit_identical(world):
+    """N logical ranks on one GPU: every rank renders its interleaved tiles; assembling the packed
+    tiles reproduces the single-rank frame bit for bit."""
+    import torch
+    scene, cam, depth, _ = build_case("blubmixed_d5")
+    cam.width, cam.height = 200, 150          # not a multiple of the tile: ragged edge tiles
+    ctx = make_ctx(scene)
+    full, _, _, st_full = ctx.render(cam, depth)
+    frame = torch.zeros(cam.height * cam.width * 3, dtype=torch.uint8, device="cuda")
+    rays = 0
+    for r in range(world):
+        _, owned, tb = api.tile_layout(cam.width, cam.height, 0, 0, r, world)
+        packed = torch.zeros(max(owned * tb, 1), dtype=torch.uint8, device="cuda")
+        st = ctx.render_device(cam, depth, packed.data_ptr(), rank=r, world=world, flags=api.FLAG_PACKED_TILES)
+        rays += st["rays_primary"]
+        ctx.assemble_tiles(packed.data_ptr(), r, world, cam.width, cam.height, frame.data_ptr())
+    torch.cuda.synchronize()
+    ctx.close()
+    assert rays == cam.width * cam.height
+    out = frame.cpu().numpy().reshape(cam.height, cam.width, 3)
+    assert np.array_equal(out, full)
+
+
+def test_full_size_property_checks():
+    """Config-2 size (1920x1080, 2 lights, depth 3): size-independent properties — every ray kind is
+    counted, rendering twice is bit-identical, brute force over the same rays gives the same frame on
+    the hit region, background pixels carry exactly the background colour."""
+    scene, cam, depth, _ = scenes.workload("bob1080")
+    ctx = make_ctx(scene)
+    a = ctx.render(cam, depth, aux=True)
+    b = ctx.render(cam, depth, aux=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    st = a[3]
+    hits = int((a[1] >= 0).sum())
+    assert st["rays_primary"] == 1920 * 1080
+    assert st["rays_shadow"] >= 2 * hits              # two lights per shaded hit, bounces add more
+    assert 0 < st["rays_secondary"] <= 3 * hits
+    miss = a[1] < 0
+    assert np.all(a[0][miss] == np.array([25, 76, 153], np.uint8))
+    small = scenes.stock_camera(480, 270)
+    c = ctx.render(small, depth, aux=True)
+    d = ctx.render(small, depth, aux=True, flags=api.FLAG_BRUTE_FORCE)
+    ctx.close()
+    assert np.array_equal(c[0], d[0]) and np.array_equal(c[1], d[1])
+
+
+def test_errors_are_reported_not_swallowed():
+    ctx = api.Context(0)
+    with pytest.raises(api.RtError) as e:
+        ctx.render(scenes.stock_camera(64, 48), 1)
+    assert e.value.code == -4
+    scene, cam, depth, _ = build_case("tetra_d10")
+    ctx.set_scene(scene)
+    ctx.commit()
+    with pytest.raises(api.RtError):
+        ctx.render(cam, depth, tile=(30, 30))
+    ctx.close()
