@@ -1,0 +1,372 @@
+#!/usr/bin/env python3
+"""bench.py — the hot path of realtrace_b200 measured on B200 (contract: see DESIGN.md §7).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload synth1m|bob1080|blub4k|analytic]
+  python bench.py --impl reference ...      # the reference's own CPU renderer, same metric/config
+
+One step = one frame of the workload.  Default workload: BASELINE.json configs[3], the synthetic
+1 003 522-triangle sphere grid at 3840x2160, primary + shadow rays — the configuration the north
+star quotes its throughput and scaling targets on; it fits one GPU.  configs[1] (bob 1080p) is
+measured in the same run and reported under "other_workloads".
+
+Metric: Mrays/s, one ray = one World::firstIntersection call of the reference (nearest-hit or
+any-hit query): primary + shadow + secondary.
+  value   frames rendered into a device buffer (scene + BVH resident in HBM, rt_render_device)
+  e2e     the same through rt_render with HOST buffers: camera in, RGB8 frame copied to pinned host
+          memory inside the timed region
+N > 1 (torchrun, one process per GPU): the frame is cut into interleaved 64x32 screen tiles, every
+rank renders its share with the scene replicated, NCCL gathers the packed tiles on rank 0, which
+scatters them into the frame; "scaling": "strong" (fixed total work).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/s (primary+shadow+secondary)"
+FMA_LANES_PER_CLK = 148 * 128          # FP32 lanes x SMs
+L2_FLUSH_BYTES = 512 << 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def total_rays(st):
+    return st["rays_primary"] + st["rays_shadow"] + st["rays_secondary"]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own Serial renderer (oracle/_ref) or, where it was not built, the port.
+def cpu_render_sample(scene, cam, depth, budget_s, threads):
+    from oracle import binding as ob
+    import __graft_entry__ as entry
+    entry.build_oracle()
+    orc = ob.best_available()
+    W = cam.width
+    # calibrate on a thin column sample, then size the real sample for ~budget_s of work
+    step0 = max(1, W // 8)
+    t0 = time.time()
+    _, _, _, info = orc.render(scene, cam, depth, ob.MODE_AS_SHIPPED, col_begin=step0 // 2, col_step=step0,
+                               nthreads=threads, aux=False)
+    per_col = max(info["render_seconds"], 1e-4) / max(info["columns_rendered"], 1)
+    build_s = info["build_seconds"]
+    cols = int(min(W, max(8, budget_s / per_col)))
+    col_step = max(1, W // cols)
+    return orc, col_step, build_s
+
+
+def cpu_step(orc, scene, cam, depth, col_step, threads):
+    from oracle import binding as ob
+    _, _, _, info = orc.render(scene, cam, depth, ob.MODE_AS_SHIPPED, col_begin=col_step // 2, col_step=col_step,
+                               nthreads=threads, aux=False)
+    return info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from realtrace_b200 import scenes
+    scene, cam, depth, desc = scenes.workload(args.workload)
+    threads = os.cpu_count() or 1
+    per_step_budget = max(2.0, 60.0 / max(args.steps + args.warmup, 1))
+    orc, col_step, build_s = cpu_render_sample(scene, cam, depth, per_step_budget, threads)
+    for _ in range(args.warmup):
+        cpu_step(orc, scene, cam, depth, col_step, threads)
+    rays, secs = 0, 0.0
+    for _ in range(args.steps):
+        info = cpu_step(orc, scene, cam, depth, col_step, threads)
+        rays += info["rays_total"]
+        secs += info["render_seconds"]
+    value = rays / secs / 1e6
+    cols = info["columns_rendered"]
+    sample = (f"every {col_step}th column of the {cam.width}x{cam.height} frame ({cols} columns, "
+              f"{info['rays_total']} rays per step), grid as shipped; scene+grid build {build_s:.2f}s excluded")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "width": cam.width, "height": cam.height,
+                       "max_depth": depth, "triangles": int(len(scene.tri_v))},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": orc.kind, "sample": sample},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
+    import torch
+    from realtrace_b200 import api, scenes
+
+    rank, world = dist_ctx["rank"], dist_ctx["world"]
+    dev = torch.device("cuda", dist_ctx["local_rank"])
+    torch.cuda.set_device(dev)
+    scene, cam, depth, desc = scenes.workload(workload)
+    W, H = cam.width, cam.height
+
+    ctx = api.Context(dist_ctx["local_rank"])
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    t0 = time.time()
+    ctx.set_scene(scene)
+    bstats = ctx.commit()
+    commit_s = time.time() - t0
+
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    _, owned, tile_bytes = api.tile_layout(W, H, 0, 0, rank, world)
+    max_owned = max(api.tile_layout(W, H, 0, 0, r, world)[1] for r in range(world))
+    frame = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
+    packed = torch.zeros(max_owned * tile_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
+    gathered = None
+    if world > 1 and rank == 0:
+        gathered = [torch.zeros(max_owned * tile_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        """One frame with everything resident: render (+ gather + assemble at N > 1)."""
+        if world == 1:
+            return ctx.render_device(cam, depth, frame.data_ptr())
+        st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES)
+        torch.distributed.gather(packed, gathered, dst=0)
+        if rank == 0:
+            for r in range(world):
+                ctx.assemble_tiles(gathered[r].data_ptr(), r, world, W, H, frame.data_ptr())
+        return st
+
+    # ---- value: device-resident frames, CUDA events around every step, L2 flushed between steps
+    for _ in range(warmup):
+        st = step_device()
+    barrier()
+    sampler = ClockSampler(dist_ctx["local_rank"])
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    stats = []
+    for k in range(steps):
+        flush.fill_(k & 0xff)
+        evs[k][0].record(stream)
+        stats.append(step_device())
+        evs[k][1].record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    rays_local = sum(total_rays(s) for s in stats)
+    launches = sum(s["kernel_launches"] for s in stats) + (world if (world > 1 and rank == 0) else 0) * steps
+    if world > 1:
+        t = torch.tensor([ms, float(rays_local), float(launches)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+        ms, rays_total, launches = float(tmax[0]), float(t[1]), int(t[2])
+    else:
+        rays_total = float(rays_local)
+    value = rays_total / (ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers through rt_render (N = 1) / render + gather + D2H of the frame (N > 1)
+    host_frame = torch.empty(H * W * 3, dtype=torch.uint8, pin_memory=True)
+    host_np = host_frame.numpy().reshape(H, W, 3)
+
+    def step_e2e():
+        if world == 1:
+            return ctx.render(cam, depth, out=host_np)[3]
+        st = step_device()
+        if rank == 0:
+            host_frame.copy_(frame, non_blocking=True)
+            torch.cuda.synchronize()
+        return st
+
+    for _ in range(max(1, warmup // 2)):
+        step_e2e()
+    barrier()
+    e2e_steps = max(3, steps // 2)
+    t0 = time.perf_counter()
+    e_rays = 0
+    for _ in range(e2e_steps):
+        e_rays += total_rays(step_e2e())
+    barrier()
+    e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e_s, float(e_rays)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+        e_s, e_rays = float(tmax[0]), float(t[1])
+    e2e_value = e_rays / e_s / 1e6
+
+    out = {"value": value, "ms_per_step": ms / steps, "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
+           "launches": launches, "clocks": sampler.summary(), "desc": desc, "cam": cam, "depth": depth,
+           "scene": scene, "build": bstats, "commit_s": commit_s, "last": stats[-1], "rays_per_frame": rays_total / steps}
+
+    # ---- roofline of the dominant kernel + work counts (single GPU, rank 0)
+    if world == 1:
+        cnt = ctx.render_device(cam, depth, frame.data_ptr(), flags=api.FLAG_COUNT_WORK)
+        n_rays = total_rays(cnt)
+        ms_k = {"k_traverse<primary> (nearest hit)": np.mean([s["ms_trace"] for s in stats]),
+                "k_traverse<shadow> (any hit)": np.mean([s["ms_shadow"] for s in stats]),
+                "k_shade<primary>": np.mean([s["ms_shade"] for s in stats]),
+                "bounce waves (k_traverse + k_shade)": np.mean([s["ms_secondary"] for s in stats]),
+                "k_resolve": np.mean([s["ms_resolve"] for s in stats])}
+        out["kernel_ms"] = {k: float(v) for k, v in ms_k.items()}
+        out["work"] = {"node_visits_per_ray": cnt["node_visits"] / n_rays, "tri_tests_per_ray": cnt["tri_tests"] / n_rays,
+                       "node_visits": cnt["node_visits"], "tri_tests": cnt["tri_tests"], "rays": n_rays}
+        # cold e2e: scene upload + LBVH build + one frame to the host
+        t0 = time.perf_counter()
+        ctx.set_scene(scene)
+        ctx.commit()
+        st = ctx.render(cam, depth, out=host_np)[3]
+        out["e2e_cold_ms"] = (time.perf_counter() - t0) * 1e3
+    ctx.close()
+    del flush
+    return out
+
+
+def run_gpu_arm(args):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist_ctx = {"rank": rank, "world": world, "local_rank": local_rank}
+    hbm_gbs, peak_src, sm_max_mhz = peaks()
+
+    main = measure_gpu(args, args.workload, args.steps, args.warmup, dist_ctx, True)
+    cam, scene, depth = main["cam"], main["scene"], main["depth"]
+
+    line = {"metric": METRIC, "value": main["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": main["desc"], "width": cam.width, "height": cam.height,
+                       "max_depth": depth, "triangles": int(len(scene.tri_v)), "lights": int(len(scene.lights)),
+                       "rays_per_frame": main["rays_per_frame"],
+                       "parallelism": f"{world} GPU(s), interleaved 64x32 tiles, scene replicated, NCCL gather",
+                       "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"},
+            "e2e": {"value": main["e2e_value"], "unit": "Mrays/s", "ms_per_step": main["e2e_ms_per_step"],
+                    "h2d_bytes_per_step": 64 + 24, "d2h_bytes_per_step": cam.width * cam.height * 3,
+                    "what": "rt_render: camera + params in, RGB8 frame into pinned host memory (scene resident)"},
+            "gpu_launches": main["launches"], "clocks": main["clocks"],
+            "build": {"commit_s": main["commit_s"], **main["build"]}}
+
+    if world == 1:
+        work = main["work"]
+        kms = main["kernel_ms"]
+        dom = max(kms, key=kms.get)
+        # algorithmic bytes / FMA lane-instructions per ray: SURVEY §8(d)
+        bytes_per_ray = 64.0 * work["node_visits_per_ray"] + 48.0 * work["tri_tests_per_ray"] + 84.0
+        fma_per_ray = 12.0 * work["node_visits_per_ray"] + 30.0 * work["tri_tests_per_ray"] + 60.0
+        frame_ms = sum(kms.values())
+        achieved = bytes_per_ray * work["rays"] / (frame_ms * 1e-3) / 1e9
+        sm_mhz = main["clocks"].get("sm_mhz") or sm_max_mhz
+        fma_peak = FMA_LANES_PER_CLK * sm_max_mhz * 1e6
+        fma_ach = fma_per_ray * work["rays"] / (frame_ms * 1e-3)
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
+                            "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                            "kernel": "k_trace + k_shade (all traversal kernels of the frame)",
+                            "dominant_kernel": dom, "kernel_ms": kms,
+                            "algorithmic_bytes_per_ray": bytes_per_ray,
+                            "node_visits_per_ray": work["node_visits_per_ray"],
+                            "tri_tests_per_ray": work["tri_tests_per_ray"],
+                            "fma": {"achieved_lane_instr_per_s": fma_ach, "peak_lane_instr_per_s": fma_peak,
+                                    "frac": fma_ach / fma_peak, "lane_instr_per_ray": fma_per_ray,
+                                    "sm_mhz_under_load": sm_mhz},
+                            "note": "node/triangle fetches are served mostly by L1/L2 (scene 112 MB ~ L2 size); "
+                                    "the HBM figure is the contract's denominator, see DESIGN.md §6"}
+        line["e2e"]["cold_ms_incl_scene_upload_and_bvh_build"] = main["e2e_cold_ms"]
+        # the reference's CPU renderer on a bounded sample of the same workload, 1 core
+        if not args.no_cpu:
+            orc, col_step, build_s = cpu_render_sample(scene, cam, depth, 12.0, 1)
+            info = cpu_step(orc, scene, cam, depth, col_step, 1)
+            line["cpu_baseline"] = {"value": info["rays_total"] / info["render_seconds"] / 1e6, "unit": "Mrays/s",
+                                    "cores": 1, "kind": orc.kind,
+                                    "sample": f"every {col_step}th column of the {cam.width}x{cam.height} frame "
+                                              f"({info['columns_rendered']} columns, {info['rays_total']} rays, "
+                                              f"{info['render_seconds']:.1f}s), grid as shipped; build {build_s:.2f}s excluded"}
+        if not args.no_others and args.workload == "synth1m":
+            other = measure_gpu(args, "bob1080", max(5, args.steps), args.warmup, dist_ctx, False)
+            line["other_workloads"] = {"bob1080": {"value": other["value"], "unit": "Mrays/s",
+                                                   "ms_per_step": other["ms_per_step"], "e2e_value": other["e2e_value"],
+                                                   "e2e_ms_per_step": other["e2e_ms_per_step"],
+                                                   "rays_per_frame": other["rays_per_frame"],
+                                                   "description": other["desc"], "kernel_ms": other["kernel_ms"],
+                                                   "work": other["work"]}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="synth1m")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        import __graft_entry__ as entry
+        if not os.path.exists(os.path.join(ROOT, "realtrace_b200", "librealtrace_b200.so")):
+            entry.build()
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -85,16 +85,19 @@ typedef struct rt_frame_stats {
     uint64_t rays_primary;        /* one ray = one World::firstIntersection call (world.cpp:35,:46) */
     uint64_t rays_shadow;
     uint64_t rays_secondary;
-    uint64_t node_visits;         /* RT_FLAG_COUNT_WORK only */
-    uint64_t tri_tests;           /* RT_FLAG_COUNT_WORK only */
+    uint64_t node_visits;         /* RT_FLAG_COUNT_WORK only: nearest-hit rays (primary + secondary) */
+    uint64_t tri_tests;           /* RT_FLAG_COUNT_WORK only: nearest-hit rays */
+    uint64_t shadow_node_visits;  /* RT_FLAG_COUNT_WORK only: any-hit (shadow) rays */
+    uint64_t shadow_tri_tests;    /* RT_FLAG_COUNT_WORK only: any-hit (shadow) rays */
     uint32_t waves;               /* wavefront iterations (bounce generations) */
     uint32_t tiles;               /* tiles rendered by this context */
     uint32_t kernel_launches;     /* CUDA kernels launched for this frame */
     uint32_t max_queue;           /* largest ray population of any wave */
     float ms_device;              /* device time of the frame, CUDA events on the render stream */
     float ms_trace;               /* device time of the primary nearest-hit kernel */
-    float ms_shade;               /* device time of the primary shadow + shade kernel */
-    float ms_secondary;           /* device time of all bounce waves (trace + shade) */
+    float ms_shadow;              /* device time of the primary wave's shadow any-hit kernel */
+    float ms_shade;               /* device time of the primary wave's shading kernel */
+    float ms_secondary;           /* device time of all bounce waves (trace + shadow + shade) */
     float ms_resolve;
 } rt_frame_stats;
 

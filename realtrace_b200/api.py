@@ -38,10 +38,11 @@ class RtAuxOut(C.Structure):
 
 class RtFrameStats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_secondary", C.c_uint64),
-                ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("waves", C.c_uint32), ("tiles", C.c_uint32),
+                ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("shadow_node_visits", C.c_uint64),
+                ("shadow_tri_tests", C.c_uint64), ("waves", C.c_uint32), ("tiles", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("max_queue", C.c_uint32), ("ms_device", C.c_float),
-                ("ms_trace", C.c_float), ("ms_shade", C.c_float), ("ms_secondary", C.c_float),
-                ("ms_resolve", C.c_float)]
+                ("ms_trace", C.c_float), ("ms_shadow", C.c_float), ("ms_shade", C.c_float),
+                ("ms_secondary", C.c_float), ("ms_resolve", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -65,6 +65,12 @@ int rt_create(rt_ctx** out, int device) {
             int v = atoi(ls);
             if (v >= 1 && v <= RT_LEAF_MAX) c->leaf_size = v;
         }
+        auto env_int = [](const char* name, int lo, int hi, int& dst) {
+            const char* e = getenv(name);
+            if (e) { int v = atoi(e); if (v >= lo && v <= hi) dst = v; }
+        };
+        env_int("RT_REFILL_MIN", 1, 32, c->refill_min);
+        env_int("RT_REFILL_MIN_SHADOW", 1, 32, c->refill_min_shadow);
         rt_render_init(c);
     } catch (const RtError& err) {
         g_create_error = err.msg;

@@ -1,17 +1,20 @@
-// render.cu — the wavefront pipeline: primary raygen + persistent-thread nearest-hit traversal,
-// shadow any-hit + shading + bounce spawning, RGB8 resolve.
+// render.cu — the wavefront pipeline: primary raygen + persistent-thread traversal (nearest hit and
+// shadow any-hit), shading + bounce spawning, RGB8 resolve.
 //
 // Replaces the reference's frame loop RenderEngine::renderLoop -> trace -> World::shade_ray
 // (/root/reference/Serial/renderengine.cpp:3-26, world.cpp:32-111) and its display conversion
 // Camera::drawPixel (camera.cpp:46-52).  One "wave" is one generation of rays:
-//   k_trace   persistent warps pull 32 rays at a time from a global cursor; wave 0 generates its
-//             rays in registers from the pixel index (tile-ordered, 8x4 pixels per warp), later
-//             waves read 48-byte SoA ray records.  Hits are compacted into a hit queue with one
-//             warp-aggregated atomic (ballot + popc); misses add throughput*background at once.
-//   k_shade   persistent warps pull hit-queue entries: per light one any-hit shadow query
-//             (world.cpp:44-51), the local Phong-like term (:126-137), then the mirror /
-//             dielectric children (:77-107) appended to the next wave's ray queue, again with one
-//             atomic per warp (shfl prefix sum).
+//   k_traverse<PRIMARY|QUEUE>  nearest hit.  Persistent warps; every LANE owns one ray and, when it
+//             finishes, takes the next one from a global cursor (ballot + one atomic per refill), so
+//             short and long rays do not hold each other up.  Wave 0 generates its rays in registers
+//             from the pixel index (tile-ordered, 8x4 pixels per 32 consecutive indices); later waves
+//             read 48-byte SoA ray records.  Hits are compacted into a hit queue with warp-aggregated
+//             atomics; misses add throughput*background at once (world.cpp:110).
+//   k_traverse<SHADOW>  one any-hit query per (hit, light): world.cpp:44-51 (no tmax).  Same kernel
+//             body, early exit on the first accepted hit, one occlusion byte out.
+//   k_shade   per hit: the local Phong-like term (world.cpp:126-137) from the occlusion bytes, then
+//             the mirror / dielectric children (:77-107) appended to the next wave's ray queue with
+//             one atomic per warp (shfl prefix sum).
 //   k_resolve 32.32 fixed-point accumulators -> clamp -> (uint8)(255 c) (color.cpp:19-28,
 //             camera.cpp:49-51) into the frame or into this rank's packed tile buffer.
 // Pixel sums use integer atomics, so the frame is bit-identical for any tile split, queue order
@@ -23,8 +26,10 @@
 
 namespace {
 
-constexpr int TRACE_TPB = 128;
+constexpr int TRAV_TPB = 128;
 constexpr int SHADE_TPB = 128;
+
+enum { MODE_PRIMARY = 0, MODE_QUEUE = 1, MODE_SHADOW = 2 };
 
 struct CamDev {
     double pos[3], u[3], v[3], w[3];
@@ -91,88 +96,197 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
     return v;
 }
 
-struct TraceArgs {
+struct TravArgs {
     SceneDev s;
     CamDev cam;
     FrameDev f;
-    RayQueue q;
-    float4* hits;
+    RayQueue q;               // QUEUE: the rays; SHADOW: the rays of the wave whose hits are tested
+    const float4* hits_in;    // SHADOW: hit records of the wave
+    const uint32_t* hitq_in;  // SHADOW: ray index of each hit
+    float4* hits;             // nearest modes: hit records out (compacted)
     uint32_t* hitq;
+    uint8_t* occl;            // SHADOW: [light][hit] 1 = occluded
     WaveCounters* wave;
     long long* accum;
     FrameCounters* fc;
     int32_t* aux_prim;
     float* aux_t;
     uint32_t brute;
-    uint32_t cap;       // ray-queue capacity (bounds n_rays after an overflow)
+    uint32_t cap;             // ray-queue capacity (bounds n_rays after an overflow)
+    uint32_t primary_wave;    // SHADOW: the wave's rays are primary rays (regenerated from the pixel)
+    int refill_min;           // idle lanes a warp waits for before it fetches new rays
 };
 
-template <bool PRIMARY, bool COUNT>
-__global__ void __launch_bounds__(TRACE_TPB) k_trace(const __grid_constant__ TraceArgs a) {
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ TravArgs a) {
+    constexpr bool ANY = MODE == MODE_SHADOW;
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const uint32_t n = PRIMARY ? a.f.n_local_pix : min(a.wave->n_rays, a.cap);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t n, n_hits_in = 0;
+    if (MODE == MODE_PRIMARY) n = a.f.n_local_pix;
+    else if (MODE == MODE_QUEUE) n = min(a.wave->n_rays, a.cap);
+    else { n_hits_in = a.wave->n_hits; n = n_hits_in * (uint32_t)a.s.n_lights; }
+    uint32_t* cursor = ANY ? &a.wave->fetch_shade : &a.wave->fetch_trace;
     const f3 bg = mk3(a.s.background[0], a.s.background[1], a.s.background[2]);
+    const bool use_bvh = !a.brute && a.s.n_bvh_tris > 0;
+
+    // per-lane ray state
+    RayPrep r;
+    HitRec hit;
+    int stack[RT_STACK_SIZE];
+    int node = RT_DONE, sp = 0;
+    bool active = false, found = false, exhausted = false, overflow = false;
+    uint32_t item = 0, pix = 0;
+    int pi = 0, pj = 0;
+    f3 w = mk3(1, 1, 1);
     WorkCount wc;
     wc.nodes = wc.tris = 0;
-    bool overflow = false;
+    uint32_t traced = 0;
+
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&a.wave->fetch_trace, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t idx = base + lane;
-        bool valid = idx < n;
-        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), w = mk3(1, 1, 1);
-        uint32_t pix = idx;
-        int pi = 0, pj = 0;
-        if (valid) {
-            if (PRIMARY) {
-                valid = local_to_pixel(a.f, idx, pi, pj);
-                if (valid) primary_ray(a.cam, pi, pj, o, d);
+        // ---- refill idle lanes from the global cursor
+        uint32_t need = __ballot_sync(FULL, !active);
+        if (!exhausted && (__popc(need) >= a.refill_min || need == FULL)) {
+            int cnt = __popc(need), leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(cursor, (uint32_t)cnt);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + (uint32_t)cnt >= n) exhausted = true;
+            uint32_t my = base + __popc(need & lt);
+            if (!active && my < n) {
+                f3 o, d;
+                bool ok = true;
+                item = my;
+                if (MODE == MODE_PRIMARY) {
+                    ok = local_to_pixel(a.f, my, pi, pj);
+                    if (ok) primary_ray(a.cam, pi, pj, o, d);
+                    pix = my;
+                    w = mk3(1, 1, 1);
+                } else if (MODE == MODE_QUEUE) {
+                    float4 ro = a.q.o_pix[my], rd = a.q.d_lvl[my], rw = a.q.w[my];
+                    o = mk3(ro); d = mk3(rd); w = mk3(rw);
+                    pix = __float_as_uint(ro.w);
+                } else {
+                    uint32_t li = my / n_hits_in, pos = my - li * n_hits_in;
+                    float4 hr = a.hits_in[pos];
+                    uint32_t idx = a.hitq_in[pos];
+                    f3 po, pd;
+                    if (a.primary_wave) {
+                        int qi, qj;
+                        local_to_pixel(a.f, idx, qi, qj);
+                        primary_ray(a.cam, qi, qj, po, pd);
+                    } else {
+                        po = mk3(a.q.o_pix[idx]);
+                        pd = mk3(a.q.d_lvl[idx]);
+                    }
+                    // dielectric hits discard their local colour (world.cpp:77-100): no shadow query
+                    int prim = __float_as_int(hr.y);
+                    uint32_t mat = prim >= 0 ? __float_as_uint(__ldg(a.s.tris + 3 * (size_t)prim + 1).w)
+                                             : a.s.analytic[rt_analytic_index(prim)].material;
+                    float4 m1 = __ldg(a.s.materials + 3 * mat + 1);
+                    if (m1.z > 0.0f && m1.w > 0.0f) {
+                        a.occl[my] = 0;
+                        ok = false;
+                    } else {
+                        f3 P = fma3(pd, hr.x, po);
+                        f3 toL = mk3(__ldg(a.s.lights + 2 * li)) - P;
+                        o = fma3(toL, 0.01f, P);              // world.cpp:45
+                        d = normalize(toL);
+                        traced++;
+                    }
+                }
+                if (ok) {
+                    hit.t = RT_FLT_MAX; hit.prim = RT_MISS; hit.beta = hit.gamma = 0.0f;
+                    found = false;
+                    active = true;
+                    sp = 0;
+                    // a NaN direction (ignored refract() failure, world.cpp:83) misses everything
+                    bool finite = d.x == d.x && d.y == d.y && d.z == d.z;
+                    r = prep_ray(o, d);
+                    node = (use_bvh && finite) ? 0 : RT_DONE;
+                    if (!finite) r.d = mk3(d.x, d.y, d.z);
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- while-while traversal of the lanes that own a ray
+        if (active) {
+            while (rt_is_internal(node)) {
+                if (COUNT) wc.nodes++;
+                node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
+            }
+            while (node < 0) {
+                if (leaf_test(a.s, node, r, hit, ANY, COUNT ? &wc : nullptr)) {
+                    found = true;
+                    if (ANY) { node = RT_DONE; break; }
+                }
+                node = sp ? stack[--sp] : RT_DONE;
+            }
+        }
+        // ---- rays that ran out of nodes: linear primitives, then the result
+        bool fin = active && node == RT_DONE;
+        if (fin) {
+            bool finite = r.d.x == r.d.x && r.d.y == r.d.y && r.d.z == r.d.z;
+            if (finite && !(ANY && found)) {
+                if (a.brute) found |= brute_walk<ANY>(a.s, r, hit, COUNT ? &wc : nullptr);
+                for (int k = 0; k < a.s.n_analytic && !(ANY && found); k++) {
+                    const AnalyticPrim p = a.s.analytic[k];
+                    if (COUNT) wc.tris++;
+                    if (analytic_test(p, r.o, r.d, hit.t, hit.beta, hit.gamma)) {
+                        hit.prim = rt_analytic_code(k);
+                        found = true;
+                    }
+                }
+            }
+            if (ANY) {
+                a.occl[item] = found ? 1 : 0;
             } else {
-                float4 ro = a.q.o_pix[idx], rd = a.q.d_lvl[idx], rw = a.q.w[idx];
-                o = mk3(ro); d = mk3(rd); w = mk3(rw);
-                pix = __float_as_uint(ro.w);
+                if (a.aux_prim) {
+                    size_t at = MODE == MODE_PRIMARY ? (size_t)pi + (size_t)pj * a.f.W : (size_t)pix;
+                    int id = -1;
+                    if (found) {
+                        if (hit.prim >= 0) id = (int)__float_as_uint(__ldg(a.s.tris + 3 * (size_t)hit.prim).w);
+                        else id = (int)a.s.analytic[rt_analytic_index(hit.prim)].object_id;
+                    }
+                    a.aux_prim[at] = id;
+                    if (a.aux_t) a.aux_t[at] = found ? hit.t : RT_FLT_MAX;
+                }
+                if (!found) accumulate(a.accum, pix, w * bg);      // world.cpp:110
+            }
+            active = false;
+        }
+        if (!ANY) {
+            // hits: one atomic per warp reserves a run of the hit queue
+            uint32_t mask = __ballot_sync(FULL, fin && found);
+            if (mask) {
+                uint32_t qbase = 0;
+                int leader = __ffs(mask) - 1;
+                if (lane == leader) qbase = atomicAdd(&a.wave->n_hits, (uint32_t)__popc(mask));
+                qbase = __shfl_sync(FULL, qbase, leader);
+                if (fin && found) {
+                    uint32_t pos = qbase + __popc(mask & lt);
+                    a.hitq[pos] = item;
+                    a.hits[pos] = make_float4(hit.t, __int_as_float(hit.prim), hit.beta, hit.gamma);
+                }
             }
         }
-        HitRec h;
-        h.t = RT_FLT_MAX; h.prim = RT_MISS; h.beta = h.gamma = 0.0f;
-        bool found = false;
-        if (valid) found = trace_ray<false>(a.s, o, d, a.brute != 0, h, COUNT ? &wc : nullptr, &overflow);
-        if (valid && a.aux_prim) {
-            size_t at = PRIMARY ? (size_t)pi + (size_t)pj * a.f.W : (size_t)pix;
-            int id = -1;
-            if (found) {
-                if (h.prim >= 0) id = (int)__float_as_uint(__ldg(a.s.tris + 3 * (size_t)h.prim).w);
-                else id = (int)a.s.analytic[rt_analytic_index(h.prim)].object_id;
-            }
-            a.aux_prim[at] = id;
-            if (a.aux_t) a.aux_t[at] = found ? h.t : RT_FLT_MAX;
-        }
-        // misses resolve to throughput * background right here (world.cpp:110)
-        if (valid && !found) accumulate(a.accum, pix, w * bg);
-        // hits: one atomic per warp reserves a run of the hit queue
-        uint32_t mask = __ballot_sync(0xffffffffu, found);
-        if (mask) {
-            uint32_t qbase = 0;
-            int leader = __ffs(mask) - 1;
-            if (lane == leader) qbase = atomicAdd(&a.wave->n_hits, (uint32_t)__popc(mask));
-            qbase = __shfl_sync(0xffffffffu, qbase, leader);
-            if (found) {
-                uint32_t pos = qbase + __popc(mask & ((1u << lane) - 1u));
-                a.hitq[pos] = idx;
-                a.hits[pos] = make_float4(h.t, __int_as_float(h.prim), h.beta, h.gamma);
-            }
-        }
+    }
+    if (ANY) {
+        uint32_t ns = warp_sum(traced);
+        if (lane == 0 && ns) atomicAdd(&a.fc->rays_shadow, (unsigned long long)ns);
     }
     if (COUNT) {
         uint32_t nn = warp_sum(wc.nodes), nt = warp_sum(wc.tris);
         if (lane == 0) {
-            atomicAdd(&a.fc->node_visits, (unsigned long long)nn);
-            atomicAdd(&a.fc->tri_tests, (unsigned long long)nt);
+            atomicAdd(&a.fc->node_visits[ANY ? 1 : 0], (unsigned long long)nn);
+            atomicAdd(&a.fc->tri_tests[ANY ? 1 : 0], (unsigned long long)nt);
         }
     }
-    if (__any_sync(0xffffffffu, overflow) && lane == 0) atomicOr(&a.wave->flags, 2u);
+    if (__any_sync(FULL, overflow) && lane == 0) atomicOr(&a.wave->flags, 2u);
 }
 
 struct ShadeArgs {
@@ -182,29 +296,24 @@ struct ShadeArgs {
     RayQueue qin, qout;
     const float4* hits;
     const uint32_t* hitq;
+    const uint8_t* occl;
     WaveCounters* wave;
     WaveCounters* next;
     long long* accum;
-    FrameCounters* fc;
     uint32_t cap;
     int max_depth;
-    uint32_t brute;
 };
 
-template <bool PRIMARY, bool COUNT>
+// Shading proper: no traversal in here, the shadow answers come from k_traverse<SHADOW>.
+template <bool PRIMARY>
 __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ ShadeArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t n = a.wave->n_hits;
     const f3 bg = mk3(a.s.background[0], a.s.background[1], a.s.background[2]);
-    WorkCount wc;
-    wc.nodes = wc.tris = 0;
-    uint32_t shadow_rays = 0;
-    bool overflow = false, qfull = false;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&a.wave->fetch_shade, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    bool qfull = false;
+    for (uint32_t base = warp * 32u; base < n; base += warps * 32u) {
         uint32_t pos = base + lane;
         bool valid = pos < n;
         ShadeOut out;
@@ -229,12 +338,9 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
                 pix = __float_as_uint(ro.w);
                 level = __float_as_int(rd.w);
             }
-            auto any_hit = [&](f3 so, f3 sd) -> bool {
-                HitRec sh;
-                return trace_ray<true>(a.s, so, sd, a.brute != 0, sh, COUNT ? &wc : nullptr, &overflow);
-            };
+            uint32_t li = 0;
+            auto any_hit = [&](f3, f3) -> bool { return a.occl[(size_t)(li++) * n + pos] != 0; };
             shade_hit(a.s, o, d, level, h, a.max_depth, any_hit, out);
-            shadow_rays += (uint32_t)out.shadow_rays;
             accumulate(a.accum, pix, w * (out.local + out.bg_weight * bg));
         }
         // append children: exclusive prefix over the warp, one atomic
@@ -261,17 +367,7 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
             }
         }
     }
-    uint32_t ns = warp_sum(shadow_rays);
-    if (lane == 0 && ns) atomicAdd(&a.fc->rays_shadow, (unsigned long long)ns);
-    if (COUNT) {
-        uint32_t nn = warp_sum(wc.nodes), nt = warp_sum(wc.tris);
-        if (lane == 0) {
-            atomicAdd(&a.fc->node_visits, (unsigned long long)nn);
-            atomicAdd(&a.fc->tri_tests, (unsigned long long)nt);
-        }
-    }
-    uint32_t fl = (__any_sync(0xffffffffu, overflow) ? 2u : 0u) | (__any_sync(0xffffffffu, qfull) ? 1u : 0u);
-    if (fl && lane == 0) atomicOr(&a.wave->flags, fl);
+    if (__any_sync(0xffffffffu, qfull) && lane == 0) atomicOr(&a.wave->flags, 1u);
 }
 
 // Color::clamp + Camera::drawPixel (color.cpp:19-28, camera.cpp:46-52): truncating 8-bit conversion.
@@ -406,6 +502,8 @@ void ensure_queues(rt_ctx* c, size_t n_rays0, bool need_bounce) {
     if (cap > hits_cap) hits_cap = cap;
     c->d_hits.reserve(hits_cap);
     c->d_hitq.reserve(hits_cap);
+    size_t nl = c->scene.n_lights > 0 ? (size_t)c->scene.n_lights : 1;
+    c->d_occl.reserve(hits_cap * nl);
     if (cap) {
         for (int b = 0; b < 2; b++)
             for (int k = 0; k < 3; k++) c->d_q[b][k].reserve(cap);
@@ -419,31 +517,65 @@ RayQueue queue_of(rt_ctx* c, int b) {
     return q;
 }
 
-template <bool PRIMARY>
-void launch_trace(rt_ctx* c, const TraceArgs& a, bool count) {
-    if (count) k_trace<PRIMARY, true><<<c->trace_blocks, TRACE_TPB, 0, c->stream>>>(a);
-    else k_trace<PRIMARY, false><<<c->trace_blocks, TRACE_TPB, 0, c->stream>>>(a);
+template <int MODE>
+void launch_traverse(rt_ctx* c, const TravArgs& a, bool count) {
+    int blocks = MODE == MODE_SHADOW ? c->shadow_blocks : c->trace_blocks;
+    if (count) k_traverse<MODE, true><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+    else k_traverse<MODE, false><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
     RT_CUDA(cudaGetLastError());
 }
 template <bool PRIMARY>
-void launch_shade(rt_ctx* c, const ShadeArgs& a, bool count) {
-    if (count) k_shade<PRIMARY, true><<<c->shade_blocks, SHADE_TPB, 0, c->stream>>>(a);
-    else k_shade<PRIMARY, false><<<c->shade_blocks, SHADE_TPB, 0, c->stream>>>(a);
+void launch_shade(rt_ctx* c, const ShadeArgs& a) {
+    k_shade<PRIMARY><<<c->shade_blocks, SHADE_TPB, 0, c->stream>>>(a);
     RT_CUDA(cudaGetLastError());
 }
 
-// Runs waves 1.. over rays already sitting in queue `cur` with population d_waves[1].n_rays (or
-// h_n1 if known).  Returns number of waves executed; accumulates launches.
+// The three kernels of one wave whose rays sit in queue `cur` (or are the primary rays).
+template <bool PRIMARY>
+uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot_out, int cur, bool count, bool shade,
+                     cudaEvent_t after_trace, cudaEvent_t after_shadow) {
+    uint32_t launches = 0;
+    ta.q = queue_of(c, cur);
+    ta.wave = c->d_waves.p + slot_in;
+    ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p;
+    launch_traverse<PRIMARY ? MODE_PRIMARY : MODE_QUEUE>(c, ta, count);
+    launches++;
+    if (after_trace) RT_CUDA(cudaEventRecord(after_trace, c->stream));
+    if (!shade) return launches;
+    if (c->scene.n_lights > 0) {
+        TravArgs sh = ta;
+        sh.hits_in = c->d_hits.p; sh.hitq_in = c->d_hitq.p; sh.occl = c->d_occl.p;
+        sh.primary_wave = PRIMARY ? 1u : 0u;
+        sh.refill_min = c->refill_min_shadow;
+        sh.aux_prim = nullptr; sh.aux_t = nullptr;
+        launch_traverse<MODE_SHADOW>(c, sh, count);
+        launches++;
+    }
+    if (after_shadow) RT_CUDA(cudaEventRecord(after_shadow, c->stream));
+    sa.qin = queue_of(c, cur);
+    sa.qout = queue_of(c, cur ^ 1);
+    sa.wave = c->d_waves.p + slot_in;
+    sa.next = c->d_waves.p + slot_out;
+    sa.occl = c->d_occl.p;
+    launch_shade<PRIMARY>(c, sa);
+    launches++;
+    return launches;
+}
+
 struct WaveResult {
-    uint32_t waves = 0, launches = 0, max_queue = 0, flags = 0;
+    uint32_t waves = 0, launches = 0, max_queue = 0;
     uint64_t secondary = 0;
 };
 
-WaveResult run_bounce_waves(rt_ctx* c, TraceArgs ta, ShadeArgs sa, int first_wave, int cur, int max_depth, bool count,
-                            bool primary_in_wave0) {
+// Runs waves first_wave.. over rays already sitting in queue `cur`.  Mirror-only scenes need no
+// host round trip: a ray of wave w has level w, so exactly max_depth waves can be populated and
+// they are launched blind (empty ones exit at once).  With dielectrics (level*2, world.cpp:98) the
+// population of each wave is read back before it is launched.
+WaveResult run_bounce_waves(rt_ctx* c, const TravArgs& ta, const ShadeArgs& sa, int first_wave, int cur, int max_depth,
+                            bool count, bool levels_equal_waves) {
     WaveResult r;
     cudaStream_t st = c->stream;
-    bool poll = c->has_dielectric || max_depth > 16 || !primary_in_wave0;
+    bool poll = c->has_dielectric || max_depth > 16 || !levels_equal_waves;
     for (int w = first_wave;; w++) {
         int slot_in = w % RT_WAVE_SLOTS, slot_out = (w + 1) % RT_WAVE_SLOTS;
         if (poll) {
@@ -458,15 +590,7 @@ WaveResult run_bounce_waves(rt_ctx* c, TraceArgs ta, ShadeArgs sa, int first_wav
             break;
         }
         if (w + 1 >= RT_WAVE_SLOTS) RT_CUDA(cudaMemsetAsync(c->d_waves.p + slot_out, 0, sizeof(WaveCounters), st));
-        ta.q = queue_of(c, cur);
-        ta.wave = c->d_waves.p + slot_in;
-        launch_trace<false>(c, ta, count);
-        sa.qin = queue_of(c, cur);
-        sa.qout = queue_of(c, cur ^ 1);
-        sa.wave = c->d_waves.p + slot_in;
-        sa.next = c->d_waves.p + slot_out;
-        launch_shade<false>(c, sa, count);
-        r.launches += 2;
+        r.launches += launch_wave<false>(c, ta, sa, slot_in, slot_out, cur, count, true, nullptr, nullptr);
         r.waves++;
         cur ^= 1;
     }
@@ -476,12 +600,12 @@ WaveResult run_bounce_waves(rt_ctx* c, TraceArgs ta, ShadeArgs sa, int first_wav
 }  // namespace
 
 void rt_render_init(rt_ctx* c) {
-    c->trace_blocks = persistent_blocks(k_trace<true, false>, TRACE_TPB, c->sm_count);
-    int tb2 = persistent_blocks(k_trace<false, false>, TRACE_TPB, c->sm_count);
-    if (tb2 < c->trace_blocks) c->trace_blocks = tb2;
-    c->shade_blocks = persistent_blocks(k_shade<true, false>, SHADE_TPB, c->sm_count);
-    int sb2 = persistent_blocks(k_shade<false, false>, SHADE_TPB, c->sm_count);
-    if (sb2 < c->shade_blocks) c->shade_blocks = sb2;
+    auto lo = [](int a, int b) { return a < b ? a : b; };
+    c->trace_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false>, TRAV_TPB, c->sm_count),
+                         persistent_blocks(k_traverse<MODE_QUEUE, false>, TRAV_TPB, c->sm_count));
+    c->shadow_blocks = persistent_blocks(k_traverse<MODE_SHADOW, false>, TRAV_TPB, c->sm_count);
+    c->shade_blocks = lo(persistent_blocks(k_shade<true>, SHADE_TPB, c->sm_count),
+                         persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
     c->d_waves.reserve(RT_WAVE_SLOTS);
     c->d_frame.reserve(1);
     RT_CUDA(cudaMallocHost((void**)&c->h_waves, RT_WAVE_SLOTS * sizeof(WaveCounters)));
@@ -503,34 +627,34 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     RT_CUDA(cudaMemsetAsync(c->d_frame.p, 0, sizeof(FrameCounters), st));
     RT_CUDA(cudaMemsetAsync(c->d_accum.p, 0, 3 * (size_t)f.n_local_pix * sizeof(long long), st));
 
-    TraceArgs ta;
-    ta.s = c->scene; ta.cam = make_cam(cam); ta.f = f; ta.q = queue_of(c, 0);
-    ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p; ta.wave = c->d_waves.p; ta.accum = c->d_accum.p;
-    ta.fc = c->d_frame.p;
+    TravArgs ta;
+    memset(&ta, 0, sizeof ta);
+    ta.s = c->scene; ta.cam = make_cam(cam); ta.f = f;
+    ta.accum = c->d_accum.p; ta.fc = c->d_frame.p;
     ta.aux_prim = aux_dev ? aux_dev->prim_id : nullptr;
     ta.aux_t = aux_dev ? aux_dev->t : nullptr;
     ta.brute = (p->flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
     ta.cap = (uint32_t)c->queue_cap;
-    uint32_t launches = 0;
-    if (f.n_local_pix) { launch_trace<true>(c, ta, count); launches++; }
-    RT_CUDA(cudaEventRecord(c->ev[1], st));
-
+    ta.refill_min = c->refill_min;
     ShadeArgs sa;
-    sa.s = c->scene; sa.cam = ta.cam; sa.f = f; sa.qin = queue_of(c, 0); sa.qout = queue_of(c, 0);
-    sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.wave = c->d_waves.p; sa.next = c->d_waves.p + 1;
-    sa.accum = c->d_accum.p; sa.fc = c->d_frame.p; sa.cap = (uint32_t)c->queue_cap;
+    memset(&sa, 0, sizeof sa);
+    sa.s = c->scene; sa.cam = ta.cam; sa.f = f;
+    sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.accum = c->d_accum.p; sa.cap = (uint32_t)c->queue_cap;
     sa.max_depth = p->max_depth;
-    sa.brute = ta.brute;
-    if (f.n_local_pix) { launch_shade<true>(c, sa, count); launches++; }
-    RT_CUDA(cudaEventRecord(c->ev[2], st));
+
+    uint32_t launches = 0;
+    if (f.n_local_pix) launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, c->ev[1], c->ev[2]);
+    else { RT_CUDA(cudaEventRecord(c->ev[1], st)); RT_CUDA(cudaEventRecord(c->ev[2], st)); }
+    RT_CUDA(cudaEventRecord(c->ev[3], st));
 
     WaveResult wr;
     if (bounce && f.n_local_pix) {
         ta.aux_prim = nullptr; ta.aux_t = nullptr;
-        wr = run_bounce_waves(c, ta, sa, 1, 0, p->max_depth, count, true);
+        // wave 0 wrote its children into queue 1
+        wr = run_bounce_waves(c, ta, sa, 1, 1, p->max_depth, count, true);
         launches += wr.launches;
     }
-    RT_CUDA(cudaEventRecord(c->ev[3], st));
+    RT_CUDA(cudaEventRecord(c->ev[6], st));
 
     if (f.n_local_pix && rgb_dev) {
         uint32_t quads = f.n_tiles_owned * (uint32_t)(f.tile_pix / 4);
@@ -539,7 +663,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         RT_CUDA(cudaGetLastError());
         launches++;
     }
-    RT_CUDA(cudaEventRecord(c->ev[6], st));
+    RT_CUDA(cudaEventRecord(c->ev[7], st));
 
     // statistics + error flags (one small D2H; also the frame's completion point)
     RT_CUDA(cudaMemcpyAsync(c->h_waves, c->d_waves.p, RT_WAVE_SLOTS * sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
@@ -573,17 +697,20 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         }
         stats->rays_shadow = c->h_frame->rays_shadow;
         stats->rays_secondary = secondary;
-        stats->node_visits = c->h_frame->node_visits;
-        stats->tri_tests = c->h_frame->tri_tests;
+        stats->node_visits = c->h_frame->node_visits[0];
+        stats->tri_tests = c->h_frame->tri_tests[0];
+        stats->shadow_node_visits = c->h_frame->node_visits[1];
+        stats->shadow_tri_tests = c->h_frame->tri_tests[1];
         stats->waves = 1 + wr.waves;
         stats->tiles = c->layout.n_tiles_owned;
         stats->kernel_launches = launches;
         stats->max_queue = max_queue > c->h_waves[0].n_hits ? max_queue : c->h_waves[0].n_hits;
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_device, c->ev[0], c->ev[6]));
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_device, c->ev[0], c->ev[7]));
         RT_CUDA(cudaEventElapsedTime(&stats->ms_trace, c->ev[0], c->ev[1]));
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_shade, c->ev[1], c->ev[2]));
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_secondary, c->ev[2], c->ev[3]));
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_resolve, c->ev[3], c->ev[6]));
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_shadow, c->ev[1], c->ev[2]));
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_shade, c->ev[2], c->ev[3]));
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_secondary, c->ev[3], c->ev[6]));
+        RT_CUDA(cudaEventElapsedTime(&stats->ms_resolve, c->ev[6], c->ev[7]));
     }
     if (flags & 1u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow: a wave spawned more rays than the queue holds"};
     if (flags & 2u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow (BVH deeper than RT_STACK_SIZE)"};
@@ -624,29 +751,23 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
     w0.n_rays = n;
     RT_CUDA(cudaMemcpyAsync(c->d_waves.p, &w0, sizeof w0, cudaMemcpyHostToDevice, st));
 
-    TraceArgs ta;
+    TravArgs ta;
     memset(&ta, 0, sizeof ta);
-    ta.s = c->scene; ta.q = queue_of(c, 0); ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p;
-    ta.wave = c->d_waves.p; ta.accum = c->d_accum.p; ta.fc = c->d_frame.p;
+    ta.s = c->scene;
+    ta.accum = c->d_accum.p; ta.fc = c->d_frame.p;
     ta.aux_prim = c->d_aux_prim.p; ta.aux_t = c->d_aux_t.p;
     ta.brute = (flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
     ta.cap = (uint32_t)cap;
+    ta.refill_min = c->refill_min;
     ShadeArgs sa;
     memset(&sa, 0, sizeof sa);
-    sa.s = c->scene; sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.accum = c->d_accum.p; sa.fc = c->d_frame.p;
-    sa.cap = (uint32_t)cap; sa.max_depth = max_depth; sa.brute = ta.brute;
-    if (!shade) {
-        launch_trace<false>(c, ta, count);
-    } else {
-        // wave 0 runs through the generic (queue-fed) kernels
-        launch_trace<false>(c, ta, count);
-        sa.qin = queue_of(c, 0); sa.qout = queue_of(c, 1);
-        sa.wave = c->d_waves.p; sa.next = c->d_waves.p + 1;
-        launch_shade<false>(c, sa, count);
-        if (bounce) {
-            ta.aux_prim = nullptr; ta.aux_t = nullptr;
-            run_bounce_waves(c, ta, sa, 1, 1, max_depth, count, false);
-        }
+    sa.s = c->scene; sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.accum = c->d_accum.p;
+    sa.cap = (uint32_t)cap; sa.max_depth = max_depth;
+    // wave 0 runs through the generic (queue-fed) kernels
+    launch_wave<false>(c, ta, sa, 0, 1, 0, count, shade, nullptr, nullptr);
+    if (bounce) {
+        ta.aux_prim = nullptr; ta.aux_t = nullptr;
+        run_bounce_waves(c, ta, sa, 1, 1, max_depth, count, false);
     }
     if (prim_out) RT_CUDA(cudaMemcpyAsync(prim_out, c->d_aux_prim.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (t_out) RT_CUDA(cudaMemcpyAsync(t_out, c->d_aux_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));

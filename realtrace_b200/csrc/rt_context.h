@@ -62,7 +62,7 @@ struct WaveCounters {
     uint32_t n_rays;        // population of this wave (written by the previous wave's shade kernel)
     uint32_t fetch_trace;   // persistent-thread work cursor of the trace kernel
     uint32_t n_hits;        // hit-queue length
-    uint32_t fetch_shade;   // work cursor of the shade kernel
+    uint32_t fetch_shade;   // work cursor of the shadow (any-hit) kernel
     uint32_t n_next;        // rays appended for the next wave
     uint32_t flags;         // bit0: ray-queue overflow, bit1: traversal stack overflow
     uint32_t pad[2];
@@ -70,7 +70,8 @@ struct WaveCounters {
 #define RT_WAVE_SLOTS 64
 
 struct FrameCounters {
-    unsigned long long rays_shadow, rays_secondary, node_visits, tri_tests;
+    unsigned long long rays_shadow;
+    unsigned long long node_visits[2], tri_tests[2];   // [0] nearest-hit rays, [1] any-hit (shadow) rays
 };
 
 // Ray queue in SoA float4 records (48 B per ray).
@@ -132,6 +133,7 @@ struct rt_ctx {
     DevBuf<float4> d_q[2][3];              // two ray queues x (o_pix, d_lvl, w)
     DevBuf<float4> d_hits;                 // HitRec per ray slot
     DevBuf<uint32_t> d_hitq;
+    DevBuf<uint8_t> d_occl;                // shadow results, [light][hit]
     size_t queue_cap = 0;
     DevBuf<WaveCounters> d_waves;
     DevBuf<FrameCounters> d_frame;
@@ -143,7 +145,8 @@ struct rt_ctx {
     WaveCounters* h_waves = nullptr;       // pinned
     FrameCounters* h_frame = nullptr;      // pinned
     cudaEvent_t ev[8] = {};
-    int trace_blocks = 0, shade_blocks = 0;
+    int trace_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
+    int refill_min = 8, refill_min_shadow = 8;   // lane-refill thresholds of k_traverse (RT_REFILL_MIN[_SHADOW])
 };
 
 // ---- entry points implemented across the .cu files ------------------------------------------------

@@ -61,7 +61,34 @@ RT_HD bool leaf_test(const SceneDev& s, int code, const RayPrep& r, HitRec& hit,
     return found;
 }
 
+// Traversal state codes: 0 <= node < RT_DONE is an internal node, node < 0 a leaf, RT_DONE = finished.
+#define RT_DONE 0x7fffffff
+RT_HD bool rt_is_internal(int node) { return (unsigned)node < (unsigned)RT_DONE; }
+
+// One internal-node step: tests both child boxes against [0, tmax] and returns where to go next —
+// the nearer hit child (the farther one is pushed), the only hit child, or the popped stack top.
+RT_HD int bvh_node_step(const SceneDev& s, const RayPrep& r, float tmax, int node, int* stack, int& sp,
+                        bool* overflow) {
+    const float4* n = s.nodes + RT_NODE_FLOAT4S * (size_t)node;
+    float4 n0 = ldg(n), n1 = ldg(n + 1), n2 = ldg(n + 2), n3 = ldg(n + 3);
+    float t0, t1;
+    bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, r, tmax, t0);
+    bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, r, tmax, t1);
+    int c0 = (int)as_uint(n3.x), c1 = (int)as_uint(n3.y);
+    if (h0 && h1) {
+        if (t1 < t0) { int tmp = c0; c0 = c1; c1 = tmp; }
+        if (sp < RT_STACK_SIZE) stack[sp++] = c1;
+        else if (overflow) *overflow = true;
+        return c0;
+    }
+    if (h0) return c0;
+    if (h1) return c1;
+    return sp ? stack[--sp] : RT_DONE;
+}
+
 // hit.t must hold the current upper bound (RT_FLT_MAX for a fresh ray), hit.prim = RT_MISS.
+// "while-while" order: descend internal nodes until a leaf is reached, then test leaves until the
+// stack yields an internal node again, so that in a warp the two phases run with many lanes each.
 template <bool ANY_HIT>
 RT_HD bool bvh_walk(const SceneDev& s, const RayPrep& r, HitRec& hit, WorkCount* wc, bool* overflow) {
     if (s.n_bvh_tris <= 0) return false;
@@ -69,32 +96,18 @@ RT_HD bool bvh_walk(const SceneDev& s, const RayPrep& r, HitRec& hit, WorkCount*
     int sp = 0;
     int node = 0;
     bool found = false;
-    for (;;) {
-        if (node >= 0) {
-            const float4* n = s.nodes + RT_NODE_FLOAT4S * (size_t)node;
-            float4 n0 = ldg(n), n1 = ldg(n + 1), n2 = ldg(n + 2), n3 = ldg(n + 3);
+    while (node != RT_DONE) {
+        while (rt_is_internal(node)) {
             if (wc) wc->nodes++;
-            float t0, t1;
-            bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, r, hit.t, t0);
-            bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, r, hit.t, t1);
-            int c0 = (int)as_uint(n3.x), c1 = (int)as_uint(n3.y);
-            if (h0 && h1) {
-                if (t1 < t0) { int tmp = c0; c0 = c1; c1 = tmp; }
-                if (sp < RT_STACK_SIZE) stack[sp++] = c1;
-                else if (overflow) *overflow = true;
-                node = c0;
-                continue;
-            }
-            if (h0) { node = c0; continue; }
-            if (h1) { node = c1; continue; }
-        } else {
+            node = bvh_node_step(s, r, hit.t, node, stack, sp, overflow);
+        }
+        while (node < 0) {
             if (leaf_test(s, node, r, hit, ANY_HIT, wc)) {
                 found = true;
                 if (ANY_HIT) return true;
             }
+            node = sp ? stack[--sp] : RT_DONE;
         }
-        if (sp == 0) break;
-        node = stack[--sp];
     }
     return found;
 }

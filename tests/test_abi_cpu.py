@@ -36,7 +36,7 @@ def test_struct_sizes_match_the_header():
     assert C.sizeof(api.RtMaterial) == 40 == scene.MATERIAL_DTYPE.itemsize
     assert C.sizeof(api.RtCamera) == 64
     assert C.sizeof(api.RtRenderParams) == 24
-    assert C.sizeof(api.RtFrameStats) == 76 + 4   # 5 x u64, 4 x u32, 5 x float, padded to 8
+    assert C.sizeof(api.RtFrameStats) == 96       # 7 x u64, 4 x u32, 6 x float
 
 
 def test_tile_layout_is_pure_host_code(lib):
