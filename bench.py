@@ -45,34 +45,50 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+    """Streams nvidia-smi clocks / throttle reasons (one process, -lms 20) while the bench runs; the
+    summary uses the samples that fall inside the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
                 if len(f) >= 7:
-                    self.rows.append(f)
+                    self.rows.append((time.perf_counter(), f))
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.05)
 
     def summary(self):
-        if not self.rows:
+        rows = [f for t, f in self.rows if self.t_begin is not None and self.t_begin <= t <= self.t_end]
+        where = "timed region"
+        if len(rows) < 2:
+            rows, where = [f for _, f in self.rows], "whole run (timed region shorter than the sampling period)"
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+        try:
+            sm = sorted(float(r[0]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                    "samples": len(rows), "window": where, "power_w_max": max(float(r[2]) for r in rows)}
+        except Exception as e:   # unexpected nvidia-smi formatting
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"unparsed nvidia-smi output: {e}"]}
 
 
 def total_rays(st):
@@ -140,7 +156,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     import torch
-    from realtrace_b200 import api, scenes
+    from realtrace_b200 import api, multigpu, scenes
 
     rank, world = dist_ctx["rank"], dist_ctx["world"]
     dev = torch.device("cuda", dist_ctx["local_rank"])
@@ -175,18 +191,19 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         if world == 1:
             return ctx.render_device(cam, depth, frame.data_ptr())
         st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES)
-        torch.distributed.gather(packed, gathered, dst=0)
+        multigpu.gather_packed(packed, rank, world, gathered)
         if rank == 0:
             for r in range(world):
                 ctx.assemble_tiles(gathered[r].data_ptr(), r, world, W, H, frame.data_ptr())
         return st
 
     # ---- value: device-resident frames, CUDA events around every step, L2 flushed between steps
+    sampler = ClockSampler(dist_ctx["local_rank"])
+    sampler.start()
     for _ in range(warmup):
         st = step_device()
     barrier()
-    sampler = ClockSampler(dist_ctx["local_rank"])
-    sampler.start()
+    sampler.t_begin = time.perf_counter()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     stats = []
     for k in range(steps):
@@ -195,7 +212,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         stats.append(step_device())
         evs[k][1].record(stream)
     barrier()
-    sampler.stop_flag = True
+    sampler.t_end = time.perf_counter()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     rays_local = sum(total_rays(s) for s in stats)
     launches = sum(s["kernel_launches"] for s in stats) + (world if (world > 1 and rank == 0) else 0) * steps
@@ -240,6 +257,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         e_s, e_rays = float(tmax[0]), float(t[1])
     e2e_value = e_rays / e_s / 1e6
 
+    sampler.stop()
     out = {"value": value, "ms_per_step": ms / steps, "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
            "launches": launches, "clocks": sampler.summary(), "desc": desc, "cam": cam, "depth": depth,
            "scene": scene, "build": bstats, "commit_s": commit_s, "last": stats[-1], "rays_per_frame": rays_total / steps}

@@ -69,8 +69,9 @@ int rt_create(rt_ctx** out, int device) {
             const char* e = getenv(name);
             if (e) { int v = atoi(e); if (v >= lo && v <= hi) dst = v; }
         };
-        env_int("RT_REFILL_MIN", 1, 32, c->refill_min);
-        env_int("RT_REFILL_MIN_SHADOW", 1, 32, c->refill_min_shadow);
+        env_int("RT_REFILL_PRIMARY", 1, 32, c->refill_primary);
+        env_int("RT_REFILL_QUEUE", 1, 32, c->refill_queue);
+        env_int("RT_REFILL_SHADOW", 1, 32, c->refill_shadow);
         rt_render_init(c);
     } catch (const RtError& err) {
         g_create_error = err.msg;

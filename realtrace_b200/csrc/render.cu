@@ -538,6 +538,7 @@ uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot
     ta.q = queue_of(c, cur);
     ta.wave = c->d_waves.p + slot_in;
     ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p;
+    ta.refill_min = PRIMARY ? c->refill_primary : c->refill_queue;
     launch_traverse<PRIMARY ? MODE_PRIMARY : MODE_QUEUE>(c, ta, count);
     launches++;
     if (after_trace) RT_CUDA(cudaEventRecord(after_trace, c->stream));
@@ -546,7 +547,7 @@ uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot
         TravArgs sh = ta;
         sh.hits_in = c->d_hits.p; sh.hitq_in = c->d_hitq.p; sh.occl = c->d_occl.p;
         sh.primary_wave = PRIMARY ? 1u : 0u;
-        sh.refill_min = c->refill_min_shadow;
+        sh.refill_min = c->refill_shadow;
         sh.aux_prim = nullptr; sh.aux_t = nullptr;
         launch_traverse<MODE_SHADOW>(c, sh, count);
         launches++;
@@ -635,7 +636,6 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     ta.aux_t = aux_dev ? aux_dev->t : nullptr;
     ta.brute = (p->flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
     ta.cap = (uint32_t)c->queue_cap;
-    ta.refill_min = c->refill_min;
     ShadeArgs sa;
     memset(&sa, 0, sizeof sa);
     sa.s = c->scene; sa.cam = ta.cam; sa.f = f;
@@ -758,7 +758,6 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
     ta.aux_prim = c->d_aux_prim.p; ta.aux_t = c->d_aux_t.p;
     ta.brute = (flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
     ta.cap = (uint32_t)cap;
-    ta.refill_min = c->refill_min;
     ShadeArgs sa;
     memset(&sa, 0, sizeof sa);
     sa.s = c->scene; sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.accum = c->d_accum.p;

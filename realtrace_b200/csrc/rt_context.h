@@ -146,7 +146,9 @@ struct rt_ctx {
     FrameCounters* h_frame = nullptr;      // pinned
     cudaEvent_t ev[8] = {};
     int trace_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
-    int refill_min = 8, refill_min_shadow = 8;   // lane-refill thresholds of k_traverse (RT_REFILL_MIN[_SHADOW])
+    // idle lanes a warp waits for before fetching new rays (k_traverse); measured on B200 (profiles/r1_tuning.md):
+    // coherent primary rays are best refilled as whole warps, shadow and bounce rays lane by lane in groups
+    int refill_primary = 32, refill_queue = 16, refill_shadow = 16;
 };
 
 // ---- entry points implemented across the .cu files ------------------------------------------------

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 names = sys.argv[1:] or ["synth1m", "bob1080"]
 for leaf in (4,):
     for refill in (1, 4, 8, 16, 24, 32):
-        env = dict(os.environ, RT_LEAF_SIZE=str(leaf), RT_REFILL_MIN=str(refill), RT_REFILL_MIN_SHADOW=str(refill))
+        env = dict(os.environ, RT_LEAF_SIZE=str(leaf), RT_REFILL_PRIMARY=str(refill), RT_REFILL_QUEUE=str(refill), RT_REFILL_SHADOW=str(refill))
         code = f"""
 import sys; sys.path.insert(0, {ROOT!r})
 from realtrace_b200 import api, scenes
