@@ -43,7 +43,11 @@ def build_host(force=False):
     if force or _stale(out, deps):
         subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I", host,
                                "-I", os.path.join(HERE, "..", "include"), "-o", out, src,
-                               "-L", HERE, "-lrealtrace_b200", "-Wl,-rpath,$ORIGIN"], cwd=host)
+                               "-L", HERE, "-lrealtrace_b200", "-lz", "-Wl,-rpath,$ORIGIN"], cwd=host)
+        # the headless lumina-compatible driver (same includes and calls as Serial/lumina.cpp)
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", host, "-o", os.path.join(HERE, "lumina_headless"),
+                               os.path.join(host, "lumina_headless.cpp"), "-L", HERE, "-lrealtrace_host",
+                               "-lrealtrace_b200", "-Wl,-rpath,$ORIGIN"], cwd=host)
     return out
 
 

@@ -1,0 +1,414 @@
+// realtrace_host.cpp — host side of the drop-in: the reference's classes (realtrace_api.h) on top
+// of the C ABI.  Flattens World -> float32 arrays once per scene revision, commits (LBVH build on
+// the GPU) and renders whole frames into Camera::getBitmap().  No ray is traced on the CPU here.
+#include "realtrace_api.h"
+
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+
+#include "realtrace_b200.h"
+
+namespace rtb200 {
+
+struct Device {
+    rt_ctx* ctx = nullptr;
+    unsigned long committed_revision = 0;
+    rt_frame_stats stats;
+    std::vector<Object*> objects_at_commit;
+
+    Device() {
+        memset(&stats, 0, sizeof stats);
+        int rc = rt_create(&ctx, 0);
+        if (rc != RT_OK) throw std::runtime_error(std::string("realtrace_b200: ") + rt_last_error(nullptr));
+    }
+    ~Device() { if (ctx) rt_destroy(ctx); }
+    void check(int rc, const char* what) {
+        if (rc != RT_OK) throw std::runtime_error(std::string("realtrace_b200: ") + what + ": " + rt_last_error(ctx));
+    }
+
+    // World -> flat arrays -> rt_scene_* -> commit.  Object ids are objectList indices (world.h:34-37).
+    void sync(World& w) {
+        if (committed_revision == w.revision) return;
+        std::vector<float> tri_v, tri_rgb, sph, pln, cyl, lights;
+        std::vector<uint32_t> tri_m, tri_id, sph_m, sph_id, pln_m, pln_id, cyl_m, cyl_id;
+        std::vector<rt_material> mats;
+        std::map<const Material*, uint32_t> mat_index;
+        bool any_bary = false;
+        auto material_of = [&](const Material* m) {
+            auto it = mat_index.find(m);
+            if (it != mat_index.end()) return it->second;
+            rt_material r;
+            r.color[0] = (float)m->color.r; r.color[1] = (float)m->color.g; r.color[2] = (float)m->color.b;
+            r.ka = (float)m->ka; r.kd = (float)m->kd; r.ks = (float)m->ks; r.kr = (float)m->kr; r.kt = (float)m->kt;
+            r.eta = (float)m->eta;
+            r.flags = m->isBarycentric() ? RT_MATERIAL_BARYCENTRIC : 0u;
+            any_bary |= m->isBarycentric();
+            uint32_t id = (uint32_t)mats.size();
+            mats.push_back(r);
+            mat_index[m] = id;
+            return id;
+        };
+        auto push3 = [](std::vector<float>& dst, const Vector3D& v) { dst.push_back((float)v.X()); dst.push_back((float)v.Y()); dst.push_back((float)v.Z()); };
+        for (size_t i = 0; i < w.objectList.size(); i++) {
+            const Object* o = w.objectList[i];
+            uint32_t m = material_of(o->getMaterial());
+            switch (o->kind()) {
+                case Object::TRIANGLE: {
+                    const Triangle* t = static_cast<const Triangle*>(o);
+                    for (int k = 0; k < 3; k++) push3(tri_v, t->getVertex(k));
+                    tri_m.push_back(m); tri_id.push_back((uint32_t)i);
+                    if (o->getMaterial()->isBarycentric()) {
+                        const BarycentricMaterial* bm = static_cast<const BarycentricMaterial*>(o->getMaterial());
+                        for (int k = 0; k < 3; k++) { const Color& c = bm->vertexColor(k); tri_rgb.push_back((float)c.r); tri_rgb.push_back((float)c.g); tri_rgb.push_back((float)c.b); }
+                    } else {
+                        for (int k = 0; k < 9; k++) tri_rgb.push_back(0.0f);
+                    }
+                    break;
+                }
+                case Object::SPHERE: {
+                    const Sphere* s = static_cast<const Sphere*>(o);
+                    push3(sph, s->getPosition()); sph.push_back((float)s->getRadius());
+                    sph_m.push_back(m); sph_id.push_back((uint32_t)i);
+                    break;
+                }
+                case Object::PLANE: {
+                    const Plane* p = static_cast<const Plane*>(o);
+                    for (int k = 0; k < 4; k++) push3(pln, p->getCorner(k));
+                    pln_m.push_back(m); pln_id.push_back((uint32_t)i);
+                    break;
+                }
+                case Object::CYLINDER: {
+                    const Cylinder* c = static_cast<const Cylinder*>(o);
+                    push3(cyl, c->getPosition()); cyl.push_back((float)c->getRadius()); push3(cyl, c->getUp());
+                    cyl_m.push_back(m); cyl_id.push_back((uint32_t)i);
+                    break;
+                }
+            }
+        }
+        if (mats.empty()) { rt_material d; memset(&d, 0, sizeof d); mats.push_back(d); }
+        for (const LightSource* l : w.lightSourceList) {
+            push3(lights, l->getPosition());
+            Color c = l->getIntensity();
+            lights.push_back((float)c.r); lights.push_back((float)c.g); lights.push_back((float)c.b);
+        }
+        check(rt_scene_set_triangles(ctx, tri_v.data(), tri_m.data(), any_bary ? tri_rgb.data() : nullptr, tri_id.data(), (uint32_t)tri_m.size()), "set_triangles");
+        check(rt_scene_set_spheres(ctx, sph.data(), sph_m.data(), sph_id.data(), (uint32_t)sph_m.size()), "set_spheres");
+        check(rt_scene_set_planes(ctx, pln.data(), pln_m.data(), pln_id.data(), (uint32_t)pln_m.size()), "set_planes");
+        check(rt_scene_set_cylinders(ctx, cyl.data(), cyl_m.data(), cyl_id.data(), (uint32_t)cyl_m.size()), "set_cylinders");
+        check(rt_scene_set_materials(ctx, mats.data(), (uint32_t)mats.size()), "set_materials");
+        check(rt_scene_set_lights(ctx, lights.data(), (uint32_t)(lights.size() / 6)), "set_lights");
+        float amb[3] = {(float)w.ambient.r, (float)w.ambient.g, (float)w.ambient.b};
+        float bg[3] = {(float)w.background.r, (float)w.background.g, (float)w.background.b};
+        check(rt_scene_set_environment(ctx, amb, bg), "set_environment");
+        check(rt_scene_commit(ctx, RT_COMMIT_BUILD), "commit");
+        objects_at_commit = w.objectList;
+        committed_revision = w.revision;
+    }
+};
+
+static Device& device_of(World& w, Device*& slot) {
+    if (!slot) slot = new Device;
+    slot->sync(w);
+    return *slot;
+}
+
+}  // namespace rtb200
+
+// ---- Material ------------------------------------------------------------------------------------
+Color Material::shade(const Ray&, const bool) const { return color; }                      // material.cpp:5-8
+
+static double det3(const Vector3D& a, const Vector3D& b, const Vector3D& c) {              // utilities.cpp:17-22
+    return a.X() * (b.Y() * c.Z() - c.Y() * b.Z()) - a.Y() * (b.X() * c.Z() - c.X() * b.Z()) + a.Z() * (b.X() * c.Y() - c.X() * b.Y());
+}
+Color BarycentricMaterial::shade(const Ray& in, const bool) const {                         // material.cpp:10-22
+    double A = det3(vertexA - vertexB, vertexA - vertexC, in.getDirection());
+    if (std::fabs(A) < 1e-7) return Color(0.0);
+    double beta = det3(vertexA - in.getOrigin(), vertexA - vertexC, in.getDirection()) / A;
+    double gamma = det3(vertexA - vertexB, vertexA - in.getOrigin(), in.getDirection()) / A;
+    if (!(beta > 0.0 && gamma > 0.0 && beta + gamma < 1.0)) return Color(0.0, 0.0, 0.0);
+    double alpha = 1.0 - (beta + gamma);
+    return alpha * colors[0] + beta * colors[1] + gamma * colors[2];
+}
+
+bool Object::intersect(Ray&) const {
+    throw std::logic_error("realtrace_b200: per-object CPU intersection is not part of the GPU core; use World::firstIntersection");
+}
+
+BBox Triangle::getWorldBound() {                                                            // triangle.cpp:31-40
+    BBox b;
+    for (int axis = 0; axis < 3; axis++)
+        for (int v = 0; v < 3; v++) {
+            double x = getVertex(v).e[axis];
+            if (x < b.axis_min[axis]) b.axis_min[axis] = x;
+            if (x > b.axis_max[axis]) b.axis_max[axis] = x;
+        }
+    return b;
+}
+
+// ---- World ---------------------------------------------------------------------------------------
+World::~World() { delete dev; }
+
+float World::firstIntersection(Ray& ray) {                                                  // world.cpp:5-17
+    rtb200::Device& d = rtb200::device_of(*this, dev);
+    Vector3D o = ray.getOrigin(), dir = ray.getDirection();
+    float r[6] = {(float)o.X(), (float)o.Y(), (float)o.Z(), (float)dir.X(), (float)dir.Y(), (float)dir.Z()};
+    int32_t prim = -1;
+    float t = FLT_MAX;
+    d.check(rt_trace_rays(d.ctx, r, 1, 0, &prim, &t), "trace_rays");
+    if (prim >= 0 && (size_t)prim < d.objects_at_commit.size() && ray.setParameter(t, d.objects_at_commit[prim])) ray.setIdx(prim);
+    return ray.getParameter();
+}
+
+Color World::shade_ray(Ray ray) {                                                           // world.cpp:32-111
+    if (ray.getLevel() > max_depth) return background;
+    rtb200::Device& d = rtb200::device_of(*this, dev);
+    Vector3D o = ray.getOrigin(), dir = ray.getDirection();
+    float r[6] = {(float)o.X(), (float)o.Y(), (float)o.Z(), (float)dir.X(), (float)dir.Y(), (float)dir.Z()};
+    float rgb[3] = {0, 0, 0};
+    d.check(rt_shade_rays(d.ctx, r, 1, max_depth, 0, rgb), "shade_rays");
+    return Color(rgb[0], rgb[1], rgb[2]);
+}
+
+// ---- Camera (camera.cpp:4-52) --------------------------------------------------------------------
+Camera::Camera(const Vector3D& _pos, const Vector3D& _target, const Vector3D& _up, float _fovy, int _w, int _h)
+    : position(_pos), target(_target), up(_up), width(_w), height(_h), fovy(_fovy) {
+    up.normalize();
+    line_of_sight = target - position;
+    w = -line_of_sight; w.normalize();
+    u = crossProduct(up, w); u.normalize();
+    v = crossProduct(w, u); v.normalize();
+    bitmap = new unsigned char[(size_t)width * height * 3];
+    memset(bitmap, 0, (size_t)width * height * 3);
+    focalHeight = 1.0f;
+    aspect = float(width) / float(height);
+    focalWidth = focalHeight * aspect;
+    focalDistance = focalHeight / (2.0 * tan(fovy * M_PI / (180.0 * 2.0)));
+}
+Camera::~Camera() { delete[] bitmap; }
+const Vector3D Camera::get_ray_direction(const int i, const int j) const {
+    Vector3D dir(0.0, 0.0, 0.0);
+    dir += -w * (double)focalDistance;
+    float xw = aspect * (i - width / 2.0 + 0.5) / width;
+    float yw = (j - height / 2.0 + 0.5) / height;
+    dir += u * (double)xw;
+    dir += v * (double)yw;
+    dir.normalize();
+    return dir;
+}
+void Camera::drawPixel(int i, int j, Color c) {
+    size_t index = ((size_t)i + (size_t)j * width) * 3;
+    bitmap[index + 0] = (unsigned char)(255 * c.r);
+    bitmap[index + 1] = (unsigned char)(255 * c.g);
+    bitmap[index + 2] = (unsigned char)(255 * c.b);
+}
+
+// ---- RenderEngine --------------------------------------------------------------------------------
+void RenderEngine::render() {
+    rtb200::Device& d = rtb200::device_of(*world, world->dev);
+    rt_camera c;
+    for (int k = 0; k < 3; k++) {
+        c.pos[k] = (float)camera->position.e[k];
+        c.u[k] = (float)camera->u.e[k]; c.v[k] = (float)camera->v.e[k]; c.w[k] = (float)camera->w.e[k];
+    }
+    c.focal_distance = camera->focalDistance;
+    c.aspect = camera->aspect;
+    c.width = camera->width; c.height = camera->height;
+    rt_render_params p;
+    memset(&p, 0, sizeof p);
+    p.max_depth = world->getMaxDepth();
+    p.world_size = 1;
+    d.check(rt_render(d.ctx, &c, &p, camera->bitmap, nullptr, &d.stats), "render");
+}
+
+void RenderEngine::frameStats(unsigned long long& primary, unsigned long long& shadow, unsigned long long& secondary, float& ms_device) const {
+    primary = shadow = secondary = 0; ms_device = 0;
+    if (!world->dev) return;
+    const rt_frame_stats& s = world->dev->stats;
+    primary = s.rays_primary; shadow = s.rays_shadow; secondary = s.rays_secondary; ms_device = s.ms_device;
+}
+
+// ---- minimal PNG reader (8-bit RGB / RGBA, non-interlaced) for the texture path of the loader.  The
+// reference goes through DevIL (lumina.cpp:209-221), which is not vendored; see DESIGN.md §2. ----------
+namespace {
+struct Image { int w = 0, h = 0, ch = 0; std::vector<unsigned char> px; };
+
+bool read_png(const std::string& path, Image& img) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::vector<unsigned char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (buf.size() < 8 || memcmp(buf.data(), sig, 8)) return false;
+    auto be32 = [&](size_t o) { return (uint32_t)buf[o] << 24 | (uint32_t)buf[o + 1] << 16 | (uint32_t)buf[o + 2] << 8 | buf[o + 3]; };
+    std::vector<unsigned char> idat;
+    int bit_depth = 0, colour = 0, interlace = 0;
+    for (size_t o = 8; o + 12 <= buf.size();) {
+        uint32_t len = be32(o);
+        std::string type((const char*)&buf[o + 4], 4);
+        if (o + 12 + len > buf.size()) return false;
+        if (type == "IHDR") { img.w = (int)be32(o + 8); img.h = (int)be32(o + 12); bit_depth = buf[o + 16]; colour = buf[o + 17]; interlace = buf[o + 20]; }
+        else if (type == "IDAT") idat.insert(idat.end(), buf.begin() + o + 8, buf.begin() + o + 8 + len);
+        else if (type == "IEND") break;
+        o += 12 + len;
+    }
+    if (bit_depth != 8 || interlace != 0 || (colour != 2 && colour != 6)) return false;
+    img.ch = colour == 2 ? 3 : 4;
+    size_t stride = (size_t)img.w * img.ch;
+    std::vector<unsigned char> raw((stride + 1) * img.h);
+    uLongf out_len = raw.size();
+    if (uncompress(raw.data(), &out_len, idat.data(), idat.size()) != Z_OK || out_len != raw.size()) return false;
+    img.px.assign(stride * img.h, 0);
+    int bpp = img.ch;
+    for (int y = 0; y < img.h; y++) {
+        const unsigned char* in = &raw[(stride + 1) * y];
+        unsigned char* cur = &img.px[stride * y];
+        const unsigned char* prev = y ? &img.px[stride * (y - 1)] : nullptr;
+        int filter = in[0];
+        for (size_t x = 0; x < stride; x++) {
+            int a = x >= (size_t)bpp ? cur[x - bpp] : 0, b = prev ? prev[x] : 0, c = (prev && x >= (size_t)bpp) ? prev[x - bpp] : 0;
+            int v = in[1 + x];
+            switch (filter) {
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) / 2; break;
+                case 4: { int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+                default: break;
+            }
+            cur[x] = (unsigned char)v;
+        }
+    }
+    return true;
+}
+
+// "normalised" fetch of realtrace_b200/objio.py: texel/255, u -> column, v -> row from the bottom.
+Color texel(const Image& im, double u, double v) {
+    int col = (int)std::floor(u * im.w), row = (int)std::floor((1.0 - v) * im.h);
+    if (col < 0) col = 0; if (col >= im.w) col = im.w - 1;
+    if (row < 0) row = 0; if (row >= im.h) row = im.h - 1;
+    const unsigned char* p = &im.px[((size_t)row * im.w + col) * im.ch];
+    return Color((double)(float)(p[0] / 255.0f), (double)(float)(p[1] / 255.0f), (double)(float)(p[2] / 255.0f));
+}
+}  // namespace
+
+void init_material_from_obj(Material* m) {                                                  // lumina.cpp:163-172
+    m->color = Color(0.8, 0.1, 0.0);
+    m->ka = 0.2; m->kd = 0.9; m->ks = 0.4; m->kr = 0.4; m->kt = 0.0; m->eta = 3.0; m->n = 128;
+}
+
+void load_image_from_obj(World* world, std::string file_name, std::string texture_file_name, std::string, int max_faces) {
+    std::ifstream is(file_name);
+    if (!is.is_open()) throw std::runtime_error("load_image_from_obj: could not open " + file_name);   // lumina.cpp:197-200 exits
+    Image tex;
+    bool has_texture = false;
+    if (!texture_file_name.empty()) {
+        if (!read_png(texture_file_name, tex)) throw std::runtime_error("load_image_from_obj: cannot decode " + texture_file_name);
+        has_texture = true;
+    }
+    const double SCALING_FACTOR = 15;                                                       // lumina.cpp:43
+    std::vector<Vector3D> vertices;
+    std::vector<std::pair<double, double>> texture_vertices;
+    std::vector<Triangle*> all_triangles;
+    std::string c;
+    double v[3];
+    while (is >> c) {                                                                       // lumina.cpp:234-287
+        if (c == "f") {
+            std::vector<int> idx[3];
+            std::string data, token;
+            for (int i = 0; i < 3; i++) {
+                is >> data;
+                std::stringstream ss(data);
+                while (getline(ss, token, '/')) idx[i].push_back(token.empty() ? 0 : stoi(token));
+            }
+            if (max_faces >= 0 && (int)all_triangles.size() >= max_faces) continue;
+            const Vector3D &a = vertices[idx[0][0] - 1], &b = vertices[idx[1][0] - 1], &cc = vertices[idx[2][0] - 1];
+            Material* m;
+            if (has_texture && idx[0].size() >= 2 && idx[1].size() >= 2 && idx[2].size() >= 2) {
+                auto tv = [&](int k) { const auto& p = texture_vertices[idx[k][1] - 1]; return texel(tex, p.first, p.second); };
+                m = new BarycentricMaterial(world, a, b, cc, tv(0), tv(1), tv(2));
+                // the textured workloads keep the loader's coefficients so that depth > 0 has mirror bounces
+                m->ka = 0.2; m->kd = 0.9; m->ks = 0.4; m->kr = 0.4; m->kt = 0.0; m->eta = 3.0;
+            } else {
+                m = new Material(world);
+                init_material_from_obj(m);
+            }
+            Triangle* t = new Triangle(a, b, cc, m);
+            all_triangles.push_back(t);
+            world->addObject(t);
+        } else if (c == "v") {
+            is >> v[0] >> v[1] >> v[2];
+            vertices.push_back(Vector3D(v[0] * SCALING_FACTOR, v[1] * SCALING_FACTOR, v[2] * SCALING_FACTOR));
+        } else if (c == "vt") {
+            is >> v[0] >> v[1];
+            texture_vertices.push_back(std::make_pair(v[0], v[1]));
+        } else {
+            getline(is, c);
+        }
+    }
+    world->uniform_grid = UniformGrid(all_triangles);                                       // lumina.cpp:289 (a no-op shim here)
+}
+
+// ---- demo entry points for the tests: scenes built through the class API exactly as
+// Serial/lumina.cpp:302-370 does, rendered with RenderEngine. ------------------------------------------
+extern "C" int rt_host_demo(const char* which, const char* assets_dir, int width, int height, int depth,
+                            unsigned char* rgb_out, unsigned long long* rays3, float* ms_device, char* err, int err_len) {
+    try {
+        std::string name(which), assets(assets_dir);
+        Vector3D camera_position(60, 60, 0), camera_target(0, 0, 0), camera_up(0, 1, 0);      // lumina.cpp:302-305
+        if (name == "analytic_close") camera_position = Vector3D(0, 10, 30);
+        Camera* camera = new Camera(camera_position, camera_target, camera_up, 45, width, height);
+        World* world = new World;
+        world->setAmbient(Color(1));                                                          // :309
+        world->setBackground(Color(0.1, 0.3, 0.6));                                           // :310
+        world->addLight(new PointLightSource(world, Vector3D(0, 30, 30), Color(0.5, 1, 1)));  // :360-362
+        if (name == "analytic" || name == "analytic_close") {                                 // the literal at :312-356
+            Material* m = new Material(world);
+            m->color = Color(0.1, 0.7, 0.0); m->ka = 0.2; m->kd = 0.9; m->ks = 0.4; m->kr = 1.0; m->kt = 0.0; m->eta = 1.0;
+            Material* m1 = new Material(world);
+            m1->color = Color(0.8, 0.1, 0.0); m1->ka = 0.2; m1->kd = 0.9; m1->ks = 0.4; m1->kr = 0.0; m1->kt = 0.0; m1->eta = 1.0;
+            Material* m2 = new Material(world);
+            m2->color = Color(1.0, 1.0, 1.0); m2->ka = 0.4; m2->kd = 0.9; m2->ks = 0.4; m2->kr = 0.1; m2->kt = 0.8; m2->eta = 2.0;
+            Material* floorMat = new Material(world);
+            floorMat->color = Color(0.5, 0.5, 0.5); floorMat->ka = 0.1; floorMat->kd = 0.9; floorMat->ks = 0.2; floorMat->kt = 0.0; floorMat->kr = 0.5; floorMat->eta = 1.0;
+            world->addObject(new Sphere(Vector3D(0, 0, 0), 3, m));
+            world->addObject(new Sphere(Vector3D(4, 0, 4), 3, m1));
+            world->addObject(new Plane(Vector3D(10, -3, 10), Vector3D(-10, -3, 10), Vector3D(-10, -3, -10), Vector3D(10, -3, -10), floorMat));
+            world->addObject(new Cylinder(Vector3D(-7, 0, -3), 1, Vector3D(0, 0, 1), m2));
+            load_image_from_obj(world, assets + "/tetrahedron.obj");
+        } else if (name == "bob_textured") {
+            world->addLight(new PointLightSource(world, Vector3D(0, 10, 0), Color(1, 1, 1)));  // light2, :361
+            load_image_from_obj(world, assets + "/bob_tri.obj", assets + "/bob_diffuse.png");
+        } else if (name == "lumina_default") {
+            load_image_from_obj(world, assets + "/bob_tri.obj", "", "", 2000);                 // :366 with the :266 cap
+        } else {
+            throw std::runtime_error("unknown demo scene " + name);
+        }
+        RenderEngine* engine = new RenderEngine(world, camera);                               // :370
+        engine->setMaxDepth(depth);
+        while (!engine->renderLoop()) {}                                                      // :464
+        memcpy(rgb_out, camera->getBitmap(), (size_t)width * height * 3);
+        float ms = 0;
+        unsigned long long a = 0, b = 0, c = 0;
+        engine->frameStats(a, b, c, ms);
+        if (rays3) { rays3[0] = a; rays3[1] = b; rays3[2] = c; }
+        if (ms_device) *ms_device = ms;
+        // second frame: the scene is resident, only the camera changes nothing -> identical bitmap
+        engine->render();
+        int same = memcmp(rgb_out, camera->getBitmap(), (size_t)width * height * 3) == 0;
+        // one-ray queries through World (firstIntersection / shade_ray)
+        Ray probe(camera->get_position(), camera->get_ray_direction(width / 2, height / 2));
+        world->firstIntersection(probe);
+        delete engine;
+        for (Object* o : world->getObjectList()) delete o;     // (materials and lights leak like in the reference)
+        delete world;
+        delete camera;
+        return same ? 0 : 1;
+    } catch (const std::exception& e) {
+        if (err && err_len > 0) { strncpy(err, e.what(), err_len - 1); err[err_len - 1] = 0; }
+        return -1;
+    }
+}
