@@ -175,47 +175,84 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     _, owned, tile_bytes = api.tile_layout(W, H, 0, 0, rank, world)
     max_owned = max(api.tile_layout(W, H, 0, 0, r, world)[1] for r in range(world))
-    frame = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
-    packed = torch.zeros(max_owned * tile_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
-    gathered = None
-    if world > 1 and rank == 0:
-        gathered = [torch.zeros(max_owned * tile_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+    frame = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev) if world == 1 else None
+    frame_ptr = frame.data_ptr() if world == 1 else None
+    tick = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    # ---- N > 1: frame assembly.  Preferred: rank 0 owns the frame in a CUDA-IPC buffer that every
+    # rank maps over NVLink; each rank's resolve kernel stores its tiles straight into it and one tiny
+    # all-reduce is the completion barrier.  Fallback (--assemble gather, or IPC unavailable): packed
+    # tiles + NCCL gather + scatter kernel on rank 0.
+    assemble = "single"
+    packed = gathered = None
+    if world > 1:
+        assemble = args.assemble
+        if assemble == "p2p":
+            ok = 1
+            try:
+                hbuf = torch.zeros(64, dtype=torch.uint8, device=dev)
+                if rank == 0:
+                    frame_ptr, handle = ctx.shared_buffer_create(H * W * 3)
+                    hbuf.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+                torch.distributed.broadcast(hbuf, 0)
+                if rank != 0:
+                    frame_ptr = ctx.shared_buffer_open(hbuf.cpu().numpy().tobytes())
+            except Exception as e:   # noqa: BLE001 — any failure means "use the gather path"
+                print(f"[bench rank {rank}] CUDA IPC unavailable ({e}); falling back to gather", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            if int(flag[0]) == 0:
+                assemble = "gather"
+        if assemble == "gather":
+            packed = torch.zeros(max_owned * tile_bytes, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                gathered = [torch.zeros(max_owned * tile_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+                frame = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
+                frame_ptr = frame.data_ptr()
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        """One frame with everything resident: render (+ gather + assemble at N > 1)."""
+    def step_device(want_stats=False):
+        """One frame with everything resident: render (+ assembly at N > 1).  Without stats the call only
+        enqueues work on the stream."""
         if world == 1:
-            return ctx.render_device(cam, depth, frame.data_ptr())
-        st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES)
+            return ctx.render_device(cam, depth, frame_ptr, want_stats=want_stats)
+        if assemble == "p2p":
+            st = ctx.render_device(cam, depth, frame_ptr, rank=rank, world=world, want_stats=want_stats)
+            torch.distributed.all_reduce(tick)          # completion barrier: all tiles are in rank 0's frame
+            return st
+        st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES,
+                               want_stats=want_stats)
         multigpu.gather_packed(packed, rank, world, gathered)
         if rank == 0:
             for r in range(world):
-                ctx.assemble_tiles(gathered[r].data_ptr(), r, world, W, H, frame.data_ptr())
+                ctx.assemble_tiles(gathered[r].data_ptr(), r, world, W, H, frame_ptr)
         return st
 
-    # ---- value: device-resident frames, CUDA events around every step, L2 flushed between steps
+    # ---- value: device-resident frames, CUDA events around every step, L2 flushed between steps.
+    # Warm-up frames carry statistics (ray counts, per-kernel times); timed frames are enqueued
+    # asynchronously and only the final barrier synchronises.
     sampler = ClockSampler(dist_ctx["local_rank"])
     sampler.start()
-    for _ in range(warmup):
-        st = step_device()
+    stats = [step_device(True) for _ in range(max(warmup, 3))]
     barrier()
     sampler.t_begin = time.perf_counter()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    stats = []
     for k in range(steps):
         flush.fill_(k & 0xff)
         evs[k][0].record(stream)
-        stats.append(step_device())
+        step_device(False)
         evs[k][1].record(stream)
     barrier()
+    ctx.synchronize()                                   # raises if any timed frame flagged an error
     sampler.t_end = time.perf_counter()
     ms = sum(a.elapsed_time(b) for a, b in evs)
-    rays_local = sum(total_rays(s) for s in stats)
-    launches = sum(s["kernel_launches"] for s in stats) + (world if (world > 1 and rank == 0) else 0) * steps
+    rays_local = total_rays(stats[-1]) * steps          # static scene + camera: every frame casts the same rays
+    launches = stats[-1]["kernel_launches"] * steps + ((world if rank == 0 else 0) * steps if assemble == "gather" else 0)
     if world > 1:
         t = torch.tensor([ms, float(rays_local), float(launches)], dtype=torch.float64, device=dev)
         tmax = t.clone()
@@ -233,10 +270,9 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     def step_e2e():
         if world == 1:
             return ctx.render(cam, depth, out=host_np)[3]
-        st = step_device()
+        st = step_device(True)
         if rank == 0:
-            host_frame.copy_(frame, non_blocking=True)
-            torch.cuda.synchronize()
+            ctx.download(frame_ptr, host_np)            # waits for the barrier all-reduce, then D2H
         return st
 
     for _ in range(max(1, warmup // 2)):
@@ -259,21 +295,29 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
 
     sampler.stop()
     out = {"value": value, "ms_per_step": ms / steps, "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
-           "launches": launches, "clocks": sampler.summary(), "desc": desc, "cam": cam, "depth": depth,
+           "launches": launches, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "cam": cam, "depth": depth,
            "scene": scene, "build": bstats, "commit_s": commit_s, "last": stats[-1], "rays_per_frame": rays_total / steps}
 
     # ---- roofline of the dominant kernel + work counts (single GPU, rank 0)
     if world == 1:
-        cnt = ctx.render_device(cam, depth, frame.data_ptr(), flags=api.FLAG_COUNT_WORK)
+        cnt = ctx.render_device(cam, depth, frame_ptr, flags=api.FLAG_COUNT_WORK)
         n_rays = total_rays(cnt)
+        n_near = cnt["rays_primary"] + cnt["rays_secondary"]
         ms_k = {"k_traverse<primary> (nearest hit)": np.mean([s["ms_trace"] for s in stats]),
                 "k_traverse<shadow> (any hit)": np.mean([s["ms_shadow"] for s in stats]),
                 "k_shade<primary>": np.mean([s["ms_shade"] for s in stats]),
                 "bounce waves (k_traverse + k_shade)": np.mean([s["ms_secondary"] for s in stats]),
                 "k_resolve": np.mean([s["ms_resolve"] for s in stats])}
         out["kernel_ms"] = {k: float(v) for k, v in ms_k.items()}
-        out["work"] = {"node_visits_per_ray": cnt["node_visits"] / n_rays, "tri_tests_per_ray": cnt["tri_tests"] / n_rays,
-                       "node_visits": cnt["node_visits"], "tri_tests": cnt["tri_tests"], "rays": n_rays}
+        nodes_all = cnt["node_visits"] + cnt["shadow_node_visits"]
+        tris_all = cnt["tri_tests"] + cnt["shadow_tri_tests"]
+        out["work"] = {"node_visits_per_ray": nodes_all / n_rays, "tri_tests_per_ray": tris_all / n_rays,
+                       "node_visits": nodes_all, "tri_tests": tris_all, "rays": n_rays,
+                       "nearest": {"rays": n_near, "node_visits_per_ray": cnt["node_visits"] / max(n_near, 1),
+                                   "tri_tests_per_ray": cnt["tri_tests"] / max(n_near, 1)},
+                       "shadow": {"rays": cnt["rays_shadow"],
+                                  "node_visits_per_ray": cnt["shadow_node_visits"] / max(cnt["rays_shadow"], 1),
+                                  "tri_tests_per_ray": cnt["shadow_tri_tests"] / max(cnt["rays_shadow"], 1)}}
         # cold e2e: scene upload + LBVH build + one frame to the host
         t0 = time.perf_counter()
         ctx.set_scene(scene)
@@ -308,7 +352,10 @@ def run_gpu_arm(args):
             "config": {"workload": args.workload, "description": main["desc"], "width": cam.width, "height": cam.height,
                        "max_depth": depth, "triangles": int(len(scene.tri_v)), "lights": int(len(scene.lights)),
                        "rays_per_frame": main["rays_per_frame"],
-                       "parallelism": f"{world} GPU(s), interleaved 64x32 tiles, scene replicated, NCCL gather",
+                       "parallelism": (f"{world} GPUs, interleaved 64x32 tiles, scene replicated, frame assembly: "
+                                       + {"p2p": "resolve kernels store into rank 0's frame over NVLink (CUDA IPC) + all-reduce barrier",
+                                          "gather": "packed tiles + NCCL gather + scatter kernel"}[main["assemble"]])
+                       if world > 1 else "1 GPU",
                        "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"},
             "e2e": {"value": main["e2e_value"], "unit": "Mrays/s", "ms_per_step": main["e2e_ms_per_step"],
                     "h2d_bytes_per_step": 64 + 24, "d2h_bytes_per_step": cam.width * cam.height * 3,
@@ -374,6 +421,7 @@ def main():
     ap.add_argument("--workload", default="synth1m")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--assemble", default="p2p", choices=["p2p", "gather"], help="N > 1 frame assembly")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

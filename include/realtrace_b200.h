@@ -160,7 +160,19 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint
 int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, void* rgb_out_dev,
                      const rt_aux_out* aux_dev, rt_frame_stats* stats);
 
-/* ---- multi-GPU tile helpers (one process per GPU; the gather itself is NCCL, outside)       */
+/* rt_render_device with stats == NULL only enqueues the frame on the context's stream and returns;
+ * rt_synchronize waits for it and reports errors raised by the kernels meanwhile.              */
+int rt_synchronize(rt_ctx* ctx);
+
+/* ---- multi-GPU (one process per GPU)                                                         */
+/* A device buffer other processes on the node can map (CUDA IPC over NVLink peer access): the
+ * owner creates it and publishes the 64-byte handle; peers open it and pass the mapped pointer as
+ * rgb_out_dev of rt_render_device, so that their resolve kernel stores its tiles straight into the
+ * owner's frame.  rt_download copies device memory of this context to the host.                */
+int rt_shared_buffer_create(rt_ctx* ctx, uint64_t bytes, void** dev_ptr, unsigned char handle[64]);
+int rt_shared_buffer_open(rt_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
+int rt_download(rt_ctx* ctx, const void* dev_ptr, void* host, uint64_t bytes);
+/* tile helpers for the gather-based assembly (the gather itself is NCCL, outside)               */
 /* number of tiles in the frame / owned by `rank`, and bytes of one packed tile                  */
 int rt_tile_layout(int32_t width, int32_t height, int32_t tile_w, int32_t tile_h, int32_t rank, int32_t world_size,
                    uint32_t* tiles_total, uint32_t* tiles_owned, uint32_t* tile_bytes);

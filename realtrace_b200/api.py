@@ -61,7 +61,7 @@ ABI_SYMBOLS = [
     "rt_scene_set_planes", "rt_scene_set_cylinders", "rt_scene_set_materials", "rt_scene_set_lights",
     "rt_scene_set_environment", "rt_scene_commit", "rt_scene_update_vertices", "rt_scene_build_stats", "rt_render",
     "rt_render_device", "rt_tile_layout", "rt_assemble_tiles", "rt_trace_rays", "rt_shade_rays", "rt_bvh_download",
-    "rt_debug_sort_pairs",
+    "rt_debug_sort_pairs", "rt_synchronize", "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_download",
 ]
 
 _lib = None
@@ -99,6 +99,10 @@ def load_library():
     lib.rt_shade_rays.argtypes = [vp, fp, C.c_uint32, C.c_int32, C.c_uint32, vp]
     lib.rt_bvh_download.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rt_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.rt_synchronize.argtypes = [vp]
+    lib.rt_shared_buffer_create.argtypes = [vp, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.rt_shared_buffer_open.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.rt_download.argtypes = [vp, vp, vp, C.c_uint64]
     for n in ABI_SYMBOLS:
         if n != "rt_last_error":
             getattr(lib, n).restype = C.c_int
@@ -234,6 +238,24 @@ class Context:
         self._check(self.lib.rt_render_device(self.h, C.byref(c), C.byref(p), rgb_dev_ptr, None,
                                               C.byref(st) if want_stats else None))
         return st.as_dict()
+
+    def synchronize(self):
+        self._check(self.lib.rt_synchronize(self.h))
+
+    def shared_buffer_create(self, nbytes):
+        """-> (device pointer, 64-byte IPC handle) of a buffer peers on this node can map."""
+        p = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self.lib.rt_shared_buffer_create(self.h, nbytes, C.byref(p), handle))
+        return p.value, handle.raw
+
+    def shared_buffer_open(self, handle):
+        p = C.c_void_p()
+        self._check(self.lib.rt_shared_buffer_open(self.h, bytes(handle), C.byref(p)))
+        return p.value
+
+    def download(self, dev_ptr, host_array):
+        self._check(self.lib.rt_download(self.h, dev_ptr, host_array.ctypes.data, host_array.nbytes))
 
     def assemble_tiles(self, packed_dev_ptr, src_rank, world, width, height, frame_dev_ptr, tile=(0, 0)):
         self._check(self.lib.rt_assemble_tiles(self.h, packed_dev_ptr, src_rank, world, width, height, tile[0], tile[1],

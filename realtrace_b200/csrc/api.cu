@@ -91,6 +91,9 @@ int rt_destroy(rt_ctx* ctx) {
         if (ev) cudaEventDestroy(ev);
     if (ctx->h_waves) cudaFreeHost(ctx->h_waves);
     if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
+    if (ctx->h_sticky) cudaFreeHost(ctx->h_sticky);
+    for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
+    for (void* p : ctx->ipc_created) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return RT_OK;
@@ -297,6 +300,46 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint
             RT_CUDA(cudaMemcpyAsync(aux->t, ctx->d_aux_t.p, npix * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         RT_CUDA(cudaStreamSynchronize(ctx->stream));
         if (deferred.code != RT_OK) throw deferred;
+    });
+}
+
+int rt_synchronize(rt_ctx* ctx) {
+    return guarded(ctx, [&] { rt_sync_and_check(ctx); });
+}
+
+int rt_shared_buffer_create(rt_ctx* ctx, uint64_t bytes, void** dev_ptr, unsigned char handle[64]) {
+    return guarded(ctx, [&] {
+        need(dev_ptr && handle && bytes > 0, "rt_shared_buffer_create: bad arguments");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        void* p = nullptr;
+        RT_CUDA(cudaMalloc(&p, bytes));
+        RT_CUDA(cudaMemset(p, 0, bytes));
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) { cudaFree(p); throw RtError{RT_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)}; }
+        memcpy(handle, &h, 64);
+        ctx->ipc_created.push_back(p);
+        *dev_ptr = p;
+    });
+}
+
+int rt_shared_buffer_open(rt_ctx* ctx, const unsigned char handle[64], void** dev_ptr) {
+    return guarded(ctx, [&] {
+        need(dev_ptr && handle, "rt_shared_buffer_open: bad arguments");
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, 64);
+        void* p = nullptr;
+        RT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_opened.push_back(p);
+        *dev_ptr = p;
+    });
+}
+
+int rt_download(rt_ctx* ctx, const void* dev_ptr, void* host, uint64_t bytes) {
+    return guarded(ctx, [&] {
+        need(dev_ptr && host, "rt_download: NULL buffer");
+        RT_CUDA(cudaMemcpyAsync(host, dev_ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }
 

@@ -77,6 +77,10 @@ __device__ __forceinline__ void primary_ray(const CamDev& c, int i, int j, f3& o
     o = mk3((float)c.pos[0], (float)c.pos[1], (float)c.pos[2]);
 }
 
+// FIRST: the wave-0 contribution of a pixel (exactly one per in-frame pixel: the primary miss in
+// k_traverse or the primary hit in k_shade) is a plain store, which also initialises the
+// accumulator — no memset of the frame; every later contribution is an integer atomic add.
+template <bool FIRST>
 __device__ __forceinline__ void accumulate(long long* accum, uint32_t pix, f3 c) {
     const float scale = 4294967296.0f, lim = 1048576.0f;
     float v[3] = {c.x, c.y, c.z};
@@ -86,7 +90,8 @@ __device__ __forceinline__ void accumulate(long long* accum, uint32_t pix, f3 c)
         if (!(x == x)) x = 0.0f;                       // NaN -> 0
         x = fminf(fmaxf(x, -lim), lim);
         long long q = __float2ll_rn(x * scale);
-        if (q) atomicAdd((unsigned long long*)(accum + 3 * (size_t)pix + k), (unsigned long long)q);
+        if (FIRST) accum[3 * (size_t)pix + k] = q;
+        else if (q) atomicAdd((unsigned long long*)(accum + 3 * (size_t)pix + k), (unsigned long long)q);
     }
 }
 
@@ -109,6 +114,7 @@ struct TravArgs {
     WaveCounters* wave;
     long long* accum;
     FrameCounters* fc;
+    uint32_t* sticky;         // error bits that survive until the next synchronising call
     int32_t* aux_prim;
     float* aux_t;
     uint32_t brute;
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
                     a.aux_prim[at] = id;
                     if (a.aux_t) a.aux_t[at] = found ? hit.t : RT_FLT_MAX;
                 }
-                if (!found) accumulate(a.accum, pix, w * bg);      // world.cpp:110
+                if (!found) accumulate<MODE == MODE_PRIMARY>(a.accum, pix, w * bg);      // world.cpp:110
             }
             active = false;
         }
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
             atomicAdd(&a.fc->tri_tests[ANY ? 1 : 0], (unsigned long long)nt);
         }
     }
-    if (__any_sync(FULL, overflow) && lane == 0) atomicOr(&a.wave->flags, 2u);
+    if (__any_sync(FULL, overflow) && lane == 0) atomicOr(a.sticky, 2u);
 }
 
 struct ShadeArgs {
@@ -300,6 +306,7 @@ struct ShadeArgs {
     WaveCounters* wave;
     WaveCounters* next;
     long long* accum;
+    uint32_t* sticky;
     uint32_t cap;
     int max_depth;
 };
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
             uint32_t li = 0;
             auto any_hit = [&](f3, f3) -> bool { return a.occl[(size_t)(li++) * n + pos] != 0; };
             shade_hit(a.s, o, d, level, h, a.max_depth, any_hit, out);
-            accumulate(a.accum, pix, w * (out.local + out.bg_weight * bg));
+            accumulate<PRIMARY>(a.accum, pix, w * (out.local + out.bg_weight * bg));
         }
         // append children: exclusive prefix over the warp, one atomic
         uint32_t k = valid ? (uint32_t)out.n_children : 0u;
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
             }
         }
     }
-    if (__any_sync(0xffffffffu, qfull) && lane == 0) atomicOr(&a.wave->flags, 1u);
+    if (__any_sync(0xffffffffu, qfull) && lane == 0) atomicOr(a.sticky, 1u);
 }
 
 // Color::clamp + Camera::drawPixel (color.cpp:19-28, camera.cpp:46-52): truncating 8-bit conversion.
@@ -600,6 +607,19 @@ WaveResult run_bounce_waves(rt_ctx* c, const TravArgs& ta, const ShadeArgs& sa, 
 
 }  // namespace
 
+// Waits for the context's stream and turns the sticky device error word into an exception.
+void rt_sync_and_check(rt_ctx* c) {
+    cudaStream_t st = c->stream;
+    RT_CUDA(cudaMemcpyAsync(c->h_sticky, c->d_sticky.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    uint32_t fl = *c->h_sticky;
+    if (fl) {
+        RT_CUDA(cudaMemsetAsync(c->d_sticky.p, 0, sizeof(uint32_t), st));
+        if (fl & 1u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow: a wave spawned more rays than the queue holds"};
+        throw RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow (BVH deeper than RT_STACK_SIZE)"};
+    }
+}
+
 void rt_render_init(rt_ctx* c) {
     auto lo = [](int a, int b) { return a < b ? a : b; };
     c->trace_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false>, TRAV_TPB, c->sm_count),
@@ -611,6 +631,9 @@ void rt_render_init(rt_ctx* c) {
     c->d_frame.reserve(1);
     RT_CUDA(cudaMallocHost((void**)&c->h_waves, RT_WAVE_SLOTS * sizeof(WaveCounters)));
     RT_CUDA(cudaMallocHost((void**)&c->h_frame, sizeof(FrameCounters)));
+    RT_CUDA(cudaMallocHost((void**)&c->h_sticky, sizeof(uint32_t)));
+    c->d_sticky.reserve(1);
+    RT_CUDA(cudaMemset(c->d_sticky.p, 0, sizeof(uint32_t)));
 }
 
 void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p, void* rgb_dev,
@@ -626,12 +649,11 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     RT_CUDA(cudaEventRecord(c->ev[0], st));
     RT_CUDA(cudaMemsetAsync(c->d_waves.p, 0, RT_WAVE_SLOTS * sizeof(WaveCounters), st));
     RT_CUDA(cudaMemsetAsync(c->d_frame.p, 0, sizeof(FrameCounters), st));
-    RT_CUDA(cudaMemsetAsync(c->d_accum.p, 0, 3 * (size_t)f.n_local_pix * sizeof(long long), st));
 
     TravArgs ta;
     memset(&ta, 0, sizeof ta);
     ta.s = c->scene; ta.cam = make_cam(cam); ta.f = f;
-    ta.accum = c->d_accum.p; ta.fc = c->d_frame.p;
+    ta.accum = c->d_accum.p; ta.fc = c->d_frame.p; ta.sticky = c->d_sticky.p;
     ta.aux_prim = aux_dev ? aux_dev->prim_id : nullptr;
     ta.aux_t = aux_dev ? aux_dev->t : nullptr;
     ta.brute = (p->flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
@@ -640,6 +662,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     memset(&sa, 0, sizeof sa);
     sa.s = c->scene; sa.cam = ta.cam; sa.f = f;
     sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.accum = c->d_accum.p; sa.cap = (uint32_t)c->queue_cap;
+    sa.sticky = c->d_sticky.p;
     sa.max_depth = p->max_depth;
 
     uint32_t launches = 0;
@@ -665,12 +688,12 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     }
     RT_CUDA(cudaEventRecord(c->ev[7], st));
 
-    // statistics + error flags (one small D2H; also the frame's completion point)
+    // Without a stats request the frame is left in flight: nothing below synchronises, errors stay in
+    // the sticky word until rt_synchronize / the next stats-bearing call.
+    if (!stats) return;
     RT_CUDA(cudaMemcpyAsync(c->h_waves, c->d_waves.p, RT_WAVE_SLOTS * sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
     RT_CUDA(cudaMemcpyAsync(c->h_frame, c->d_frame.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
-    RT_CUDA(cudaStreamSynchronize(st));
-    uint32_t flags = 0;
-    for (int w = 0; w < RT_WAVE_SLOTS; w++) flags |= c->h_waves[w].flags;
+    rt_sync_and_check(c);
     uint64_t secondary = wr.secondary;
     uint32_t max_queue = wr.max_queue;
     if (bounce && !c->has_dielectric && p->max_depth <= 16) {   // blind mode: read populations now
@@ -679,41 +702,37 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
             if (c->h_waves[w].n_rays > max_queue) max_queue = c->h_waves[w].n_rays;
         }
     }
-    if (stats) {
-        memset(stats, 0, sizeof *stats);
-        stats->rays_primary = (uint64_t)cam->width * (uint64_t)cam->height;
-        if (c->layout.world > 1) {   // in-frame pixels of the owned tiles
-            uint64_t np = 0;
-            const TileLayout& L = c->layout;
-            uint32_t total = (uint32_t)L.tiles_x * (uint32_t)L.tiles_y;
-            for (uint32_t t = (uint32_t)L.rank; t < total; t += (uint32_t)L.world) {
-                int tx = (int)(t % (uint32_t)L.tiles_x), ty = (int)(t / (uint32_t)L.tiles_x);
-                int w = L.width - tx * L.tile_w, h = L.height - ty * L.tile_h;
-                if (w > L.tile_w) w = L.tile_w;
-                if (h > L.tile_h) h = L.tile_h;
-                np += (uint64_t)w * (uint64_t)h;
-            }
-            stats->rays_primary = np;
+    memset(stats, 0, sizeof *stats);
+    stats->rays_primary = (uint64_t)cam->width * (uint64_t)cam->height;
+    if (c->layout.world > 1) {   // in-frame pixels of the owned tiles
+        uint64_t np = 0;
+        const TileLayout& L = c->layout;
+        uint32_t total = (uint32_t)L.tiles_x * (uint32_t)L.tiles_y;
+        for (uint32_t t = (uint32_t)L.rank; t < total; t += (uint32_t)L.world) {
+            int tx = (int)(t % (uint32_t)L.tiles_x), ty = (int)(t / (uint32_t)L.tiles_x);
+            int w = L.width - tx * L.tile_w, h = L.height - ty * L.tile_h;
+            if (w > L.tile_w) w = L.tile_w;
+            if (h > L.tile_h) h = L.tile_h;
+            np += (uint64_t)w * (uint64_t)h;
         }
-        stats->rays_shadow = c->h_frame->rays_shadow;
-        stats->rays_secondary = secondary;
-        stats->node_visits = c->h_frame->node_visits[0];
-        stats->tri_tests = c->h_frame->tri_tests[0];
-        stats->shadow_node_visits = c->h_frame->node_visits[1];
-        stats->shadow_tri_tests = c->h_frame->tri_tests[1];
-        stats->waves = 1 + wr.waves;
-        stats->tiles = c->layout.n_tiles_owned;
-        stats->kernel_launches = launches;
-        stats->max_queue = max_queue > c->h_waves[0].n_hits ? max_queue : c->h_waves[0].n_hits;
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_device, c->ev[0], c->ev[7]));
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_trace, c->ev[0], c->ev[1]));
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_shadow, c->ev[1], c->ev[2]));
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_shade, c->ev[2], c->ev[3]));
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_secondary, c->ev[3], c->ev[6]));
-        RT_CUDA(cudaEventElapsedTime(&stats->ms_resolve, c->ev[6], c->ev[7]));
+        stats->rays_primary = np;
     }
-    if (flags & 1u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow: a wave spawned more rays than the queue holds"};
-    if (flags & 2u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow (BVH deeper than RT_STACK_SIZE)"};
+    stats->rays_shadow = c->h_frame->rays_shadow;
+    stats->rays_secondary = secondary;
+    stats->node_visits = c->h_frame->node_visits[0];
+    stats->tri_tests = c->h_frame->tri_tests[0];
+    stats->shadow_node_visits = c->h_frame->node_visits[1];
+    stats->shadow_tri_tests = c->h_frame->tri_tests[1];
+    stats->waves = 1 + wr.waves;
+    stats->tiles = c->layout.n_tiles_owned;
+    stats->kernel_launches = launches;
+    stats->max_queue = max_queue > c->h_waves[0].n_hits ? max_queue : c->h_waves[0].n_hits;
+    RT_CUDA(cudaEventElapsedTime(&stats->ms_device, c->ev[0], c->ev[7]));
+    RT_CUDA(cudaEventElapsedTime(&stats->ms_trace, c->ev[0], c->ev[1]));
+    RT_CUDA(cudaEventElapsedTime(&stats->ms_shadow, c->ev[1], c->ev[2]));
+    RT_CUDA(cudaEventElapsedTime(&stats->ms_shade, c->ev[2], c->ev[3]));
+    RT_CUDA(cudaEventElapsedTime(&stats->ms_secondary, c->ev[3], c->ev[6]));
+    RT_CUDA(cudaEventElapsedTime(&stats->ms_resolve, c->ev[6], c->ev[7]));
 }
 
 void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth, uint32_t flags, bool shade,
@@ -754,13 +773,14 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
     TravArgs ta;
     memset(&ta, 0, sizeof ta);
     ta.s = c->scene;
-    ta.accum = c->d_accum.p; ta.fc = c->d_frame.p;
+    ta.accum = c->d_accum.p; ta.fc = c->d_frame.p; ta.sticky = c->d_sticky.p;
     ta.aux_prim = c->d_aux_prim.p; ta.aux_t = c->d_aux_t.p;
     ta.brute = (flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
     ta.cap = (uint32_t)cap;
     ShadeArgs sa;
     memset(&sa, 0, sizeof sa);
     sa.s = c->scene; sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.accum = c->d_accum.p;
+    sa.sticky = c->d_sticky.p;
     sa.cap = (uint32_t)cap; sa.max_depth = max_depth;
     // wave 0 runs through the generic (queue-fed) kernels
     launch_wave<false>(c, ta, sa, 0, 1, 0, count, shade, nullptr, nullptr);
@@ -776,12 +796,7 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
         RT_CUDA(cudaGetLastError());
         RT_CUDA(cudaMemcpyAsync(rgb_out, c->d_rgbf_out.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    RT_CUDA(cudaMemcpyAsync(c->h_waves, c->d_waves.p, RT_WAVE_SLOTS * sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
-    RT_CUDA(cudaStreamSynchronize(st));
-    uint32_t fl = 0;
-    for (int k = 0; k < RT_WAVE_SLOTS; k++) fl |= c->h_waves[k].flags;
-    if (fl & 1u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow in rt_shade_rays"};
-    if (fl & 2u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow"};
+    rt_sync_and_check(c);
 }
 
 void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int width, int height, int tile_w,

@@ -64,7 +64,7 @@ struct WaveCounters {
     uint32_t n_hits;        // hit-queue length
     uint32_t fetch_shade;   // work cursor of the shadow (any-hit) kernel
     uint32_t n_next;        // rays appended for the next wave
-    uint32_t flags;         // bit0: ray-queue overflow, bit1: traversal stack overflow
+    uint32_t flags;         // unused (errors go to the context's sticky word)
     uint32_t pad[2];
 };
 #define RT_WAVE_SLOTS 64
@@ -144,6 +144,9 @@ struct rt_ctx {
     DevBuf<float> d_rgbf_out;
     WaveCounters* h_waves = nullptr;       // pinned
     FrameCounters* h_frame = nullptr;      // pinned
+    DevBuf<uint32_t> d_sticky;             // bit0 ray-queue overflow, bit1 traversal stack overflow
+    uint32_t* h_sticky = nullptr;          // pinned
+    std::vector<void*> ipc_opened, ipc_created;
     cudaEvent_t ev[8] = {};
     int trace_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
     // idle lanes a warp waits for before fetching new rays (k_traverse); measured on B200 (profiles/r1_tuning.md):
@@ -159,5 +162,6 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
 void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth, uint32_t flags, bool shade,
                    int32_t* prim_out, float* t_out, float* rgb_out);      // render.cu
 void rt_render_init(rt_ctx* c);                                     // render.cu
+void rt_sync_and_check(rt_ctx* c);                                  // render.cu
 void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int width, int height, int tile_w,
                  int tile_h, void* frame);                          // render.cu
