@@ -166,7 +166,9 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
 
     ctx = api.Context(dist_ctx["local_rank"])
     stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
+    # run the library on torch's current stream so that torch CUDA events and NCCL collectives order
+    # with its kernels; handle 0 is the legacy default stream, which the ABI names cudaStreamLegacy (0x1)
+    ctx.set_stream(stream.cuda_stream or 1)
     t0 = time.time()
     ctx.set_scene(scene)
     bstats = ctx.commit()

@@ -116,7 +116,8 @@ int rt_create(rt_ctx** out, int device);
 int rt_destroy(rt_ctx* ctx);
 const char* rt_last_error(rt_ctx* ctx);      /* ctx may be NULL: last error of rt_create        */
 /* Run all further work of this context on an existing CUDA stream (a cudaStream_t passed as a
- * pointer, e.g. torch.cuda.current_stream().cuda_stream); NULL restores the context's stream. */
+ * pointer, e.g. torch.cuda.current_stream().cuda_stream); NULL restores the context's own stream.
+ * The legacy default stream is named by CUDA's handle cudaStreamLegacy, (void*)0x1.           */
 int rt_set_stream(rt_ctx* ctx, void* cuda_stream);
 
 /* ---- scene: replaces World::addObject / addLight / setAmbient / setBackground (world.h:26-37)
