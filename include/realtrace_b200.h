@@ -106,6 +106,7 @@ typedef struct rt_build_stats {
     uint32_t n_large_triangles;   /* outliers tested linearly */
     uint32_t n_nodes;
     uint32_t sort_passes;
+    uint32_t leaf_size;           /* triangles per leaf at most (RT_LEAF_SIZE, default 1) */
     float ms_build;               /* device time: bounds + Morton + sort + hierarchy + refit */
     float ms_refit;               /* device time of the last refit */
 } rt_build_stats;

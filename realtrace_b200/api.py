@@ -50,7 +50,7 @@ class RtFrameStats(C.Structure):
 
 class RtBuildStats(C.Structure):
     _fields_ = [("n_triangles", C.c_uint32), ("n_large_triangles", C.c_uint32), ("n_nodes", C.c_uint32),
-                ("sort_passes", C.c_uint32), ("ms_build", C.c_float), ("ms_refit", C.c_float)]
+                ("sort_passes", C.c_uint32), ("leaf_size", C.c_uint32), ("ms_build", C.c_float), ("ms_refit", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

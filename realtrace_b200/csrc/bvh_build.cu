@@ -404,6 +404,7 @@ void rt_build_bvh(rt_ctx* c, bool refit_only) {
     RT_CUDA(cudaEventSynchronize(c->ev[5]));
     RT_CUDA(cudaEventElapsedTime(&c->build_stats.ms_build, c->ev[4], c->ev[5]));
     c->build_stats.n_triangles = c->n_bvh;
+    c->build_stats.leaf_size = (uint32_t)c->leaf_size;
     c->build_stats.n_large_triangles = c->n_large;
     c->build_stats.n_nodes = c->n_bvh >= 2 ? c->n_bvh - 1 : (c->n_bvh == 1 ? 1u : 0u);
     publish_scene(c);

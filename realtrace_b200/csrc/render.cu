@@ -69,11 +69,10 @@ __device__ __forceinline__ void primary_ray(const CamDev& c, int i, int j, f3& o
     double dx = -c.w[0] * c.focal + c.u[0] * (double)xw + c.v[0] * (double)yw;
     double dy = -c.w[1] * c.focal + c.u[1] * (double)xw + c.v[1] * (double)yw;
     double dz = -c.w[2] * c.focal + c.u[2] * (double)xw + c.v[2] * (double)yw;
-    double l = sqrt(dx * dx + dy * dy + dz * dz);
-    // get_ray_direction normalises, then Ray's constructor normalises again
-    dx /= l; dy /= l; dz /= l;
-    l = sqrt(dx * dx + dy * dy + dz * dz);
-    d = mk3((float)(dx / l), (float)(dy / l), (float)(dz / l));
+    // get_ray_direction normalises and Ray's constructor normalises again; the second pass moves the
+    // FP64 value by <= 1 ulp, far below the final rounding to FP32, so one reciprocal length is used
+    double inv = 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+    d = mk3((float)(dx * inv), (float)(dy * inv), (float)(dz * inv));
     o = mk3((float)c.pos[0], (float)c.pos[1], (float)c.pos[2]);
 }
 
@@ -121,6 +120,7 @@ struct TravArgs {
     uint32_t cap;             // ray-queue capacity (bounds n_rays after an overflow)
     uint32_t primary_wave;    // SHADOW: the wave's rays are primary rays (regenerated from the pixel)
     int refill_min;           // idle lanes a warp waits for before it fetches new rays
+    int loop_style;           // 0: while-while; k > 0: if-if in bursts of k steps
 };
 
 template <int MODE, bool COUNT>
@@ -221,16 +221,33 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
         }
         // ---- while-while traversal of the lanes that own a ray
         if (active) {
-            while (rt_is_internal(node)) {
-                if (COUNT) wc.nodes++;
-                node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
-            }
-            while (node < 0) {
-                if (leaf_test(a.s, node, r, hit, ANY, COUNT ? &wc : nullptr)) {
-                    found = true;
-                    if (ANY) { node = RT_DONE; break; }
+            if (a.loop_style == 0) {
+                while (rt_is_internal(node)) {
+                    if (COUNT) wc.nodes++;
+                    node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                 }
-                node = sp ? stack[--sp] : RT_DONE;
+                while (node < 0) {
+                    if (leaf_test(a.s, node, r, hit, ANY, COUNT ? &wc : nullptr)) {
+                        found = true;
+                        if (ANY) { node = RT_DONE; break; }
+                    }
+                    node = sp ? stack[--sp] : RT_DONE;
+                }
+            } else {
+                // "if-if": every lane advances one step of whatever kind per iteration, for a bounded
+                // number of iterations before the warp looks at its refill state again
+                for (int it = 0; it < a.loop_style && node != RT_DONE; it++) {
+                    if (rt_is_internal(node)) {
+                        if (COUNT) wc.nodes++;
+                        node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
+                    } else {
+                        if (leaf_test(a.s, node, r, hit, ANY, COUNT ? &wc : nullptr)) {
+                            found = true;
+                            if (ANY) { node = RT_DONE; break; }
+                        }
+                        node = sp ? stack[--sp] : RT_DONE;
+                    }
+                }
             }
         }
         // ---- rays that ran out of nodes: linear primitives, then the result
@@ -546,6 +563,7 @@ uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot
     ta.wave = c->d_waves.p + slot_in;
     ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p;
     ta.refill_min = PRIMARY ? c->refill_primary : c->refill_queue;
+    ta.loop_style = PRIMARY ? c->loop_primary : c->loop_queue;
     launch_traverse<PRIMARY ? MODE_PRIMARY : MODE_QUEUE>(c, ta, count);
     launches++;
     if (after_trace) RT_CUDA(cudaEventRecord(after_trace, c->stream));
@@ -555,6 +573,7 @@ uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot
         sh.hits_in = c->d_hits.p; sh.hitq_in = c->d_hitq.p; sh.occl = c->d_occl.p;
         sh.primary_wave = PRIMARY ? 1u : 0u;
         sh.refill_min = c->refill_shadow;
+        sh.loop_style = c->loop_shadow;
         sh.aux_prim = nullptr; sh.aux_t = nullptr;
         launch_traverse<MODE_SHADOW>(c, sh, count);
         launches++;

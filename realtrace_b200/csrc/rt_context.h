@@ -123,7 +123,7 @@ struct rt_ctx {
     DevBuf<uint32_t> d_visit;
     SceneDev scene{};
     rt_build_stats build_stats{};
-    int leaf_size = 4;
+    int leaf_size = 1;                     // measured best on B200 with the if-if walk (profiles/r1_tuning.md)
     float scene_abs_max = 1.0f;
 
     // ---- render state
@@ -152,6 +152,7 @@ struct rt_ctx {
     // idle lanes a warp waits for before fetching new rays (k_traverse); measured on B200 (profiles/r1_tuning.md):
     // coherent primary rays are best refilled as whole warps, shadow and bounce rays lane by lane in groups
     int refill_primary = 32, refill_queue = 16, refill_shadow = 16;
+    int loop_primary = 64, loop_queue = 64, loop_shadow = 64;   // k_traverse loop style per ray class (0 = while-while)
 };
 
 // ---- entry points implemented across the .cu files ------------------------------------------------

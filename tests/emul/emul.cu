@@ -272,3 +272,27 @@ extern "C" int emul_bvh(const oracle_scene* in, int leaf_size, float* nodes, uin
     if (n_bvh) *n_bvh = S.n_bvh;
     return (int)(S.nodes.size() / 4);
 }
+
+// Per-pixel traversal cost of the primary rays (node visits, triangle tests) — used to study load
+// balance (profiles/r1_tuning.md).
+extern "C" int emul_primary_cost(const oracle_scene* in, const rt_camera* cam, int leaf_size, uint32_t* nodes, uint32_t* tris) {
+    EmulScene S;
+    build(in, leaf_size, S);
+    const SceneDev& s = S.dev;
+    const int W = cam->width, H = cam->height;
+    bool overflow = false;
+    for (int j = 0; j < H; j++)
+        for (int i = 0; i < W; i++) {
+            float xw = (float)((double)cam->aspect * (i - W / 2.0 + 0.5) / W), yw = (float)((j - H / 2.0 + 0.5) / H);
+            double dd[3];
+            for (int k = 0; k < 3; k++) dd[k] = -(double)cam->w[k] * (double)cam->focal_distance + (double)cam->u[k] * (double)xw + (double)cam->v[k] * (double)yw;
+            double l = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+            f3 d = mk3((float)(dd[0] / l), (float)(dd[1] / l), (float)(dd[2] / l));
+            HitRec h;
+            WorkCount wc{0, 0};
+            trace_ray<false>(s, mk3(cam->pos[0], cam->pos[1], cam->pos[2]), d, false, h, &wc, &overflow);
+            nodes[(size_t)i + (size_t)j * W] = wc.nodes;
+            tris[(size_t)i + (size_t)j * W] = wc.tris;
+        }
+    return 0;
+}

