@@ -37,10 +37,11 @@ RT_HD int tri_test(f3 a, f3 e1, f3 e2, f3 o, f3 d, float& tcur, float& beta, flo
     float sg = A > 0.0f ? 1.0f : -1.0f;
     float b = bA * sg, g = gA * sg, aa = A * sg;
     if (!(b > 0.0f && g > 0.0f && b + g < aa)) return 0;
-    float t = -dot(e2, q) / A;
+    float inv = rt_rcp(A);
+    float t = -dot(e2, q) * inv;
     if (!accept_t(t, tcur)) return 1;
-    beta = bA / A;
-    gamma = gA / A;
+    beta = bA * inv;
+    gamma = gA * inv;
     return 2;
 }
 
