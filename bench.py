@@ -45,50 +45,77 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Streams nvidia-smi clocks / throttle reasons (one process, -lms 20) while the bench runs; the
-    summary uses the samples that fall inside the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock, power and throttle reasons through NVML (nvidia_ml_py) every few ms while the
+    bench runs; the summary uses the samples that fall inside the timed region.  Falls back to polling
+    nvidia-smi when NVML is not importable."""
+    SMI_Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag = index, [], False
         self.t_begin = self.t_end = None
+        self.source = None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        idx = self.index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        self.source = "nvml"
+        while not self.stop_flag:
+            r = get_reasons(h)
+            self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(sm_max),
+                              nv.nvmlDeviceGetPowerUsage(h) / 1000.0, [n for n, b in bits.items() if r & b]))
+            time.sleep(0.004)
+
+    def _smi_loop(self):
+        self.source = "nvidia-smi"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.SMI_Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append((time.perf_counter(), float(f[0]), float(f[1]), float(f[2]),
+                                      [n for k, n in enumerate(names) if f[3 + k].lower().startswith("active")]))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                f = [x.strip() for x in line.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append((time.perf_counter(), f))
+            self._nvml_loop()
         except Exception:
-            pass
-
-    def stop(self):
-        if self.proc is not None:
             try:
-                self.proc.terminate()
+                self._smi_loop()
             except Exception:
                 pass
 
+    def stop(self):
+        self.stop_flag = True
+
     def summary(self):
-        rows = [f for t, f in self.rows if self.t_begin is not None and self.t_begin <= t <= self.t_end]
+        rows = [r for r in self.rows if self.t_begin is not None and self.t_begin <= r[0] <= self.t_end]
         where = "timed region"
         if len(rows) < 2:
-            rows, where = [f for _, f in self.rows], "whole run (timed region shorter than the sampling period)"
+            rows, where = list(self.rows), "whole run (timed region shorter than the sampling period)"
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        try:
-            sm = sorted(float(r[0]) for r in rows)
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
-            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
-                    "samples": len(rows), "window": where, "power_w_max": max(float(r[2]) for r in rows)}
-        except Exception as e:   # unexpected nvidia-smi formatting
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"unparsed nvidia-smi output: {e}"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        sm = sorted(r[1] for r in rows)
+        reasons = sorted({n for r in rows for n in r[4]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": rows[0][2], "reasons": reasons,
+                "samples": len(rows), "window": where, "source": self.source, "power_w_max": max(r[3] for r in rows)}
 
 
 def total_rays(st):
@@ -369,26 +396,36 @@ def run_gpu_arm(args):
         work = main["work"]
         kms = main["kernel_ms"]
         dom = max(kms, key=kms.get)
-        # algorithmic bytes / FMA lane-instructions per ray: SURVEY §8(d)
-        bytes_per_ray = 64.0 * work["node_visits_per_ray"] + 48.0 * work["tri_tests_per_ray"] + 84.0
-        fma_per_ray = 12.0 * work["node_visits_per_ray"] + 30.0 * work["tri_tests_per_ray"] + 60.0
-        frame_ms = sum(kms.values())
-        achieved = bytes_per_ray * work["rays"] / (frame_ms * 1e-3) / 1e9
+        # algorithmic bytes / FMA lane-instructions per ray: SURVEY §8(d), applied to the rays the dominant
+        # kernel traces (nearest-hit rays for k_traverse<primary>, any-hit rays for k_traverse<shadow>)
+        cls = work["shadow"] if "shadow" in dom else work["nearest"]
+        bytes_per_ray = 64.0 * cls["node_visits_per_ray"] + 48.0 * cls["tri_tests_per_ray"] + 84.0
+        fma_per_ray = 12.0 * cls["node_visits_per_ray"] + 30.0 * cls["tri_tests_per_ray"] + 60.0
+        dom_ms = kms[dom]
+        achieved = bytes_per_ray * cls["rays"] / (dom_ms * 1e-3) / 1e9
         sm_mhz = main["clocks"].get("sm_mhz") or sm_max_mhz
         fma_peak = FMA_LANES_PER_CLK * sm_max_mhz * 1e6
-        fma_ach = fma_per_ray * work["rays"] / (frame_ms * 1e-3)
+        fma_ach = fma_per_ray * cls["rays"] / (dom_ms * 1e-3)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj.get(args.workload, {}).get("k_traverse<shadow>" if "shadow" in dom else "k_traverse<primary>")
         line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                            "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
-                            "kernel": "k_trace + k_shade (all traversal kernels of the frame)",
-                            "dominant_kernel": dom, "kernel_ms": kms,
+                            "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
+                            "kernel": dom, "kernel_ms": kms, "rays_in_kernel": cls["rays"],
                             "algorithmic_bytes_per_ray": bytes_per_ray,
-                            "node_visits_per_ray": work["node_visits_per_ray"],
-                            "tri_tests_per_ray": work["tri_tests_per_ray"],
+                            "node_visits_per_ray": cls["node_visits_per_ray"],
+                            "tri_tests_per_ray": cls["tri_tests_per_ray"],
                             "fma": {"achieved_lane_instr_per_s": fma_ach, "peak_lane_instr_per_s": fma_peak,
                                     "frac": fma_ach / fma_peak, "lane_instr_per_ray": fma_per_ray,
                                     "sm_mhz_under_load": sm_mhz},
-                            "note": "node/triangle fetches are served mostly by L1/L2 (scene 112 MB ~ L2 size); "
-                                    "the HBM figure is the contract's denominator, see DESIGN.md §6"}
+                            "frame_totals": {"node_visits_per_ray": work["node_visits_per_ray"],
+                                             "tri_tests_per_ray": work["tri_tests_per_ray"], "rays": work["rays"]},
+                            "note": "algorithmic bytes are SURVEY 8(d)'s 64 B per node visit + 48 B per triangle test + 84 B "
+                                    "per ray; neighbouring rays share nodes through L1/L2 (ncu: L1 hit ~80 %, DRAM < 3 % "
+                                    "busy), so achieved can exceed the HBM copy peak — `traffic` is what DRAM really moved "
+                                    "per launch; the binding limit is instruction issue, see fma.frac and DESIGN.md 6"}
         line["e2e"]["cold_ms_incl_scene_upload_and_bvh_build"] = main["e2e_cold_ms"]
         # the reference's CPU renderer on a bounded sample of the same workload, 1 core
         if not args.no_cpu:
