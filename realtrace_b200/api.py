@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librealtrace_b200.so")
+LIB_PATH = os.environ.get("RT_LIB_PATH") or os.path.join(HERE, "librealtrace_b200.so")   # RT_LIB_PATH: tuning builds only
 
 FLAG_BRUTE_FORCE, FLAG_COUNT_WORK, FLAG_PACKED_TILES = 1, 2, 4
 COMMIT_BUILD, COMMIT_REFIT = 0, 1

@@ -27,6 +27,7 @@
 namespace {
 
 constexpr int TRAV_TPB = 128;
+// min CTAs/SM in __launch_bounds__ measured: 10 (48 regs) = no bound (55 regs, 9 CTAs/SM); 12 and 16 spill and lose 15-50 %
 constexpr int SHADE_TPB = 128;
 
 enum { MODE_PRIMARY = 0, MODE_QUEUE = 1, MODE_SHADOW = 2 };
@@ -646,6 +647,11 @@ void rt_render_init(rt_ctx* c) {
     c->shadow_blocks = persistent_blocks(k_traverse<MODE_SHADOW, false>, TRAV_TPB, c->sm_count);
     c->shade_blocks = lo(persistent_blocks(k_shade<true>, SHADE_TPB, c->sm_count),
                          persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
+    if (c->blocks_per_sm > 0) {   // RT_BLOCKS_PER_SM: cap the persistent grids (tuning)
+        int cap = c->blocks_per_sm * c->sm_count;
+        c->trace_blocks = lo(c->trace_blocks, cap);
+        c->shadow_blocks = lo(c->shadow_blocks, cap);
+    }
     c->d_waves.reserve(RT_WAVE_SLOTS);
     c->d_frame.reserve(1);
     RT_CUDA(cudaMallocHost((void**)&c->h_waves, RT_WAVE_SLOTS * sizeof(WaveCounters)));

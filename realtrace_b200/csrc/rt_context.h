@@ -149,6 +149,7 @@ struct rt_ctx {
     std::vector<void*> ipc_opened, ipc_created;
     cudaEvent_t ev[8] = {};
     int trace_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
+    int blocks_per_sm = 0;                 // 0 = as many persistent CTAs as fit
     // idle lanes a warp waits for before fetching new rays (k_traverse); measured on B200 (profiles/r1_tuning.md):
     // coherent primary rays are best refilled as whole warps, shadow and bounce rays lane by lane in groups
     int refill_primary = 32, refill_queue = 16, refill_shadow = 16;

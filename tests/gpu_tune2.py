@@ -1,13 +1,9 @@
 """Development probe: loop style / leaf size / refill sweeps, full frame and a 1/8 share."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-configs = []
-for leaf in (1, 2, 4):
-    for loop in (16, 64, 256):
-        configs.append(dict(RT_LEAF_SIZE=leaf, RT_LOOP_PRIMARY=loop, RT_LOOP_SHADOW=loop))
-for rs in (8, 32):
-    configs.append(dict(RT_LEAF_SIZE=1, RT_LOOP_PRIMARY=64, RT_LOOP_SHADOW=64, RT_REFILL_SHADOW=rs))
-configs.append(dict(RT_LEAF_SIZE=1, RT_LOOP_PRIMARY=64, RT_LOOP_SHADOW=64, RT_REFILL_PRIMARY=24))
+configs = [dict()]
+for mb in (10, 12, 16):
+    configs.append(dict(RT_LIB_PATH=os.path.join(ROOT, "tests", "emul", f"librt_mb{mb}.so")))
 code = f"""
 import sys, os; sys.path.insert(0, {ROOT!r})
 from realtrace_b200 import api, scenes
