@@ -70,6 +70,14 @@ typedef struct rt_render_params {
     int32_t rank, world_size;     /* interleaved tile ownership: this context renders the
                                      tiles with (tile_id % world_size) == rank; {0,1} = all */
     uint32_t flags;
+    /* Dynamic tile stealing (multi-GPU, needs a frame every rank can write, see
+     * rt_shared_buffer_*): with steal_pool_div = k > 0 every k-th group of world_size tiles is not
+     * owned by anybody; ranks that run out of their own tiles claim 8x4-pixel blocks of those
+     * tiles from the shared cursor (64 x uint32, zero-initialised, slot frame_index % 64) with
+     * system-scope atomics.  All ranks must pass the same k, cursor and frame_index.           */
+    int32_t steal_pool_div;
+    uint32_t frame_index;
+    void* steal_cursor;
 } rt_render_params;
 #define RT_FLAG_BRUTE_FORCE   1u  /* test every triangle linearly instead of walking the BVH */
 #define RT_FLAG_COUNT_WORK    2u  /* count BVH node visits / triangle tests (slower)         */
@@ -93,6 +101,8 @@ typedef struct rt_frame_stats {
     uint32_t tiles;               /* tiles rendered by this context */
     uint32_t kernel_launches;     /* CUDA kernels launched for this frame */
     uint32_t max_queue;           /* largest ray population of any wave */
+    uint32_t stolen_blocks;       /* 8x4-pixel blocks this context claimed from the shared pool */
+    uint32_t reserved0;
     float ms_device;              /* device time of the frame, CUDA events on the render stream */
     float ms_trace;               /* device time of the primary nearest-hit kernel */
     float ms_shadow;              /* device time of the primary wave's shadow any-hit kernel */

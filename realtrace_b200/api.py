@@ -29,7 +29,8 @@ class RtCamera(C.Structure):
 
 class RtRenderParams(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("rank", C.c_int32),
-                ("world_size", C.c_int32), ("flags", C.c_uint32)]
+                ("world_size", C.c_int32), ("flags", C.c_uint32), ("steal_pool_div", C.c_int32),
+                ("frame_index", C.c_uint32), ("steal_cursor", C.c_void_p)]
 
 
 class RtAuxOut(C.Structure):
@@ -40,7 +41,8 @@ class RtFrameStats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_secondary", C.c_uint64),
                 ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("shadow_node_visits", C.c_uint64),
                 ("shadow_tri_tests", C.c_uint64), ("waves", C.c_uint32), ("tiles", C.c_uint32),
-                ("kernel_launches", C.c_uint32), ("max_queue", C.c_uint32), ("ms_device", C.c_float),
+                ("kernel_launches", C.c_uint32), ("max_queue", C.c_uint32), ("stolen_blocks", C.c_uint32),
+                ("reserved0", C.c_uint32), ("ms_device", C.c_float),
                 ("ms_trace", C.c_float), ("ms_shadow", C.c_float), ("ms_shade", C.c_float),
                 ("ms_secondary", C.c_float), ("ms_resolve", C.c_float)]
 
@@ -204,9 +206,11 @@ class Context:
 
     # ---- rendering
     @staticmethod
-    def _params(max_depth, tile=(0, 0), rank=0, world=1, flags=0):
+    def _params(max_depth, tile=(0, 0), rank=0, world=1, flags=0, steal=None):
         p = RtRenderParams()
         p.max_depth, p.tile_w, p.tile_h, p.rank, p.world_size, p.flags = max_depth, tile[0], tile[1], rank, world, flags
+        if steal is not None:      # (pool_div, frame_index, cursor device pointer)
+            p.steal_pool_div, p.frame_index, p.steal_cursor = steal
         return p
 
     def render(self, cam, max_depth, aux=False, tile=(0, 0), rank=0, world=1, flags=0, out=None):
@@ -230,10 +234,12 @@ class Context:
                                        C.byref(a) if a is not None else None, C.byref(st)))
         return rgb, prim, t, st.as_dict()
 
-    def render_device(self, cam, max_depth, rgb_dev_ptr, tile=(0, 0), rank=0, world=1, flags=0, want_stats=True):
-        """Device-buffer frame (rt_render_device); rgb_dev_ptr is a CUDA device pointer (int)."""
+    def render_device(self, cam, max_depth, rgb_dev_ptr, tile=(0, 0), rank=0, world=1, flags=0, want_stats=True,
+                      steal=None):
+        """Device-buffer frame (rt_render_device); rgb_dev_ptr is a CUDA device pointer (int).
+        steal = (pool_div, frame_index, cursor_dev_ptr) enables dynamic tile stealing."""
         c = camera_struct(cam)
-        p = self._params(max_depth, tile, rank, world, flags)
+        p = self._params(max_depth, tile, rank, world, flags, steal)
         st = RtFrameStats()
         self._check(self.lib.rt_render_device(self.h, C.byref(c), C.byref(p), rgb_dev_ptr, None,
                                               C.byref(st) if want_stats else None))

@@ -40,20 +40,34 @@ struct CamDev {
 
 struct FrameDev {
     int W, H, tile_w, tile_h, tiles_x, tile_pix;
-    uint32_t n_tiles_owned, n_local_pix;
+    uint32_t n_tiles_owned, n_local_pix;   // the statically owned tiles and their pixel count
     const uint32_t* tile_ids;
+    // dynamic tile stealing: blocks of 8x4 pixels of the pool tiles, claimed through steal_cursor
+    const uint32_t* pool_ids;              // pool tile ids (the same list on every rank)
+    uint32_t n_pool_blocks;                // pool tiles * blocks per tile
+    uint32_t* stolen_map;                  // slot -> pool block claimed by this rank
+    uint32_t* steal_cursor;                // system-scope cursor of this frame, nullptr = no stealing
 };
 
-// local pixel index -> frame pixel.  A tile is cut into 8x4 blocks (one warp each); lane = x%8 + 8*(y%4).
-__device__ __forceinline__ bool local_to_pixel(const FrameDev& f, uint32_t lp, int& i, int& j) {
-    uint32_t tl = lp / (uint32_t)f.tile_pix, p = lp % (uint32_t)f.tile_pix;
-    uint32_t tile = __ldg(f.tile_ids + tl);
+// (tile, 8x4 block, lane) -> frame pixel; lane = x%8 + 8*(y%4).
+__device__ __forceinline__ bool block_to_pixel(const FrameDev& f, uint32_t tile, uint32_t b, uint32_t l, int& i, int& j) {
     int tx = (int)(tile % (uint32_t)f.tiles_x), ty = (int)(tile / (uint32_t)f.tiles_x);
-    int b = (int)(p >> 5), l = (int)(p & 31);
     int bpr = f.tile_w >> 3;
-    i = tx * f.tile_w + (b % bpr) * 8 + (l & 7);
-    j = ty * f.tile_h + (b / bpr) * 4 + (l >> 3);
+    i = tx * f.tile_w + (int)(b % (uint32_t)bpr) * 8 + (int)(l & 7);
+    j = ty * f.tile_h + (int)(b / (uint32_t)bpr) * 4 + (int)(l >> 3);
     return i < f.W && j < f.H;
+}
+
+// local pixel index -> frame pixel.  Indices below n_local_pix walk the owned tiles in 8x4 blocks;
+// indices above address blocks stolen from the pool, 32 per slot of stolen_map.
+__device__ __forceinline__ bool local_to_pixel(const FrameDev& f, uint32_t lp, int& i, int& j) {
+    if (lp < f.n_local_pix) {
+        uint32_t tl = lp / (uint32_t)f.tile_pix, p = lp % (uint32_t)f.tile_pix;
+        return block_to_pixel(f, __ldg(f.tile_ids + tl), p >> 5, p & 31, i, j);
+    }
+    uint32_t slot = (lp - f.n_local_pix) >> 5;
+    uint32_t pb = f.stolen_map[slot], bpt = (uint32_t)f.tile_pix >> 5;
+    return block_to_pixel(f, __ldg(f.pool_ids + pb / bpt), pb % bpt, lp & 31, i, j);
 }
 __device__ __forceinline__ uint32_t pixel_in_tile_to_local(const FrameDev& f, uint32_t tl, int x, int y) {
     int bpr = f.tile_w >> 3;
@@ -144,6 +158,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
     int stack[RT_STACK_SIZE];
     int node = RT_DONE, sp = 0;
     bool active = false, found = false, exhausted = false, overflow = false;
+    bool steal_done = !(MODE == MODE_PRIMARY && a.f.steal_cursor != nullptr && a.f.n_pool_blocks > 0);
     uint32_t item = 0, pix = 0;
     int pi = 0, pj = 0;
     f3 w = mk3(1, 1, 1);
@@ -154,20 +169,41 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
     for (;;) {
         // ---- refill idle lanes from the global cursor
         uint32_t need = __ballot_sync(FULL, !active);
+        uint32_t my = 0;
+        bool have = false;
         if (!exhausted && (__popc(need) >= a.refill_min || need == FULL)) {
             int cnt = __popc(need), leader = __ffs(need) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(cursor, (uint32_t)cnt);
             base = __shfl_sync(FULL, base, leader);
             if (base + (uint32_t)cnt >= n) exhausted = true;
-            uint32_t my = base + __popc(need & lt);
-            if (!active && my < n) {
+            my = base + __popc(need & lt);
+            have = !active && my < n;
+        } else if (MODE == MODE_PRIMARY && exhausted && !steal_done && need == FULL) {
+            // own tiles are done: claim one 8x4 block of the shared pool (system-scope atomic: the
+            // cursor lives in rank 0's memory and is reached over NVLink by the other ranks)
+            uint32_t pb = 0, slot = 0;
+            if (lane == 0) {
+                pb = atomicAdd_system(a.f.steal_cursor, 1u);
+                if (pb < a.f.n_pool_blocks) {
+                    slot = atomicAdd(&a.fc->stolen_blocks, 1u);
+                    a.f.stolen_map[slot] = pb;
+                }
+            }
+            __syncwarp();
+            pb = __shfl_sync(FULL, pb, 0);
+            slot = __shfl_sync(FULL, slot, 0);
+            if (pb >= a.f.n_pool_blocks) steal_done = true;
+            else { my = a.f.n_local_pix + slot * 32u + (uint32_t)lane; have = true; }
+        }
+        {
+            if (have) {
                 f3 o, d;
                 bool ok = true;
                 item = my;
                 if (MODE == MODE_PRIMARY) {
                     ok = local_to_pixel(a.f, my, pi, pj);
-                    if (ok) primary_ray(a.cam, pi, pj, o, d);
+                    if (ok) { primary_ray(a.cam, pi, pj, o, d); traced++; }
                     pix = my;
                     w = mk3(1, 1, 1);
                 } else if (MODE == MODE_QUEUE) {
@@ -217,7 +253,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
             }
         }
         if (!__any_sync(FULL, active)) {
-            if (exhausted) break;
+            if (exhausted && steal_done) break;
             continue;
         }
         // ---- while-while traversal of the lanes that own a ray
@@ -299,9 +335,9 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
             }
         }
     }
-    if (ANY) {
+    if (ANY || MODE == MODE_PRIMARY) {
         uint32_t ns = warp_sum(traced);
-        if (lane == 0 && ns) atomicAdd(&a.fc->rays_shadow, (unsigned long long)ns);
+        if (lane == 0 && ns) atomicAdd(ANY ? &a.fc->rays_shadow : &a.fc->rays_primary, (unsigned long long)ns);
     }
     if (COUNT) {
         uint32_t nn = warp_sum(wc.nodes), nt = warp_sum(wc.tris);
@@ -405,18 +441,35 @@ __device__ __forceinline__ uint32_t to_u8(long long q) {
 
 // One thread per 4 horizontally adjacent pixels of an owned tile.
 __global__ void __launch_bounds__(256) k_resolve(FrameDev f, const long long* __restrict__ accum,
-                                                uint8_t* __restrict__ out, int packed) {
+                                                uint8_t* __restrict__ out, int packed,
+                                                const FrameCounters* __restrict__ fc) {
     uint32_t quads_per_row = (uint32_t)f.tile_w >> 2;
     uint32_t quads_per_tile = quads_per_row * (uint32_t)f.tile_h;
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= f.n_tiles_owned * quads_per_tile) return;
-    uint32_t tl = q / quads_per_tile, r = q % quads_per_tile;
-    int y = (int)(r / quads_per_row), x0 = (int)(r % quads_per_row) * 4;
-    uint32_t tile = __ldg(f.tile_ids + tl);
+    uint32_t static_quads = f.n_tiles_owned * quads_per_tile;
+    uint32_t tl = 0, tile, lp0;
+    int y, x0;
+    if (q < static_quads) {
+        tl = q / quads_per_tile;
+        uint32_t r = q % quads_per_tile;
+        y = (int)(r / quads_per_row); x0 = (int)(r % quads_per_row) * 4;
+        tile = __ldg(f.tile_ids + tl);
+        lp0 = pixel_in_tile_to_local(f, tl, x0, y);
+    } else {
+        // blocks claimed from the shared pool: 8 quads (4 rows x 2) per 8x4 block
+        uint32_t sq = q - static_quads, slot = sq >> 3, qq = sq & 7;
+        if (f.steal_cursor == nullptr || slot >= fc->stolen_blocks) return;
+        uint32_t pb = f.stolen_map[slot], bpt = (uint32_t)f.tile_pix >> 5;
+        tile = __ldg(f.pool_ids + pb / bpt);
+        uint32_t blk = pb % bpt;
+        int bpr = f.tile_w >> 3, row = (int)(qq >> 1), xq = (int)(qq & 1) * 4;
+        x0 = (int)(blk % (uint32_t)bpr) * 8 + xq;
+        y = (int)(blk / (uint32_t)bpr) * 4 + row;
+        lp0 = f.n_local_pix + slot * 32u + (uint32_t)(row * 8 + xq);
+    }
     int tx = (int)(tile % (uint32_t)f.tiles_x), ty = (int)(tile / (uint32_t)f.tiles_x);
     int j = ty * f.tile_h + y, i0 = tx * f.tile_w + x0;
     if (j >= f.H || i0 >= f.W) return;
-    uint32_t lp0 = pixel_in_tile_to_local(f, tl, x0, y);
     uint32_t px[12];
     int npx = min(4, f.W - i0);
     for (int k = 0; k < 4; k++) {
@@ -493,23 +546,38 @@ void setup_layout(rt_ctx* c, const rt_camera* cam, const rt_render_params* p) {
     L.tile_h = p->tile_h > 0 ? p->tile_h : 32;
     L.rank = p->world_size > 1 ? p->rank : 0;
     L.world = p->world_size > 1 ? p->world_size : 1;
+    L.pool_div = (L.world > 1 && p->steal_pool_div > 0) ? p->steal_pool_div : 0;
     if (L.tile_w % 8 || L.tile_h % 4) throw RtError{RT_ERR_INVALID_ARGUMENT, "tile_w must be a multiple of 8 and tile_h of 4"};
     if (L.rank < 0 || L.rank >= L.world) throw RtError{RT_ERR_INVALID_ARGUMENT, "rank outside [0, world_size)"};
+    if (L.pool_div && (p->flags & RT_FLAG_PACKED_TILES))
+        throw RtError{RT_ERR_INVALID_ARGUMENT, "tile stealing needs a frame-layout output, not RT_FLAG_PACKED_TILES"};
     L.tiles_x = (L.width + L.tile_w - 1) / L.tile_w;
     L.tiles_y = (L.height + L.tile_h - 1) / L.tile_h;
     if (L == c->layout && c->d_tile_ids.p) return;
-    std::vector<uint32_t> ids;
+    // tile t belongs to group t / world; every pool_div-th group is the shared pool, the other groups are
+    // dealt out round robin (tile t -> rank t % world)
+    std::vector<uint32_t> ids, pool;
     uint32_t total = (uint32_t)L.tiles_x * (uint32_t)L.tiles_y;
-    for (uint32_t t = (uint32_t)L.rank; t < total; t += (uint32_t)L.world) ids.push_back(t);
+    for (uint32_t t = 0; t < total; t++) {
+        uint32_t g = t / (uint32_t)L.world;
+        if (L.pool_div && g % (uint32_t)L.pool_div == (uint32_t)L.pool_div - 1) pool.push_back(t);
+        else if (t % (uint32_t)L.world == (uint32_t)L.rank) ids.push_back(t);
+    }
     L.n_tiles_owned = (uint32_t)ids.size();
+    L.n_pool_tiles = (uint32_t)pool.size();
     c->d_tile_ids.reserve(ids.size() ? ids.size() : 1);
+    c->d_pool_ids.reserve(pool.size() ? pool.size() : 1);
+    uint32_t bpt = (uint32_t)(L.tile_w * L.tile_h) / 32u;
+    c->d_stolen_map.reserve(pool.size() ? pool.size() * bpt : 1);
     if (!ids.empty())
         RT_CUDA(cudaMemcpyAsync(c->d_tile_ids.p, ids.data(), ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    if (!pool.empty())
+        RT_CUDA(cudaMemcpyAsync(c->d_pool_ids.p, pool.data(), pool.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     RT_CUDA(cudaStreamSynchronize(c->stream));
     c->layout = L;
 }
 
-FrameDev frame_dev(const rt_ctx* c) {
+FrameDev frame_dev(rt_ctx* c, const rt_render_params* p) {
     const TileLayout& L = c->layout;
     FrameDev f;
     f.W = L.width; f.H = L.height; f.tile_w = L.tile_w; f.tile_h = L.tile_h; f.tiles_x = L.tiles_x;
@@ -517,6 +585,29 @@ FrameDev frame_dev(const rt_ctx* c) {
     f.n_tiles_owned = L.n_tiles_owned;
     f.n_local_pix = L.n_tiles_owned * (uint32_t)f.tile_pix;
     f.tile_ids = c->d_tile_ids.p;
+    f.pool_ids = c->d_pool_ids.p;
+    f.n_pool_blocks = L.n_pool_tiles * ((uint32_t)f.tile_pix / 32u);
+    f.stolen_map = c->d_stolen_map.p;
+    f.steal_cursor = nullptr;
+    if (L.pool_div && L.n_pool_tiles) {
+        uint32_t slot = p->frame_index % 64u;
+        if (p->steal_cursor) {
+            f.steal_cursor = (uint32_t*)p->steal_cursor + slot;
+            // rank 0 owns the cursor array: clear the slot that comes into use 32 frames from now (every
+            // rank has passed this frame's completion barrier long before it gets there)
+            if (L.rank == 0)
+                RT_CUDA(cudaMemsetAsync((uint32_t*)p->steal_cursor + (p->frame_index + 32u) % 64u, 0, sizeof(uint32_t), c->stream));
+        } else {
+            // no shared cursor: logical ranks rendered one after the other by this context
+            c->d_local_cursor.reserve(64);
+            if (!c->local_cursor_valid || c->local_cursor_frame != p->frame_index) {
+                RT_CUDA(cudaMemsetAsync(c->d_local_cursor.p, 0, 64 * sizeof(uint32_t), c->stream));
+                c->local_cursor_valid = true;
+                c->local_cursor_frame = p->frame_index;
+            }
+            f.steal_cursor = c->d_local_cursor.p + slot;
+        }
+    }
     return f;
 }
 
@@ -665,11 +756,12 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
                      const rt_aux_out* aux_dev, rt_frame_stats* stats) {
     cudaStream_t st = c->stream;
     setup_layout(c, cam, p);
-    FrameDev f = frame_dev(c);
+    FrameDev f = frame_dev(c, p);
     const bool count = (p->flags & RT_FLAG_COUNT_WORK) != 0;
     const bool bounce = c->has_reflective && p->max_depth >= 1;
-    ensure_queues(c, f.n_local_pix, bounce);
-    c->d_accum.reserve(3 * (size_t)(f.n_local_pix ? f.n_local_pix : 1));
+    const size_t pix_cap = (size_t)f.n_local_pix + (size_t)f.n_pool_blocks * 32u;   // own tiles + everything stealable
+    ensure_queues(c, pix_cap, bounce);
+    c->d_accum.reserve(3 * (pix_cap ? pix_cap : 1));
 
     RT_CUDA(cudaEventRecord(c->ev[0], st));
     RT_CUDA(cudaMemsetAsync(c->d_waves.p, 0, RT_WAVE_SLOTS * sizeof(WaveCounters), st));
@@ -691,12 +783,13 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     sa.max_depth = p->max_depth;
 
     uint32_t launches = 0;
-    if (f.n_local_pix) launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, c->ev[1], c->ev[2]);
+    const bool has_work = f.n_local_pix > 0 || f.steal_cursor != nullptr;
+    if (has_work) launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, c->ev[1], c->ev[2]);
     else { RT_CUDA(cudaEventRecord(c->ev[1], st)); RT_CUDA(cudaEventRecord(c->ev[2], st)); }
     RT_CUDA(cudaEventRecord(c->ev[3], st));
 
     WaveResult wr;
-    if (bounce && f.n_local_pix) {
+    if (bounce && has_work) {
         ta.aux_prim = nullptr; ta.aux_t = nullptr;
         // wave 0 wrote its children into queue 1
         wr = run_bounce_waves(c, ta, sa, 1, 1, p->max_depth, count, true);
@@ -704,10 +797,10 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     }
     RT_CUDA(cudaEventRecord(c->ev[6], st));
 
-    if (f.n_local_pix && rgb_dev) {
-        uint32_t quads = f.n_tiles_owned * (uint32_t)(f.tile_pix / 4);
+    if (has_work && rgb_dev) {
+        uint32_t quads = f.n_tiles_owned * (uint32_t)(f.tile_pix / 4) + (f.steal_cursor ? f.n_pool_blocks * 8u : 0u);
         k_resolve<<<(quads + 255) / 256, 256, 0, st>>>(f, c->d_accum.p, (uint8_t*)rgb_dev,
-                                                       (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0);
+                                                       (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0, c->d_frame.p);
         RT_CUDA(cudaGetLastError());
         launches++;
     }
@@ -728,20 +821,8 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         }
     }
     memset(stats, 0, sizeof *stats);
-    stats->rays_primary = (uint64_t)cam->width * (uint64_t)cam->height;
-    if (c->layout.world > 1) {   // in-frame pixels of the owned tiles
-        uint64_t np = 0;
-        const TileLayout& L = c->layout;
-        uint32_t total = (uint32_t)L.tiles_x * (uint32_t)L.tiles_y;
-        for (uint32_t t = (uint32_t)L.rank; t < total; t += (uint32_t)L.world) {
-            int tx = (int)(t % (uint32_t)L.tiles_x), ty = (int)(t / (uint32_t)L.tiles_x);
-            int w = L.width - tx * L.tile_w, h = L.height - ty * L.tile_h;
-            if (w > L.tile_w) w = L.tile_w;
-            if (h > L.tile_h) h = L.tile_h;
-            np += (uint64_t)w * (uint64_t)h;
-        }
-        stats->rays_primary = np;
-    }
+    stats->rays_primary = c->h_frame->rays_primary;
+    stats->stolen_blocks = c->h_frame->stolen_blocks;
     stats->rays_shadow = c->h_frame->rays_shadow;
     stats->rays_secondary = secondary;
     stats->node_visits = c->h_frame->node_visits[0];

@@ -70,7 +70,8 @@ struct WaveCounters {
 #define RT_WAVE_SLOTS 64
 
 struct FrameCounters {
-    unsigned long long rays_shadow;
+    unsigned long long rays_primary, rays_shadow;
+    unsigned int stolen_blocks, pad;
     unsigned long long node_visits[2], tri_tests[2];   // [0] nearest-hit rays, [1] any-hit (shadow) rays
 };
 
@@ -82,12 +83,13 @@ struct RayQueue {
 };
 
 struct TileLayout {
-    int width = 0, height = 0, tile_w = 0, tile_h = 0, rank = 0, world = 1;
+    int width = 0, height = 0, tile_w = 0, tile_h = 0, rank = 0, world = 1, pool_div = 0;
     int tiles_x = 0, tiles_y = 0;
-    uint32_t n_tiles_owned = 0;
+    uint32_t n_tiles_owned = 0;    // statically owned by this rank
+    uint32_t n_pool_tiles = 0;     // shared pool (dynamic stealing)
     bool operator==(const TileLayout& o) const {
         return width == o.width && height == o.height && tile_w == o.tile_w && tile_h == o.tile_h && rank == o.rank &&
-               world == o.world;
+               world == o.world && pool_div == o.pool_div;
     }
 };
 
@@ -128,7 +130,10 @@ struct rt_ctx {
 
     // ---- render state
     TileLayout layout;
-    DevBuf<uint32_t> d_tile_ids;
+    DevBuf<uint32_t> d_tile_ids, d_pool_ids, d_stolen_map;
+    DevBuf<uint32_t> d_local_cursor;       // stand-in steal cursor when the caller passes none
+    bool local_cursor_valid = false;
+    uint32_t local_cursor_frame = 0;
     DevBuf<long long> d_accum;             // 3 per local pixel, 32.32 fixed point
     DevBuf<float4> d_q[2][3];              // two ray queues x (o_pix, d_lvl, w)
     DevBuf<float4> d_hits;                 // HitRec per ray slot

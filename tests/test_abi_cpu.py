@@ -35,8 +35,8 @@ def test_struct_sizes_match_the_header():
     from realtrace_b200 import api, scene
     assert C.sizeof(api.RtMaterial) == 40 == scene.MATERIAL_DTYPE.itemsize
     assert C.sizeof(api.RtCamera) == 64
-    assert C.sizeof(api.RtRenderParams) == 24
-    assert C.sizeof(api.RtFrameStats) == 96       # 7 x u64, 4 x u32, 6 x float
+    assert C.sizeof(api.RtRenderParams) == 40
+    assert C.sizeof(api.RtFrameStats) == 104      # 7 x u64, 6 x u32, 6 x float
 
 
 def test_tile_layout_is_pure_host_code(lib):

@@ -209,3 +209,30 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(api.RtError):
         ctx.render(cam, depth, tile=(30, 30))
     ctx.close()
+
+
+@pytest.mark.parametrize("world,pool_div", [(2, 2), (4, 4), (8, 3)])
+def test_dynamic_tile_stealing_is_bit_identical(world, pool_div):
+    """Logical ranks rendered one after the other into ONE frame: every pool_div-th tile group is not
+    owned by anybody; the rank that gets there first claims its 8x4 blocks from the shared cursor.
+    The frame must equal the single-rank frame bit for bit, every pixel traced exactly once."""
+    import torch
+    scene, cam, depth, _ = build_case("blubmixed_d5")
+    cam.width, cam.height = 456, 270          # ragged edge tiles, 8 x 9 tiles
+    ctx = make_ctx(scene)
+    full = ctx.render(cam, depth)[0]
+    for frame_index in (0, 1, 70):            # 70: slot wrap-around of the 64-entry cursor array
+        frame = torch.zeros(cam.height * cam.width * 3, dtype=torch.uint8, device="cuda")
+        primary, stolen = 0, 0
+        order = list(range(world)) if frame_index != 1 else list(reversed(range(world)))
+        for r in order:
+            st = ctx.render_device(cam, depth, frame.data_ptr(), rank=r, world=world,
+                                   steal=(pool_div, frame_index, None))
+            primary += st["rays_primary"]
+            stolen += st["stolen_blocks"]
+        torch.cuda.synchronize()
+        out = frame.cpu().numpy().reshape(cam.height, cam.width, 3)
+        assert primary == cam.width * cam.height
+        assert stolen > 0
+        assert np.array_equal(out, full), frame_index
+    ctx.close()
