@@ -214,6 +214,8 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     # tiles + NCCL gather + scatter kernel on rank 0.
     assemble = "single"
     packed = gathered = None
+    cursor_ptr = None
+    frame_no = [0]
     if world > 1:
         assemble = args.assemble
         if assemble == "p2p":
@@ -226,6 +228,13 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
                 torch.distributed.broadcast(hbuf, 0)
                 if rank != 0:
                     frame_ptr = ctx.shared_buffer_open(hbuf.cpu().numpy().tobytes())
+                if args.steal_div > 0:                  # the shared tile-stealing cursor (64 x uint32) lives on rank 0
+                    if rank == 0:
+                        cursor_ptr, handle = ctx.shared_buffer_create(256)
+                        hbuf.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+                    torch.distributed.broadcast(hbuf, 0)
+                    if rank != 0:
+                        cursor_ptr = ctx.shared_buffer_open(hbuf.cpu().numpy().tobytes())
             except Exception as e:   # noqa: BLE001 — any failure means "use the gather path"
                 print(f"[bench rank {rank}] CUDA IPC unavailable ({e}); falling back to gather", file=sys.stderr)
                 ok = 0
@@ -251,7 +260,9 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         if world == 1:
             return ctx.render_device(cam, depth, frame_ptr, want_stats=want_stats)
         if assemble == "p2p":
-            st = ctx.render_device(cam, depth, frame_ptr, rank=rank, world=world, want_stats=want_stats)
+            steal = (args.steal_div, frame_no[0], cursor_ptr) if cursor_ptr else None
+            frame_no[0] += 1
+            st = ctx.render_device(cam, depth, frame_ptr, rank=rank, world=world, want_stats=want_stats, steal=steal)
             torch.distributed.all_reduce(tick)          # completion barrier: all tiles are in rank 0's frame
             return st
         st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES,
@@ -382,7 +393,8 @@ def run_gpu_arm(args):
                        "max_depth": depth, "triangles": int(len(scene.tri_v)), "lights": int(len(scene.lights)),
                        "rays_per_frame": main["rays_per_frame"],
                        "parallelism": (f"{world} GPUs, interleaved 64x32 tiles, scene replicated, frame assembly: "
-                                       + {"p2p": "resolve kernels store into rank 0's frame over NVLink (CUDA IPC) + all-reduce barrier",
+                                       + {"p2p": "resolve kernels store into rank 0's frame over NVLink (CUDA IPC) + all-reduce barrier"
+                                                 + (f", dynamic tile stealing (1/{args.steal_div} of the tile groups pooled)" if args.steal_div > 0 else ""),
                                           "gather": "packed tiles + NCCL gather + scatter kernel"}[main["assemble"]])
                        if world > 1 else "1 GPU",
                        "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"},
@@ -461,6 +473,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "gather"], help="N > 1 frame assembly")
+    ap.add_argument("--steal-div", type=int, default=4,
+                    help="N > 1 with p2p assembly: every k-th tile group forms the shared pool ranks steal from (0 = off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

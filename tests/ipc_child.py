@@ -19,7 +19,11 @@ def main():
     ctx.set_scene(scene)
     ctx.commit()
     ptr = ctx.shared_buffer_open(handle)
-    ctx.render_device(cam, depth, ptr, rank=rank, world=world, want_stats=False)   # asynchronous frame
+    steal = None
+    if len(sys.argv) > 6:
+        cursor = ctx.shared_buffer_open(bytes.fromhex(sys.argv[6]))
+        steal = (int(sys.argv[7]), int(sys.argv[8]), cursor)
+    ctx.render_device(cam, depth, ptr, rank=rank, world=world, want_stats=False, steal=steal)   # asynchronous frame
     ctx.synchronize()
     ctx.close()
     print("IPC_CHILD_OK", flush=True)

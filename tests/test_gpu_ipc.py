@@ -33,6 +33,28 @@ def test_two_processes_assemble_one_frame_through_ipc():
     assert np.array_equal(out, full)
 
 
+def test_two_processes_steal_from_one_cursor():
+    """The stealing cursor is mapped by a second process too (system-scope atomics on IPC memory)."""
+    scene, cam, depth, _ = build_case("blubmixed_d5")
+    cam.width, cam.height = 456, 270
+    ctx = api.Context(0)
+    ctx.set_scene(scene)
+    ctx.commit()
+    full = ctx.render(cam, depth)[0]
+    ptr, handle = ctx.shared_buffer_create(cam.width * cam.height * 3)
+    cursor, chandle = ctx.shared_buffer_create(256)
+    # the child (rank 1) goes first and takes the whole pool; the parent then only finds its own tiles
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ipc_child.py"), handle.hex(), "1", "2",
+                        str(cam.width), str(cam.height), chandle.hex(), "2", "5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "IPC_CHILD_OK" in r.stdout, r.stdout + r.stderr
+    st = ctx.render_device(cam, depth, ptr, rank=0, world=2, steal=(2, 5, cursor))
+    out = np.zeros((cam.height, cam.width, 3), np.uint8)
+    ctx.download(ptr, out)
+    ctx.close()
+    assert st["stolen_blocks"] == 0 and st["rays_primary"] < cam.width * cam.height // 2
+    assert np.array_equal(out, full)
+
+
 def test_async_frames_then_synchronize():
     scene, cam, depth, _ = build_case("bobtex_d3")
     ctx = api.Context(0)
