@@ -31,6 +31,7 @@ constexpr int TRAV_TPB = 128;
 constexpr int SHADE_TPB = 128;
 
 enum { MODE_PRIMARY = 0, MODE_QUEUE = 1, MODE_SHADOW = 2 };
+#define RT_STEAL_RUN 4        // 8x4-pixel blocks claimed from the shared pool per system-scope atomic
 
 struct CamDev {
     double pos[3], u[3], v[3], w[3];
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
     int node = RT_DONE, sp = 0;
     bool active = false, found = false, exhausted = false, overflow = false;
     bool steal_done = !(MODE == MODE_PRIMARY && a.f.steal_cursor != nullptr && a.f.n_pool_blocks > 0);
+    uint32_t steal_left = 0, steal_slot = 0;
     uint32_t item = 0, pix = 0;
     int pi = 0, pj = 0;
     f3 w = mk3(1, 1, 1);
@@ -180,21 +182,29 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
             my = base + __popc(need & lt);
             have = !active && my < n;
         } else if (MODE == MODE_PRIMARY && exhausted && !steal_done && need == FULL) {
-            // own tiles are done: claim one 8x4 block of the shared pool (system-scope atomic: the
-            // cursor lives in rank 0's memory and is reached over NVLink by the other ranks)
-            uint32_t pb = 0, slot = 0;
-            if (lane == 0) {
-                pb = atomicAdd_system(a.f.steal_cursor, 1u);
-                if (pb < a.f.n_pool_blocks) {
-                    slot = atomicAdd(&a.fc->stolen_blocks, 1u);
-                    a.f.stolen_map[slot] = pb;
+            // own tiles are done: work through the shared pool in runs of RT_STEAL_RUN 8x4 blocks, one
+            // system-scope atomic per run (the cursor lives in rank 0's memory, reached over NVLink)
+            if (steal_left == 0) {
+                uint32_t pb = 0, slot = 0, cnt = 0;
+                if (lane == 0) {
+                    pb = atomicAdd_system(a.f.steal_cursor, (uint32_t)RT_STEAL_RUN);
+                    if (pb < a.f.n_pool_blocks) {
+                        cnt = min((uint32_t)RT_STEAL_RUN, a.f.n_pool_blocks - pb);
+                        slot = atomicAdd(&a.fc->stolen_blocks, cnt);
+                        for (uint32_t k = 0; k < cnt; k++) a.f.stolen_map[slot + k] = pb + k;
+                    }
                 }
+                __syncwarp();
+                steal_left = __shfl_sync(FULL, cnt, 0);
+                steal_slot = __shfl_sync(FULL, slot, 0);
+                if (steal_left == 0) steal_done = true;
             }
-            __syncwarp();
-            pb = __shfl_sync(FULL, pb, 0);
-            slot = __shfl_sync(FULL, slot, 0);
-            if (pb >= a.f.n_pool_blocks) steal_done = true;
-            else { my = a.f.n_local_pix + slot * 32u + (uint32_t)lane; have = true; }
+            if (steal_left) {
+                my = a.f.n_local_pix + steal_slot * 32u + (uint32_t)lane;
+                have = true;
+                steal_slot++;
+                steal_left--;
+            }
         }
         {
             if (have) {
