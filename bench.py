@@ -473,7 +473,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "gather"], help="N > 1 frame assembly")
-    ap.add_argument("--steal-div", type=int, default=8,
+    ap.add_argument("--steal-div", type=int, default=0,
                     help="N > 1 with p2p assembly: every k-th tile group forms the shared pool ranks steal from (0 = off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
