@@ -254,9 +254,18 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    orbit = workload == "orbit"
+    orbit_k = [0]
+
     def step_device(want_stats=False):
         """One frame with everything resident: render (+ assembly at N > 1).  Without stats the call only
-        enqueues work on the stream."""
+        enqueues work on the stream.  Workload "orbit" (config 5): every frame first refits the LBVH
+        (rt_scene_commit REFIT) and moves the camera one step along the 120-frame orbit."""
+        nonlocal cam
+        if orbit:
+            ctx.commit(api.COMMIT_REFIT, want_stats=False)
+            cam = scenes.orbit_camera(orbit_k[0] % 120, width=W, height=H)
+            orbit_k[0] += 1
         if world == 1:
             return ctx.render_device(cam, depth, frame_ptr, want_stats=want_stats)
         if assemble == "p2p":
@@ -292,6 +301,9 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     sampler.t_end = time.perf_counter()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     rays_local = total_rays(stats[-1]) * steps          # static scene + camera: every frame casts the same rays
+    if orbit:                                           # moving camera: count the rays of the timed frames exactly
+        orbit_k[0] -= steps
+        rays_local = sum(total_rays(step_device(True)) for _ in range(steps))
     launches = stats[-1]["kernel_launches"] * steps + ((world if rank == 0 else 0) * steps if assemble == "gather" else 0)
     if world > 1:
         t = torch.tensor([ms, float(rays_local), float(launches)], dtype=torch.float64, device=dev)

@@ -191,9 +191,11 @@ class Context:
         bg = (C.c_float * 3)(*s.background)
         self._check(lib.rt_scene_set_environment(h, amb, bg))
 
-    def commit(self, mode=COMMIT_BUILD):
+    def commit(self, mode=COMMIT_BUILD, want_stats=True):
+        """BUILD uploads + builds the LBVH (synchronous); REFIT only enqueues the refit kernels —
+        pass want_stats=False to keep it asynchronous."""
         self._check(self.lib.rt_scene_commit(self.h, mode))
-        return self.build_stats()
+        return self.build_stats() if want_stats else None
 
     def update_vertices(self, tri_v):
         v = np.ascontiguousarray(tri_v, np.float32).reshape(-1, 9)

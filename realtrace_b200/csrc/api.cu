@@ -246,6 +246,11 @@ int rt_scene_update_vertices(rt_ctx* ctx, const float* v, uint32_t n) {
 int rt_scene_build_stats(rt_ctx* ctx, rt_build_stats* out) {
     return guarded(ctx, [&] {
         need(out != nullptr, "rt_scene_build_stats: out is NULL");
+        if (ctx->refit_pending) {
+            RT_CUDA(cudaEventSynchronize(ctx->ev[9]));
+            RT_CUDA(cudaEventElapsedTime(&ctx->build_stats.ms_refit, ctx->ev[8], ctx->ev[9]));
+            ctx->refit_pending = false;
+        }
         *out = ctx->build_stats;
     });
 }

@@ -327,11 +327,11 @@ static void run_refit(rt_ctx* c) {
 void rt_build_bvh(rt_ctx* c, bool refit_only) {
     cudaStream_t st = c->stream;
     if (refit_only) {
-        RT_CUDA(cudaEventRecord(c->ev[4], st));
+        // asynchronous: only enqueues; rt_scene_build_stats reads the event pair later
+        RT_CUDA(cudaEventRecord(c->ev[8], st));
         run_refit(c);
-        RT_CUDA(cudaEventRecord(c->ev[5], st));
-        RT_CUDA(cudaEventSynchronize(c->ev[5]));
-        RT_CUDA(cudaEventElapsedTime(&c->build_stats.ms_refit, c->ev[4], c->ev[5]));
+        RT_CUDA(cudaEventRecord(c->ev[9], st));
+        c->refit_pending = true;
         publish_scene(c);
         return;
     }

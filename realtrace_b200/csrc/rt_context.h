@@ -152,7 +152,8 @@ struct rt_ctx {
     DevBuf<uint32_t> d_sticky;             // bit0 ray-queue overflow, bit1 traversal stack overflow
     uint32_t* h_sticky = nullptr;          // pinned
     std::vector<void*> ipc_opened, ipc_created;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};               // 0-3,6,7 frame; 4,5 build; 8,9 refit
+    bool refit_pending = false;
     int trace_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
     int blocks_per_sm = 0;                 // 0 = as many persistent CTAs as fit
     // idle lanes a warp waits for before fetching new rays (k_traverse); measured on B200 (profiles/r1_tuning.md):
