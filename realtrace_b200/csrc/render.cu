@@ -140,9 +140,14 @@ struct TravArgs {
     int loop_style;           // 0: while-while; k > 0: if-if in bursts of k steps
 };
 
-template <int MODE, bool COUNT>
+// FUSE (nearest-hit modes only): a lane whose ray hit something does not go idle — it turns into
+// the shadow ray(s) of that hit (one per light, same walk with early exit) and only then emits the
+// hit together with its occlusion bits.  One kernel and one tail per wave instead of two, no second
+// derivation of the hit point, and lanes whose rays missed keep pulling new rays meanwhile.
+template <int MODE, bool COUNT, bool FUSE>
 __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ TravArgs a) {
     constexpr bool ANY = MODE == MODE_SHADOW;
+    static_assert(!(FUSE && ANY), "FUSE applies to the nearest-hit modes");
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -165,9 +170,25 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
     uint32_t item = 0, pix = 0;
     int pi = 0, pj = 0;
     f3 w = mk3(1, 1, 1);
-    WorkCount wc;
-    wc.nodes = wc.tris = 0;
-    uint32_t traced = 0;
+    WorkCount wc, wcs;
+    wc.nodes = wc.tris = wcs.nodes = wcs.tris = 0;
+    uint32_t traced = 0, traced_shadow = 0;
+    // FUSE: phase < 0 = nearest-hit query, phase = li >= 0 = shadow ray towards light li of the saved hit
+    int phase = -1;
+    HitRec nh;
+    nh.t = RT_FLT_MAX; nh.prim = RT_MISS; nh.beta = nh.gamma = 0.0f;
+    f3 P = mk3(0, 0, 0);
+    uint32_t occl_mask = 0;
+    auto start_shadow = [&](int li) {
+        f3 toL = mk3(__ldg(a.s.lights + 2 * li)) - P;
+        f3 sd = normalize(toL);
+        r = prep_ray(fma3(toL, 0.01f, P), sd);                 // world.cpp:45
+        hit.t = RT_FLT_MAX; hit.prim = RT_MISS;
+        found = false;
+        sp = 0;
+        node = (use_bvh && sd.x == sd.x && sd.y == sd.y && sd.z == sd.z) ? 0 : RT_DONE;
+        traced_shadow++;
+    };
 
     for (;;) {
         // ---- refill idle lanes from the global cursor
@@ -254,6 +275,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
                     hit.t = RT_FLT_MAX; hit.prim = RT_MISS; hit.beta = hit.gamma = 0.0f;
                     found = false;
                     active = true;
+                    phase = -1;
                     sp = 0;
                     // a NaN direction (ignored refract() failure, world.cpp:83) misses everything
                     bool finite = d.x == d.x && d.y == d.y && d.z == d.z;
@@ -267,17 +289,19 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
             if (exhausted && steal_done) break;
             continue;
         }
-        // ---- while-while traversal of the lanes that own a ray
+        // ---- traversal of the lanes that own a ray
+        const bool any = FUSE ? phase >= 0 : ANY;
+        WorkCount* wcp = COUNT ? (any ? &wcs : &wc) : nullptr;
         if (active) {
             if (a.loop_style == 0) {
                 while (rt_is_internal(node)) {
-                    if (COUNT) wc.nodes++;
+                    if (COUNT) wcp->nodes++;
                     node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                 }
                 while (node < 0) {
-                    if (leaf_test(a.s, node, r, hit, ANY, COUNT ? &wc : nullptr)) {
+                    if (leaf_test(a.s, node, r, hit, any, wcp)) {
                         found = true;
-                        if (ANY) { node = RT_DONE; break; }
+                        if (any) { node = RT_DONE; break; }
                     }
                     node = sp ? stack[--sp] : RT_DONE;
                 }
@@ -286,12 +310,12 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
                 // number of iterations before the warp looks at its refill state again
                 for (int it = 0; it < a.loop_style && node != RT_DONE; it++) {
                     if (rt_is_internal(node)) {
-                        if (COUNT) wc.nodes++;
+                        if (COUNT) wcp->nodes++;
                         node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                     } else {
-                        if (leaf_test(a.s, node, r, hit, ANY, COUNT ? &wc : nullptr)) {
+                        if (leaf_test(a.s, node, r, hit, any, wcp)) {
                             found = true;
-                            if (ANY) { node = RT_DONE; break; }
+                            if (any) { node = RT_DONE; break; }
                         }
                         node = sp ? stack[--sp] : RT_DONE;
                     }
@@ -300,21 +324,29 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
         }
         // ---- rays that ran out of nodes: linear primitives, then the result
         bool fin = active && node == RT_DONE;
+        bool emit = false;
         if (fin) {
             bool finite = r.d.x == r.d.x && r.d.y == r.d.y && r.d.z == r.d.z;
-            if (finite && !(ANY && found)) {
-                if (a.brute) found |= brute_walk<ANY>(a.s, r, hit, COUNT ? &wc : nullptr);
-                for (int k = 0; k < a.s.n_analytic && !(ANY && found); k++) {
+            if (finite && !(any && found)) {
+                if (a.brute) found |= any ? brute_walk<true>(a.s, r, hit, wcp) : brute_walk<false>(a.s, r, hit, wcp);
+                for (int k = 0; k < a.s.n_analytic && !(any && found); k++) {
                     const AnalyticPrim p = a.s.analytic[k];
-                    if (COUNT) wc.tris++;
+                    if (COUNT) wcp->tris++;
                     if (analytic_test(p, r.o, r.d, hit.t, hit.beta, hit.gamma)) {
                         hit.prim = rt_analytic_code(k);
                         found = true;
                     }
                 }
             }
-            if (ANY) {
-                a.occl[item] = found ? 1 : 0;
+            if (any) {
+                if (FUSE) {
+                    occl_mask |= (found ? 1u : 0u) << phase;
+                    phase++;
+                    if (phase < a.s.n_lights) { start_shadow(phase); fin = false; }
+                    else emit = true;
+                } else {
+                    a.occl[item] = found ? 1 : 0;
+                }
             } else {
                 if (a.aux_prim) {
                     size_t at = MODE == MODE_PRIMARY ? (size_t)pi + (size_t)pj * a.f.W : (size_t)pix;
@@ -326,22 +358,42 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
                     a.aux_prim[at] = id;
                     if (a.aux_t) a.aux_t[at] = found ? hit.t : RT_FLT_MAX;
                 }
-                if (!found) accumulate<MODE == MODE_PRIMARY>(a.accum, pix, w * bg);      // world.cpp:110
+                if (!found) {
+                    accumulate<MODE == MODE_PRIMARY>(a.accum, pix, w * bg);      // world.cpp:110
+                } else {
+                    nh = hit;
+                    occl_mask = 0;
+                    emit = true;
+                    if (FUSE && a.s.n_lights > 0) {
+                        // dielectric hits discard their local colour (world.cpp:77-100): no shadow query
+                        uint32_t mat = hit.prim >= 0 ? __float_as_uint(__ldg(a.s.tris + 3 * (size_t)hit.prim + 1).w)
+                                                     : a.s.analytic[rt_analytic_index(hit.prim)].material;
+                        float4 m1 = __ldg(a.s.materials + 3 * mat + 1);
+                        if (!(m1.z > 0.0f && m1.w > 0.0f)) {
+                            P = fma3(r.d, hit.t, r.o);
+                            phase = 0;
+                            start_shadow(0);
+                            emit = false;
+                            fin = false;
+                        }
+                    }
+                }
             }
-            active = false;
+            if (fin) active = false;
         }
         if (!ANY) {
             // hits: one atomic per warp reserves a run of the hit queue
-            uint32_t mask = __ballot_sync(FULL, fin && found);
+            uint32_t mask = __ballot_sync(FULL, emit);
             if (mask) {
                 uint32_t qbase = 0;
                 int leader = __ffs(mask) - 1;
                 if (lane == leader) qbase = atomicAdd(&a.wave->n_hits, (uint32_t)__popc(mask));
                 qbase = __shfl_sync(FULL, qbase, leader);
-                if (fin && found) {
+                if (emit) {
                     uint32_t pos = qbase + __popc(mask & lt);
                     a.hitq[pos] = item;
-                    a.hits[pos] = make_float4(hit.t, __int_as_float(hit.prim), hit.beta, hit.gamma);
+                    a.hits[pos] = make_float4(nh.t, __int_as_float(nh.prim), nh.beta, nh.gamma);
+                    if (FUSE) a.occl[pos] = (uint8_t)occl_mask;
                 }
             }
         }
@@ -350,11 +402,20 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
         uint32_t ns = warp_sum(traced);
         if (lane == 0 && ns) atomicAdd(ANY ? &a.fc->rays_shadow : &a.fc->rays_primary, (unsigned long long)ns);
     }
+    if (FUSE) {
+        uint32_t ns = warp_sum(traced_shadow);
+        if (lane == 0 && ns) atomicAdd(&a.fc->rays_shadow, (unsigned long long)ns);
+    }
     if (COUNT) {
         uint32_t nn = warp_sum(wc.nodes), nt = warp_sum(wc.tris);
+        uint32_t sn = warp_sum(wcs.nodes), st = warp_sum(wcs.tris);
         if (lane == 0) {
             atomicAdd(&a.fc->node_visits[ANY ? 1 : 0], (unsigned long long)nn);
             atomicAdd(&a.fc->tri_tests[ANY ? 1 : 0], (unsigned long long)nt);
+            if (FUSE) {
+                atomicAdd(&a.fc->node_visits[1], (unsigned long long)sn);
+                atomicAdd(&a.fc->tri_tests[1], (unsigned long long)st);
+            }
         }
     }
     if (__any_sync(FULL, overflow) && lane == 0) atomicOr(a.sticky, 2u);
@@ -374,6 +435,7 @@ struct ShadeArgs {
     uint32_t* sticky;
     uint32_t cap;
     int max_depth;
+    int occl_bits;            // 1: occl[hit] is a bit mask over lights (fused traversal); 0: occl[light][hit] bytes
 };
 
 // Shading proper: no traversal in here, the shadow answers come from k_traverse<SHADOW>.
@@ -411,7 +473,11 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
                 level = __float_as_int(rd.w);
             }
             uint32_t li = 0;
-            auto any_hit = [&](f3, f3) -> bool { return a.occl[(size_t)(li++) * n + pos] != 0; };
+            auto any_hit = [&](f3, f3) -> bool {
+                bool o2 = a.occl_bits ? ((a.occl[pos] >> li) & 1u) != 0 : a.occl[(size_t)li * n + pos] != 0;
+                li++;
+                return o2;
+            };
             shade_hit(a.s, o, d, level, h, a.max_depth, any_hit, out);
             accumulate<PRIMARY>(a.accum, pix, w * (out.local + out.bg_weight * bg));
         }
@@ -644,11 +710,11 @@ RayQueue queue_of(rt_ctx* c, int b) {
     return q;
 }
 
-template <int MODE>
+template <int MODE, bool FUSE>
 void launch_traverse(rt_ctx* c, const TravArgs& a, bool count) {
-    int blocks = MODE == MODE_SHADOW ? c->shadow_blocks : c->trace_blocks;
-    if (count) k_traverse<MODE, true><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
-    else k_traverse<MODE, false><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+    int blocks = MODE == MODE_SHADOW ? c->shadow_blocks : (FUSE ? c->fused_blocks : c->trace_blocks);
+    if (count) k_traverse<MODE, true, FUSE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+    else k_traverse<MODE, false, FUSE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
     RT_CUDA(cudaGetLastError());
 }
 template <bool PRIMARY>
@@ -667,18 +733,26 @@ uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot
     ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p;
     ta.refill_min = PRIMARY ? c->refill_primary : c->refill_queue;
     ta.loop_style = PRIMARY ? c->loop_primary : c->loop_queue;
-    launch_traverse<PRIMARY ? MODE_PRIMARY : MODE_QUEUE>(c, ta, count);
+    const bool fuse = shade && c->fuse_shadow && c->scene.n_lights > 0 && c->scene.n_lights <= 8;
+    if (fuse) {
+        ta.occl = c->d_occl.p;
+        ta.refill_min = PRIMARY ? c->refill_primary_fused : c->refill_queue;
+        launch_traverse<PRIMARY ? MODE_PRIMARY : MODE_QUEUE, true>(c, ta, count);
+    } else {
+        launch_traverse<PRIMARY ? MODE_PRIMARY : MODE_QUEUE, false>(c, ta, count);
+    }
     launches++;
     if (after_trace) RT_CUDA(cudaEventRecord(after_trace, c->stream));
     if (!shade) return launches;
-    if (c->scene.n_lights > 0) {
+    sa.occl_bits = fuse ? 1 : 0;
+    if (!fuse && c->scene.n_lights > 0) {
         TravArgs sh = ta;
         sh.hits_in = c->d_hits.p; sh.hitq_in = c->d_hitq.p; sh.occl = c->d_occl.p;
         sh.primary_wave = PRIMARY ? 1u : 0u;
         sh.refill_min = c->refill_shadow;
         sh.loop_style = c->loop_shadow;
         sh.aux_prim = nullptr; sh.aux_t = nullptr;
-        launch_traverse<MODE_SHADOW>(c, sh, count);
+        launch_traverse<MODE_SHADOW, false>(c, sh, count);
         launches++;
     }
     if (after_shadow) RT_CUDA(cudaEventRecord(after_shadow, c->stream));
@@ -744,14 +818,17 @@ void rt_sync_and_check(rt_ctx* c) {
 
 void rt_render_init(rt_ctx* c) {
     auto lo = [](int a, int b) { return a < b ? a : b; };
-    c->trace_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false>, TRAV_TPB, c->sm_count),
-                         persistent_blocks(k_traverse<MODE_QUEUE, false>, TRAV_TPB, c->sm_count));
-    c->shadow_blocks = persistent_blocks(k_traverse<MODE_SHADOW, false>, TRAV_TPB, c->sm_count);
+    c->trace_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false, false>, TRAV_TPB, c->sm_count),
+                         persistent_blocks(k_traverse<MODE_QUEUE, false, false>, TRAV_TPB, c->sm_count));
+    c->fused_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false, true>, TRAV_TPB, c->sm_count),
+                         persistent_blocks(k_traverse<MODE_QUEUE, false, true>, TRAV_TPB, c->sm_count));
+    c->shadow_blocks = persistent_blocks(k_traverse<MODE_SHADOW, false, false>, TRAV_TPB, c->sm_count);
     c->shade_blocks = lo(persistent_blocks(k_shade<true>, SHADE_TPB, c->sm_count),
                          persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
     if (c->blocks_per_sm > 0) {   // RT_BLOCKS_PER_SM: cap the persistent grids (tuning)
         int cap = c->blocks_per_sm * c->sm_count;
         c->trace_blocks = lo(c->trace_blocks, cap);
+        c->fused_blocks = lo(c->fused_blocks, cap);
         c->shadow_blocks = lo(c->shadow_blocks, cap);
     }
     c->d_waves.reserve(RT_WAVE_SLOTS);

@@ -154,7 +154,9 @@ struct rt_ctx {
     std::vector<void*> ipc_opened, ipc_created;
     cudaEvent_t ev[10] = {};               // 0-3,6,7 frame; 4,5 build; 8,9 refit
     bool refit_pending = false;
-    int trace_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
+    int trace_blocks = 0, fused_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
+    int fuse_shadow = 1;                   // shadow rays ride in the lane that found the hit (RT_FUSE_SHADOW)
+    int refill_primary_fused = 16;
     int blocks_per_sm = 0;                 // 0 = as many persistent CTAs as fit
     // idle lanes a warp waits for before fetching new rays (k_traverse); measured on B200 (profiles/r1_tuning.md):
     // coherent primary rays are best refilled as whole warps, shadow and bounce rays lane by lane in groups

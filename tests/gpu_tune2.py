@@ -1,13 +1,13 @@
 """Development probe: loop style / leaf size / refill sweeps, full frame and a 1/8 share."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-configs = [dict()]
-for mb in (10, 12, 16):
-    configs.append(dict(RT_LIB_PATH=os.path.join(ROOT, "tests", "emul", f"librt_mb{mb}.so")))
+configs = [dict(RT_FUSE_SHADOW=0)]
+for r in (8, 16, 24, 32):
+    configs.append(dict(RT_FUSE_SHADOW=1, RT_REFILL_PRIMARY_FUSED=r))
 code = f"""
 import sys, os; sys.path.insert(0, {ROOT!r})
 from realtrace_b200 import api, scenes
-scene, cam, depth, desc = scenes.workload('synth1m')
+scene, cam, depth, desc = scenes.workload(os.environ.get('WL', 'synth1m'))
 ctx = api.Context(0); ctx.set_scene(scene); ctx.commit()
 out = []
 for world in (1, 8):
