@@ -81,6 +81,8 @@ typedef struct rt_render_params {
 } rt_render_params;
 #define RT_FLAG_BRUTE_FORCE   1u  /* test every triangle linearly instead of walking the BVH */
 #define RT_FLAG_COUNT_WORK    2u  /* count BVH node visits / triangle tests (slower)         */
+#define RT_FLAG_WARP_TIMES    8u  /* debug: record start/end time of every warp of the primary
+                                     traversal kernel (read back with rt_debug_warp_times)      */
 #define RT_FLAG_PACKED_TILES  4u  /* output buffer holds this rank's tiles back to back
                                      (tile-local row-major RGB8) instead of a full frame    */
 
@@ -203,6 +205,10 @@ int rt_shade_rays(rt_ctx* ctx, const float* rays, uint32_t n, int32_t max_depth,
  * index into the triangle array given to rt_scene_set_triangles; keys: sorted Morton keys.     */
 int rt_bvh_download(rt_ctx* ctx, float* nodes, uint32_t* tri_order, uint64_t* keys, uint32_t* n_nodes,
                     uint32_t* n_bvh_triangles);
+
+/* Debug timeline (RT_FLAG_WARP_TIMES): out receives {start_ns, end_ns} per warp of the last primary
+ * traversal kernel; *n_warps in: capacity, out: warps written.                                   */
+int rt_debug_warp_times(rt_ctx* ctx, uint64_t* out, uint32_t* n_warps);
 
 /* Device radix sort used by the builder, exposed for its own test: sorts (key, value) pairs
  * given in HOST memory, stable, ascending.                                                     */

@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RT_LIB_PATH") or os.path.join(HERE, "librealtrace_b200.so")   # RT_LIB_PATH: tuning builds only
 
-FLAG_BRUTE_FORCE, FLAG_COUNT_WORK, FLAG_PACKED_TILES = 1, 2, 4
+FLAG_BRUTE_FORCE, FLAG_COUNT_WORK, FLAG_PACKED_TILES, FLAG_WARP_TIMES = 1, 2, 4, 8
 COMMIT_BUILD, COMMIT_REFIT = 0, 1
 
 
@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "rt_scene_set_planes", "rt_scene_set_cylinders", "rt_scene_set_materials", "rt_scene_set_lights",
     "rt_scene_set_environment", "rt_scene_commit", "rt_scene_update_vertices", "rt_scene_build_stats", "rt_render",
     "rt_render_device", "rt_tile_layout", "rt_assemble_tiles", "rt_trace_rays", "rt_shade_rays", "rt_bvh_download",
-    "rt_debug_sort_pairs", "rt_synchronize", "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_download",
+    "rt_debug_sort_pairs", "rt_debug_warp_times", "rt_synchronize", "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_download",
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def load_library():
     lib.rt_shade_rays.argtypes = [vp, fp, C.c_uint32, C.c_int32, C.c_uint32, vp]
     lib.rt_bvh_download.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rt_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.rt_debug_warp_times.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
     lib.rt_synchronize.argtypes = [vp]
     lib.rt_shared_buffer_create.argtypes = [vp, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
     lib.rt_shared_buffer_open.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p)]
@@ -292,6 +293,13 @@ class Context:
         keys = np.zeros(nb.value, np.uint64)
         self._check(self.lib.rt_bvh_download(self.h, _ptr(nodes), _ptr(order), _ptr(keys), C.byref(nn), C.byref(nb)))
         return nodes, order, keys
+
+    def warp_times(self, max_warps=1 << 16):
+        """(n, 2) uint64 {start_ns, end_ns} per warp of the last primary traversal kernel (FLAG_WARP_TIMES)."""
+        out = np.zeros((max_warps, 2), np.uint64)
+        n = C.c_uint32(max_warps)
+        self._check(self.lib.rt_debug_warp_times(self.h, out.ctypes.data, C.byref(n)))
+        return out[:n.value]
 
     def sort_pairs(self, keys, values):
         keys = np.ascontiguousarray(keys, np.uint64).copy()

@@ -409,6 +409,19 @@ int rt_bvh_download(rt_ctx* ctx, float* nodes, uint32_t* tri_order, uint64_t* ke
     });
 }
 
+int rt_debug_warp_times(rt_ctx* ctx, uint64_t* out, uint32_t* n_warps) {
+    return guarded(ctx, [&] {
+        need(out && n_warps, "rt_debug_warp_times: NULL argument");
+        uint32_t have = (uint32_t)(ctx->d_warp_times.cap / 2);
+        uint32_t n = have < *n_warps ? have : *n_warps;
+        if (n) {
+            RT_CUDA(cudaMemcpyAsync(out, ctx->d_warp_times.p, (size_t)n * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        *n_warps = n;
+    });
+}
+
 int rt_debug_sort_pairs(rt_ctx* ctx, uint64_t* keys, uint32_t* values, uint32_t n) {
     return guarded(ctx, [&] {
         need(n == 0 || (keys && values), "rt_debug_sort_pairs: NULL buffer");

@@ -138,6 +138,7 @@ struct TravArgs {
     uint32_t primary_wave;    // SHADOW: the wave's rays are primary rays (regenerated from the pixel)
     int refill_min;           // idle lanes a warp waits for before it fetches new rays
     int loop_style;           // 0: while-while; k > 0: if-if in bursts of k steps
+    unsigned long long* warp_times;   // debug (RT_FLAG_WARP_TIMES): per warp {start, end} in ns, 2 per warp
 };
 
 // FUSE (nearest-hit modes only): a lane whose ray hit something does not go idle — it turns into
@@ -156,6 +157,8 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
     else if (MODE == MODE_QUEUE) n = min(a.wave->n_rays, a.cap);
     else { n_hits_in = a.wave->n_hits; n = n_hits_in * (uint32_t)a.s.n_lights; }
     uint32_t* cursor = ANY ? &a.wave->fetch_shade : &a.wave->fetch_trace;
+    unsigned long long t_start = 0;
+    if (a.warp_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     const f3 bg = mk3(a.s.background[0], a.s.background[1], a.s.background[2]);
     const bool use_bvh = !a.brute && a.s.n_bvh_tris > 0;
 
@@ -419,6 +422,13 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
         }
     }
     if (__any_sync(FULL, overflow) && lane == 0) atomicOr(a.sticky, 2u);
+    if (a.warp_times && lane == 0) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        a.warp_times[2 * wid] = t_start;
+        a.warp_times[2 * wid + 1] = t_end;
+    }
 }
 
 struct ShadeArgs {
@@ -752,6 +762,7 @@ uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot
         sh.refill_min = c->refill_shadow;
         sh.loop_style = c->loop_shadow;
         sh.aux_prim = nullptr; sh.aux_t = nullptr;
+        sh.warp_times = nullptr;
         launch_traverse<MODE_SHADOW, false>(c, sh, count);
         launches++;
     }
@@ -870,6 +881,10 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     sa.sticky = c->d_sticky.p;
     sa.max_depth = p->max_depth;
 
+    if (p->flags & RT_FLAG_WARP_TIMES) {
+        c->d_warp_times.reserve(2 * (size_t)(c->trace_blocks > c->fused_blocks ? c->trace_blocks : c->fused_blocks) * (TRAV_TPB / 32));
+        ta.warp_times = c->d_warp_times.p;
+    }
     uint32_t launches = 0;
     const bool has_work = f.n_local_pix > 0 || f.steal_cursor != nullptr;
     if (has_work) launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, c->ev[1], c->ev[2]);
@@ -879,6 +894,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     WaveResult wr;
     if (bounce && has_work) {
         ta.aux_prim = nullptr; ta.aux_t = nullptr;
+        ta.warp_times = nullptr;
         // wave 0 wrote its children into queue 1
         wr = run_bounce_waves(c, ta, sa, 1, 1, p->max_depth, count, true);
         launches += wr.launches;

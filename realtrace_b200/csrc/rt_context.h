@@ -147,6 +147,7 @@ struct rt_ctx {
     DevBuf<float> d_aux_t;
     DevBuf<float> d_rays_in;               // rt_trace_rays / rt_shade_rays staging
     DevBuf<float> d_rgbf_out;
+    DevBuf<unsigned long long> d_warp_times;   // debug timeline of the primary traversal kernel
     WaveCounters* h_waves = nullptr;       // pinned
     FrameCounters* h_frame = nullptr;      // pinned
     DevBuf<uint32_t> d_sticky;             // bit0 ray-queue overflow, bit1 traversal stack overflow
@@ -156,7 +157,7 @@ struct rt_ctx {
     bool refit_pending = false;
     int trace_blocks = 0, fused_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
     int fuse_shadow = 1;                   // shadow rays ride in the lane that found the hit (RT_FUSE_SHADOW)
-    int refill_primary_fused = 16;
+    int refill_primary_fused = 32;
     int blocks_per_sm = 0;                 // 0 = as many persistent CTAs as fit
     // idle lanes a warp waits for before fetching new rays (k_traverse); measured on B200 (profiles/r1_tuning.md):
     // coherent primary rays are best refilled as whole warps, shadow and bounce rays lane by lane in groups
