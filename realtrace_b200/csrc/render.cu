@@ -49,6 +49,8 @@ struct FrameDev {
     uint32_t n_pool_blocks;                // pool tiles * blocks per tile
     uint32_t* stolen_map;                  // slot -> pool block claimed by this rank
     uint32_t* steal_cursor;                // system-scope cursor of this frame, nullptr = no stealing
+    uint32_t* tile_cost;                   // per owned tile: clocks its warps spent this frame (feedback for the
+                                           // heavy-tiles-first order of the next frame), nullptr = off
 };
 
 // (tile, 8x4 block, lane) -> frame pixel; lane = x%8 + 8*(y%4).
@@ -170,6 +172,8 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
     bool active = false, found = false, exhausted = false, overflow = false;
     bool steal_done = !(MODE == MODE_PRIMARY && a.f.steal_cursor != nullptr && a.f.n_pool_blocks > 0);
     uint32_t steal_left = 0, steal_slot = 0;
+    uint32_t batch_tile = 0xffffffffu;
+    long long batch_t0 = 0;
     uint32_t item = 0, pix = 0;
     int pi = 0, pj = 0;
     f3 w = mk3(1, 1, 1);
@@ -198,11 +202,20 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
         uint32_t need = __ballot_sync(FULL, !active);
         uint32_t my = 0;
         bool have = false;
+        if (MODE == MODE_PRIMARY && a.f.tile_cost && need == FULL && batch_tile != 0xffffffffu) {
+            // the warp has just finished a whole 32-pixel batch: charge its duration to the tile
+            if (lane == 0) atomicAdd(a.f.tile_cost + batch_tile, (uint32_t)((clock64() - batch_t0) >> 6));
+            batch_tile = 0xffffffffu;
+        }
         if (!exhausted && (__popc(need) >= a.refill_min || need == FULL)) {
             int cnt = __popc(need), leader = __ffs(need) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(cursor, (uint32_t)cnt);
             base = __shfl_sync(FULL, base, leader);
+            if (MODE == MODE_PRIMARY && a.f.tile_cost && need == FULL && base < n) {
+                batch_tile = base / (uint32_t)a.f.tile_pix;
+                batch_t0 = clock64();
+            }
             if (base + (uint32_t)cnt >= n) exhausted = true;
             my = base + __popc(need & lt);
             have = !active && my < n;
@@ -518,6 +531,36 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
     if (__any_sync(0xffffffffu, qfull) && lane == 0) atomicOr(a.sticky, 1u);
 }
 
+// Heavy tiles first: reorders this rank's tile list by the cost measured in the frame that just ended
+// (descending), so that the LAST batches the persistent warps pick up are the cheap ones and the
+// kernel does not end on a long tail of expensive batches.  One CTA, bitonic sort of <= 4096 keys
+// (cost << 32 | tile id) in shared memory.  Only the order of work changes, never a pixel.
+#define RT_SORT_TILES_MAX 4096
+__global__ void __launch_bounds__(1024) k_sort_tiles(uint32_t* __restrict__ tile_ids, uint32_t* __restrict__ cost, uint32_t n) {
+    __shared__ unsigned long long key[RT_SORT_TILES_MAX];
+    uint32_t m = 1;
+    while (m < n) m <<= 1;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+        key[i] = i < n ? ((unsigned long long)cost[i] << 32) | tile_ids[i] : 0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                uint32_t l = i ^ j;
+                if (l > i) {
+                    unsigned long long a = key[i], b = key[l];
+                    bool desc = (i & k) == 0;          // descending overall
+                    if (desc ? a < b : a > b) { key[i] = b; key[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        tile_ids[i] = (uint32_t)(key[i] & 0xffffffffu);
+        cost[i] = 0;
+    }
+}
+
 // Color::clamp + Camera::drawPixel (color.cpp:19-28, camera.cpp:46-52): truncating 8-bit conversion.
 __device__ __forceinline__ uint32_t to_u8(long long q) {
     double c = (double)q * (1.0 / 4294967296.0);
@@ -662,6 +705,7 @@ void setup_layout(rt_ctx* c, const rt_camera* cam, const rt_render_params* p) {
         RT_CUDA(cudaMemcpyAsync(c->d_pool_ids.p, pool.data(), pool.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     RT_CUDA(cudaStreamSynchronize(c->stream));
     c->layout = L;
+    c->tile_cost_valid = false;
 }
 
 FrameDev frame_dev(rt_ctx* c, const rt_render_params* p) {
@@ -675,6 +719,16 @@ FrameDev frame_dev(rt_ctx* c, const rt_render_params* p) {
     f.pool_ids = c->d_pool_ids.p;
     f.n_pool_blocks = L.n_pool_tiles * ((uint32_t)f.tile_pix / 32u);
     f.stolen_map = c->d_stolen_map.p;
+    f.tile_cost = nullptr;
+    if (c->tile_feedback && L.n_tiles_owned > 1 && L.n_tiles_owned <= RT_SORT_TILES_MAX && c->refill_primary == 32 &&
+        (!c->fuse_shadow || c->refill_primary_fused == 32) && !(p->flags & RT_FLAG_PACKED_TILES)) {
+        c->d_tile_cost.reserve(L.n_tiles_owned);
+        if (!c->tile_cost_valid) {
+            RT_CUDA(cudaMemsetAsync(c->d_tile_cost.p, 0, L.n_tiles_owned * sizeof(uint32_t), c->stream));
+            c->tile_cost_valid = true;
+        }
+        f.tile_cost = c->d_tile_cost.p;
+    }
     f.steal_cursor = nullptr;
     if (L.pool_div && L.n_pool_tiles) {
         uint32_t slot = p->frame_index % 64u;
@@ -905,6 +959,11 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         uint32_t quads = f.n_tiles_owned * (uint32_t)(f.tile_pix / 4) + (f.steal_cursor ? f.n_pool_blocks * 8u : 0u);
         k_resolve<<<(quads + 255) / 256, 256, 0, st>>>(f, c->d_accum.p, (uint8_t*)rgb_dev,
                                                        (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0, c->d_frame.p);
+        RT_CUDA(cudaGetLastError());
+        launches++;
+    }
+    if (f.tile_cost) {   // after the last kernel that indexes pixels through tile_ids
+        k_sort_tiles<<<1, 1024, 0, st>>>(c->d_tile_ids.p, c->d_tile_cost.p, f.n_tiles_owned);
         RT_CUDA(cudaGetLastError());
         launches++;
     }
