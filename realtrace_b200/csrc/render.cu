@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
         bool have = false;
         if (MODE == MODE_PRIMARY && a.f.tile_cost && need == FULL && batch_tile != 0xffffffffu) {
             // the warp has just finished a whole 32-pixel batch: charge its duration to the tile
-            if (lane == 0) atomicAdd(a.f.tile_cost + batch_tile, (uint32_t)((clock64() - batch_t0) >> 6));
+            if (lane == 0) atomicMax(a.f.tile_cost + batch_tile, (uint32_t)((clock64() - batch_t0) >> 6));
             batch_tile = 0xffffffffu;
         }
         if (!exhausted && (__popc(need) >= a.refill_min || need == FULL)) {
@@ -532,16 +532,25 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
 }
 
 // Heavy tiles first: reorders this rank's tile list by the cost measured in the frame that just ended
-// (descending), so that the LAST batches the persistent warps pick up are the cheap ones and the
-// kernel does not end on a long tail of expensive batches.  One CTA, bitonic sort of <= 4096 keys
+// (slowest 32-pixel batch of the tile, descending), so that the LAST batches the persistent warps pick
+// up are cheap ones and the kernel does not end on a long tail of expensive batches.  One CTA, bitonic sort of <= 4096 keys
 // (cost << 32 | tile id) in shared memory.  Only the order of work changes, never a pixel.
 #define RT_SORT_TILES_MAX 4096
 __global__ void __launch_bounds__(1024) k_sort_tiles(uint32_t* __restrict__ tile_ids, uint32_t* __restrict__ cost, uint32_t n) {
     __shared__ unsigned long long key[RT_SORT_TILES_MAX];
     uint32_t m = 1;
     while (m < n) m <<= 1;
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
-        key[i] = i < n ? ((unsigned long long)cost[i] << 32) | tile_ids[i] : 0ull;
+    // key: half-octave bucket of the tile's slowest batch, then the tile id DEscending in the low word
+    // (stored inverted), so that tiles of similar cost keep their spatial (cache-friendly) order
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        unsigned long long k = 0ull;
+        if (i < n) {
+            uint32_t c = cost[i], b = 0;
+            if (c) { int e = 31 - __clz((int)c); b = 2u * (uint32_t)e + ((e > 0 && (c >> (e - 1)) & 1u) ? 1u : 0u) + 1u; }
+            k = ((unsigned long long)b << 32) | (0xffffffffu - tile_ids[i]);
+        }
+        key[i] = k;
+    }
     __syncthreads();
     for (uint32_t k = 2; k <= m; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
@@ -556,7 +565,7 @@ __global__ void __launch_bounds__(1024) k_sort_tiles(uint32_t* __restrict__ tile
             __syncthreads();
         }
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        tile_ids[i] = (uint32_t)(key[i] & 0xffffffffu);
+        tile_ids[i] = 0xffffffffu - (uint32_t)(key[i] & 0xffffffffu);
         cost[i] = 0;
     }
 }
@@ -706,6 +715,7 @@ void setup_layout(rt_ctx* c, const rt_camera* cam, const rt_render_params* p) {
     RT_CUDA(cudaStreamSynchronize(c->stream));
     c->layout = L;
     c->tile_cost_valid = false;
+    c->frames_in_layout = 0;
 }
 
 FrameDev frame_dev(rt_ctx* c, const rt_render_params* p) {
@@ -962,11 +972,15 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         RT_CUDA(cudaGetLastError());
         launches++;
     }
-    if (f.tile_cost) {   // after the last kernel that indexes pixels through tile_ids
+    // re-sort after the first two frames of a layout and then every 8th frame (the one-CTA sort costs
+    // ~50 us; costs keep accumulating as maxima in between); it runs after the last kernel that indexes
+    // pixels through tile_ids
+    if (f.tile_cost && (c->frames_in_layout < 2 || c->frames_in_layout % 8 == 0)) {
         k_sort_tiles<<<1, 1024, 0, st>>>(c->d_tile_ids.p, c->d_tile_cost.p, f.n_tiles_owned);
         RT_CUDA(cudaGetLastError());
         launches++;
     }
+    c->frames_in_layout++;
     RT_CUDA(cudaEventRecord(c->ev[7], st));
 
     // Without a stats request the frame is left in flight: nothing below synchronises, errors stay in

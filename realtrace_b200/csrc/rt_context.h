@@ -132,6 +132,7 @@ struct rt_ctx {
     TileLayout layout;
     DevBuf<uint32_t> d_tile_ids, d_pool_ids, d_stolen_map, d_tile_cost;
     bool tile_cost_valid = false;
+    uint32_t frames_in_layout = 0;
     int tile_feedback = 1;                 // heavy-tiles-first reordering from last frame's cost (RT_TILE_FEEDBACK)
     DevBuf<uint32_t> d_local_cursor;       // stand-in steal cursor when the caller passes none
     bool local_cursor_valid = false;
