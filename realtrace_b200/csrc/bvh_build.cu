@@ -98,8 +98,11 @@ __global__ void __launch_bounds__(TPB) k_morton(const float* __restrict__ v, uin
         atomicAdd(n_large, 1u);
     } else {
         f3 ext = chi - clo;
-        f3 inv = mk3(ext.x > 0.0f ? 1.0f / ext.x : 0.0f, ext.y > 0.0f ? 1.0f / ext.y : 0.0f,
-                     ext.z > 0.0f ? 1.0f / ext.z : 0.0f);
+        // one scale for all axes (cubic Morton cells): a flat scene must not spend its top splits on
+        // slicing the thin axis into pancakes
+        float emax = fmaxf(ext.x, fmaxf(ext.y, ext.z));
+        float iu = emax > 0.0f ? 1.0f / emax : 0.0f;
+        f3 inv = mk3(iu, iu, iu);
         f3 ctr = (bx.lo + bx.hi) * 0.5f;
         key = morton63(ctr, clo, inv);
     }

@@ -84,7 +84,9 @@ void build(const oracle_scene* in, int leaf_size, EmulScene& S) {
         S.keys.assign(n, 0); S.order.resize(n); S.n_large = 0;
         float scene_ext = fmaxf(sb.hi.x - sb.lo.x, fmaxf(sb.hi.y - sb.lo.y, sb.hi.z - sb.lo.z));
         f3 ext = cb.hi - cb.lo;
-        f3 inv = mk3(ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f, ext.z > 0 ? 1.0f / ext.z : 0.0f);
+        float emax = fmaxf(ext.x, fmaxf(ext.y, ext.z));
+        float iu = emax > 0 ? 1.0f / emax : 0.0f;
+        f3 inv = mk3(iu, iu, iu);   // cubic cells: one scale for all axes
         for (uint32_t i = 0; i < n; i++) {
             Aabb b = tri_aabb(vtx(in->tri_v, i, 0), vtx(in->tri_v, i, 1), vtx(in->tri_v, i, 2));
             float te = fmaxf(b.hi.x - b.lo.x, fmaxf(b.hi.y - b.lo.y, b.hi.z - b.lo.z));
