@@ -80,6 +80,15 @@ __device__ __forceinline__ uint32_t pixel_in_tile_to_local(const FrameDev& f, ui
     return tl * (uint32_t)f.tile_pix + (uint32_t)(b * 32 + l);
 }
 
+// Output byte offset of an owned pixel: frame layout (camera.cpp:48) or this rank's packed tiles.
+__device__ __forceinline__ size_t pixel_byte_offset(const FrameDev& f, uint32_t lp, int i, int j, int packed) {
+    if (!packed) return ((size_t)i + (size_t)j * f.W) * 3;
+    uint32_t tl = lp / (uint32_t)f.tile_pix, p = lp % (uint32_t)f.tile_pix;
+    int bpr = f.tile_w >> 3, b = (int)(p >> 5), l = (int)(p & 31);
+    int x = (b % bpr) * 8 + (l & 7), y = (b / bpr) * 4 + (l >> 3);
+    return ((size_t)tl * f.tile_pix + (size_t)y * f.tile_w + x) * 3;
+}
+
 // Camera::get_ray_direction (camera.cpp:33-44) + the Ray constructor's normalisation (ray.h:25-29),
 // evaluated in FP64 like the reference and rounded once to FP32.
 __device__ __forceinline__ void primary_ray(const CamDev& c, int i, int j, f3& o, f3& d) {
@@ -95,19 +104,39 @@ __device__ __forceinline__ void primary_ray(const CamDev& c, int i, int j, f3& o
     o = mk3((float)c.pos[0], (float)c.pos[1], (float)c.pos[2]);
 }
 
+// Color::clamp + Camera::drawPixel (color.cpp:19-28, camera.cpp:46-52): truncating 8-bit conversion of
+// a 32.32 fixed-point channel.
+__device__ __forceinline__ uint32_t to_u8(long long q) {
+    double c = (double)q * (1.0 / 4294967296.0);
+    if (c > 1.0) c = 1.0;
+    if (c < 0.0) c = 0.0;
+    return (uint32_t)(255.0 * c);
+}
+
+__device__ __forceinline__ long long to_fixed(float x) {
+    if (!(x == x)) x = 0.0f;                           // NaN -> 0
+    x = fminf(fmaxf(x, -1048576.0f), 1048576.0f);
+    return __float2ll_rn(x * 4294967296.0f);
+}
+
+// Scenes without bounces get exactly one contribution per pixel (primary miss or primary hit): it is
+// converted and stored as RGB8 on the spot — same rounding chain as accumulate + k_resolve — and the
+// accumulator buffer and the resolve kernel are skipped altogether.
+__device__ __forceinline__ void write_pixel_direct(uint8_t* out, size_t byte0, f3 c) {
+    out[byte0 + 0] = (uint8_t)to_u8(to_fixed(c.x));
+    out[byte0 + 1] = (uint8_t)to_u8(to_fixed(c.y));
+    out[byte0 + 2] = (uint8_t)to_u8(to_fixed(c.z));
+}
+
 // FIRST: the wave-0 contribution of a pixel (exactly one per in-frame pixel: the primary miss in
 // k_traverse or the primary hit in k_shade) is a plain store, which also initialises the
 // accumulator — no memset of the frame; every later contribution is an integer atomic add.
 template <bool FIRST>
 __device__ __forceinline__ void accumulate(long long* accum, uint32_t pix, f3 c) {
-    const float scale = 4294967296.0f, lim = 1048576.0f;
     float v[3] = {c.x, c.y, c.z};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float x = v[k];
-        if (!(x == x)) x = 0.0f;                       // NaN -> 0
-        x = fminf(fmaxf(x, -lim), lim);
-        long long q = __float2ll_rn(x * scale);
+        long long q = to_fixed(v[k]);
         if (FIRST) accum[3 * (size_t)pix + k] = q;
         else if (q) atomicAdd((unsigned long long*)(accum + 3 * (size_t)pix + k), (unsigned long long)q);
     }
@@ -141,6 +170,8 @@ struct TravArgs {
     int refill_min;           // idle lanes a warp waits for before it fetches new rays
     int loop_style;           // 0: while-while; k > 0: if-if in bursts of k steps
     unsigned long long* warp_times;   // debug (RT_FLAG_WARP_TIMES): per warp {start, end} in ns, 2 per warp
+    uint8_t* direct_rgb;      // PRIMARY, scene without bounces: RGB8 output written in place of the accumulator
+    int direct_packed;
 };
 
 // FUSE (nearest-hit modes only): a lane whose ray hit something does not go idle — it turns into
@@ -375,7 +406,10 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
                     if (a.aux_t) a.aux_t[at] = found ? hit.t : RT_FLT_MAX;
                 }
                 if (!found) {
-                    accumulate<MODE == MODE_PRIMARY>(a.accum, pix, w * bg);      // world.cpp:110
+                    if (MODE == MODE_PRIMARY && a.direct_rgb)
+                        write_pixel_direct(a.direct_rgb, pixel_byte_offset(a.f, pix, pi, pj, a.direct_packed), w * bg);
+                    else
+                        accumulate<MODE == MODE_PRIMARY>(a.accum, pix, w * bg);      // world.cpp:110
                 } else {
                     nh = hit;
                     occl_mask = 0;
@@ -459,6 +493,8 @@ struct ShadeArgs {
     uint32_t cap;
     int max_depth;
     int occl_bits;            // 1: occl[hit] is a bit mask over lights (fused traversal); 0: occl[light][hit] bytes
+    uint8_t* direct_rgb;      // see TravArgs
+    int direct_packed;
 };
 
 // Shading proper: no traversal in here, the shadow answers come from k_traverse<SHADOW>.
@@ -484,8 +520,8 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
             h.t = hr.x; h.prim = __float_as_int(hr.y); h.beta = hr.z; h.gamma = hr.w;
             f3 o, d;
             int level = 0;
+            int pi = 0, pj = 0;
             if (PRIMARY) {
-                int pi, pj;
                 local_to_pixel(a.f, idx, pi, pj);
                 primary_ray(a.cam, pi, pj, o, d);
                 pix = idx;
@@ -502,7 +538,9 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
                 return o2;
             };
             shade_hit(a.s, o, d, level, h, a.max_depth, any_hit, out);
-            accumulate<PRIMARY>(a.accum, pix, w * (out.local + out.bg_weight * bg));
+            f3 contrib = w * (out.local + out.bg_weight * bg);
+            if (PRIMARY && a.direct_rgb) write_pixel_direct(a.direct_rgb, pixel_byte_offset(a.f, pix, pi, pj, a.direct_packed), contrib);
+            else accumulate<PRIMARY>(a.accum, pix, contrib);
         }
         // append children: exclusive prefix over the warp, one atomic
         uint32_t k = valid ? (uint32_t)out.n_children : 0u;
@@ -568,14 +606,6 @@ __global__ void __launch_bounds__(1024) k_sort_tiles(uint32_t* __restrict__ tile
         tile_ids[i] = 0xffffffffu - (uint32_t)(key[i] & 0xffffffffu);
         cost[i] = 0;
     }
-}
-
-// Color::clamp + Camera::drawPixel (color.cpp:19-28, camera.cpp:46-52): truncating 8-bit conversion.
-__device__ __forceinline__ uint32_t to_u8(long long q) {
-    double c = (double)q * (1.0 / 4294967296.0);
-    if (c > 1.0) c = 1.0;
-    if (c < 0.0) c = 0.0;
-    return (uint32_t)(255.0 * c);
 }
 
 // One thread per 4 horizontally adjacent pixels of an owned tile.
@@ -949,6 +979,13 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         c->d_warp_times.reserve(2 * (size_t)(c->trace_blocks > c->fused_blocks ? c->trace_blocks : c->fused_blocks) * (TRAV_TPB / 32));
         ta.warp_times = c->d_warp_times.p;
     }
+    // no bounces => one contribution per pixel => RGB8 straight from the wave-0 kernels (stolen blocks keep
+    // the accumulator path: their packed offset is not defined)
+    const bool direct = !bounce && rgb_dev != nullptr && f.steal_cursor == nullptr;
+    if (direct) {
+        ta.direct_rgb = sa.direct_rgb = (uint8_t*)rgb_dev;
+        ta.direct_packed = sa.direct_packed = (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0;
+    }
     uint32_t launches = 0;
     const bool has_work = f.n_local_pix > 0 || f.steal_cursor != nullptr;
     if (has_work) launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, c->ev[1], c->ev[2]);
@@ -965,7 +1002,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     }
     RT_CUDA(cudaEventRecord(c->ev[6], st));
 
-    if (has_work && rgb_dev) {
+    if (has_work && rgb_dev && !direct) {
         uint32_t quads = f.n_tiles_owned * (uint32_t)(f.tile_pix / 4) + (f.steal_cursor ? f.n_pool_blocks * 8u : 0u);
         k_resolve<<<(quads + 255) / 256, 256, 0, st>>>(f, c->d_accum.p, (uint8_t*)rgb_dev,
                                                        (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0, c->d_frame.p);
