@@ -272,7 +272,8 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
             steal = (args.steal_div, frame_no[0], cursor_ptr) if cursor_ptr else None
             frame_no[0] += 1
             st = ctx.render_device(cam, depth, frame_ptr, rank=rank, world=world, want_stats=want_stats, steal=steal)
-            torch.distributed.all_reduce(tick)          # completion barrier: all tiles are in rank 0's frame
+            if not args.diag_no_barrier:
+                torch.distributed.all_reduce(tick)      # completion barrier: all tiles are in rank 0's frame
             return st
         st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES,
                                want_stats=want_stats)
@@ -291,11 +292,13 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     barrier()
     sampler.t_begin = time.perf_counter()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t_host0 = time.perf_counter()
     for k in range(steps):
         flush.fill_(k & 0xff)
         evs[k][0].record(stream)
         step_device(False)
         evs[k][1].record(stream)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps
     barrier()
     ctx.synchronize()                                   # raises if any timed frame flagged an error
     sampler.t_end = time.perf_counter()
@@ -347,7 +350,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
 
     sampler.stop()
     out = {"value": value, "ms_per_step": ms / steps, "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
-           "launches": launches, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "cam": cam, "depth": depth,
+           "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "cam": cam, "depth": depth,
            "scene": scene, "build": bstats, "commit_s": commit_s, "last": stats[-1], "rays_per_frame": rays_total / steps}
 
     # ---- roofline of the dominant kernel + work counts (single GPU, rank 0)
@@ -414,6 +417,7 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": 64 + 24, "d2h_bytes_per_step": cam.width * cam.height * 3,
                     "what": "rt_render: camera + params in, RGB8 frame into pinned host memory (scene resident)"},
             "gpu_launches": main["launches"], "clocks": main["clocks"],
+            "host_enqueue_ms_per_step": main["host_enqueue_ms_per_step"],
             "build": {"commit_s": main["commit_s"], **main["build"]}}
 
     if world == 1:
@@ -485,6 +489,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "gather"], help="N > 1 frame assembly")
+    ap.add_argument("--diag-no-barrier", action="store_true",
+                    help="diagnostic only: skip the per-frame completion barrier at N > 1 (frames are then NOT guaranteed complete)")
     ap.add_argument("--steal-div", type=int, default=0,
                     help="N > 1 with p2p assembly: every k-th tile group forms the shared pool ranks steal from (0 = off)")
     args = ap.parse_args()
