@@ -214,7 +214,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     # tiles + NCCL gather + scatter kernel on rank 0.
     assemble = "single"
     packed = gathered = None
-    cursor_ptr = None
+    cursor_ptr = sync_ptr = None
     frame_no = [0]
     if world > 1:
         assemble = args.assemble
@@ -228,6 +228,14 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
                 torch.distributed.broadcast(hbuf, 0)
                 if rank != 0:
                     frame_ptr = ctx.shared_buffer_open(hbuf.cpu().numpy().tobytes())
+                # handshake buffer (arrival counters + consumed counter) on rank 0
+                if rank == 0:
+                    sync_ptr, handle = ctx.shared_buffer_create(1024)
+                    hbuf.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+                torch.distributed.broadcast(hbuf, 0)
+                if rank != 0:
+                    sync_ptr = ctx.shared_buffer_open(hbuf.cpu().numpy().tobytes())
+                packed = torch.zeros(max_owned * tile_bytes, dtype=torch.uint8, device=dev)
                 if args.steal_div > 0:                  # the shared tile-stealing cursor (64 x uint32) lives on rank 0
                     if rank == 0:
                         cursor_ptr, handle = ctx.shared_buffer_create(256)
@@ -269,11 +277,19 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         if world == 1:
             return ctx.render_device(cam, depth, frame_ptr, want_stats=want_stats)
         if assemble == "p2p":
-            steal = (args.steal_div, frame_no[0], cursor_ptr) if cursor_ptr else None
+            k = frame_no[0]
             frame_no[0] += 1
-            st = ctx.render_device(cam, depth, frame_ptr, rank=rank, world=world, want_stats=want_stats, steal=steal)
+            if cursor_ptr:      # stealing: any rank may render any pool tile -> resolve straight into the shared frame
+                ctx.peer_sync(sync_ptr, rank, world, k, 0)
+                st = ctx.render_device(cam, depth, frame_ptr, rank=rank, world=world, want_stats=want_stats,
+                                       steal=(args.steal_div, k, cursor_ptr))
+            else:               # own tiles into a local packed buffer, then one kernel pushes them over NVLink
+                st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world,
+                                       flags=api.FLAG_PACKED_TILES, want_stats=want_stats)
+                ctx.peer_sync(sync_ptr, rank, world, k, 0)
+                ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr)
             if not args.diag_no_barrier:
-                torch.distributed.all_reduce(tick)      # completion barrier: all tiles are in rank 0's frame
+                ctx.peer_sync(sync_ptr, rank, world, k, 1)   # completion handshake: after it, rank 0 holds the frame
             return st
         st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES,
                                want_stats=want_stats)
@@ -408,7 +424,8 @@ def run_gpu_arm(args):
                        "max_depth": depth, "triangles": int(len(scene.tri_v)), "lights": int(len(scene.lights)),
                        "rays_per_frame": main["rays_per_frame"],
                        "parallelism": (f"{world} GPUs, interleaved 64x32 tiles, scene replicated, frame assembly: "
-                                       + {"p2p": "resolve kernels store into rank 0's frame over NVLink (CUDA IPC) + all-reduce barrier"
+                                       + {"p2p": "every rank pushes its tiles into rank 0's frame over NVLink (CUDA IPC peer stores) + "
+                                                 "flag handshake in peer memory (no collective)"
                                                  + (f", dynamic tile stealing (1/{args.steal_div} of the tile groups pooled)" if args.steal_div > 0 else ""),
                                           "gather": "packed tiles + NCCL gather + scatter kernel"}[main["assemble"]])
                        if world > 1 else "1 GPU",

@@ -186,6 +186,12 @@ int rt_synchronize(rt_ctx* ctx);
 int rt_shared_buffer_create(rt_ctx* ctx, uint64_t bytes, void** dev_ptr, unsigned char handle[64]);
 int rt_shared_buffer_open(rt_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
 int rt_download(rt_ctx* ctx, const void* dev_ptr, void* host, uint64_t bytes);
+/* Frame-completion handshake through a shared buffer (>= 1 KiB from rt_shared_buffer_create on rank 0,
+ * opened by the others) instead of a collective: enqueue phase 0 before and phase 1 after the kernels
+ * that write frame `frame_index` into rank 0's memory.  After phase 1 has run on rank 0's stream the
+ * frame is complete there; ranks > 0 never run more than one frame ahead of rank 0.  frame_index must
+ * count 0, 1, 2, ... identically on all ranks.                                                    */
+int rt_peer_sync(rt_ctx* ctx, void* sync_buf, int32_t rank, int32_t world_size, uint32_t frame_index, int32_t phase);
 /* tile helpers for the gather-based assembly (the gather itself is NCCL, outside)               */
 /* number of tiles in the frame / owned by `rank`, and bytes of one packed tile                  */
 int rt_tile_layout(int32_t width, int32_t height, int32_t tile_w, int32_t tile_h, int32_t rank, int32_t world_size,

@@ -347,6 +347,13 @@ int rt_shared_buffer_open(rt_ctx* ctx, const unsigned char handle[64], void** de
     });
 }
 
+int rt_peer_sync(rt_ctx* ctx, void* sync_buf, int32_t rank, int32_t world_size, uint32_t frame_index, int32_t phase) {
+    return guarded(ctx, [&] {
+        need(sync_buf && world_size >= 1 && rank >= 0 && rank < world_size && (phase == 0 || phase == 1), "rt_peer_sync: bad arguments");
+        rt_peer_sync_enqueue(ctx, sync_buf, rank, world_size, frame_index, phase);
+    });
+}
+
 int rt_download(rt_ctx* ctx, const void* dev_ptr, void* host, uint64_t bytes) {
     return guarded(ctx, [&] {
         need(dev_ptr && host, "rt_download: NULL buffer");

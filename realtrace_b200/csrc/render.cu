@@ -691,6 +691,36 @@ __global__ void __launch_bounds__(256) k_assemble(const uint8_t* __restrict__ pa
     }
 }
 
+// ---- frame-completion handshake between ranks through peer memory (NVLink), no collective library:
+// sync[0..63] arrival counters (slot = frame % 64), sync[64] = number of frames rank 0 has consumed.
+//   phase 0 (before a rank writes frame k into rank 0's buffer): ranks > 0 wait until consumed >= k
+//   phase 1 (after the write): ranks > 0 add 1 to slot k; rank 0 waits for world-1 arrivals, clears the
+//   slot that comes into use 32 frames later and publishes consumed = k + 1
+// The spinning kernels are single threads on DIFFERENT GPUs and give up after ~2 s (sticky bit 4).
+__global__ void k_peer_wait_consumed(volatile uint32_t* sync, uint32_t frame, uint32_t* sticky) {
+    long long t0 = clock64();
+    while (sync[64] < frame) {
+        if (clock64() - t0 > 4000000000ll) { atomicOr(sticky, 4u); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+__global__ void k_peer_arrive(uint32_t* sync, uint32_t frame) {
+    __threadfence_system();
+    atomicAdd_system(sync + (frame % 64u), 1u);
+}
+__global__ void k_peer_wait_all(volatile uint32_t* sync, uint32_t frame, uint32_t expect, uint32_t* sticky) {
+    long long t0 = clock64();
+    while (sync[frame % 64u] < expect) {
+        if (clock64() - t0 > 4000000000ll) { atomicOr(sticky, 4u); break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    sync[(frame + 32u) % 64u] = 0u;
+    sync[64] = frame + 1u;
+    __threadfence_system();
+}
+
 CamDev make_cam(const rt_camera* c) {
     CamDev d;
     for (int k = 0; k < 3; k++) { d.pos[k] = c->pos[k]; d.u[k] = c->u[k]; d.v[k] = c->v[k]; d.w[k] = c->w[k]; }
@@ -916,6 +946,7 @@ void rt_sync_and_check(rt_ctx* c) {
     uint32_t fl = *c->h_sticky;
     if (fl) {
         RT_CUDA(cudaMemsetAsync(c->d_sticky.p, 0, sizeof(uint32_t), st));
+        if (fl & 4u) throw RtError{RT_ERR_CUDA, "peer frame handshake timed out (a rank did not arrive within ~2 s)"};
         if (fl & 1u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow: a wave spawned more rays than the queue holds"};
         throw RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow (BVH deeper than RT_STACK_SIZE)"};
     }
@@ -1117,6 +1148,19 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
         RT_CUDA(cudaMemcpyAsync(rgb_out, c->d_rgbf_out.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     rt_sync_and_check(c);
+}
+
+void rt_peer_sync_enqueue(rt_ctx* c, void* sync_buf, int rank, int world, uint32_t frame_index, int phase) {
+    uint32_t* sync = (uint32_t*)sync_buf;
+    cudaStream_t st = c->stream;
+    if (world <= 1) return;
+    if (phase == 0) {
+        if (rank != 0) k_peer_wait_consumed<<<1, 1, 0, st>>>(sync, frame_index, c->d_sticky.p);
+    } else {
+        if (rank != 0) k_peer_arrive<<<1, 1, 0, st>>>(sync, frame_index);
+        else k_peer_wait_all<<<1, 1, 0, st>>>(sync, frame_index, (uint32_t)(world - 1), c->d_sticky.p);
+    }
+    RT_CUDA(cudaGetLastError());
 }
 
 void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int width, int height, int tile_w,
