@@ -288,8 +288,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
                                        flags=api.FLAG_PACKED_TILES, want_stats=want_stats)
                 ctx.peer_sync(sync_ptr, rank, world, k, 0)
                 ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr)
-            if not args.diag_no_barrier:
-                ctx.peer_sync(sync_ptr, rank, world, k, 1)   # completion handshake: after it, rank 0 holds the frame
+            ctx.peer_sync(sync_ptr, rank, world, k, 1)       # completion handshake: after it, rank 0 holds the frame
             return st
         st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES,
                                want_stats=want_stats)
@@ -311,6 +310,10 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     t_host0 = time.perf_counter()
     for k in range(steps):
         flush.fill_(k & 0xff)
+        if world > 1:
+            # untimed alignment: without it the L2 flush of a lagging rank (outside its own event pair) would be
+            # counted inside the event pair of every rank that waits for it
+            torch.distributed.all_reduce(tick)
         evs[k][0].record(stream)
         step_device(False)
         evs[k][1].record(stream)
@@ -506,8 +509,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "gather"], help="N > 1 frame assembly")
-    ap.add_argument("--diag-no-barrier", action="store_true",
-                    help="diagnostic only: skip the per-frame completion barrier at N > 1 (frames are then NOT guaranteed complete)")
     ap.add_argument("--steal-div", type=int, default=0,
                     help="N > 1 with p2p assembly: every k-th tile group forms the shared pool ranks steal from (0 = off)")
     args = ap.parse_args()
