@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
             r = get_reasons(h)
             self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(sm_max),
                               nv.nvmlDeviceGetPowerUsage(h) / 1000.0, [n for n, b in bits.items() if r & b]))
-            time.sleep(0.004)
+            time.sleep(0.01)
 
     def _smi_loop(self):
         self.source = "nvidia-smi"
@@ -264,6 +264,9 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
 
     orbit = workload == "orbit"
     orbit_k = [0]
+    cam_py = cam
+    cam = api.camera_struct(cam_py)      # flattened once: the per-frame host path is then a few ctypes calls
+    orbit_cams = [api.camera_struct(scenes.orbit_camera(k, width=W, height=H)) for k in range(120)] if orbit else None
 
     def step_device(want_stats=False):
         """One frame with everything resident: render (+ assembly at N > 1).  Without stats the call only
@@ -272,7 +275,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         nonlocal cam
         if orbit:
             ctx.commit(api.COMMIT_REFIT, want_stats=False)
-            cam = scenes.orbit_camera(orbit_k[0] % 120, width=W, height=H)
+            cam = orbit_cams[orbit_k[0] % 120]
             orbit_k[0] += 1
         if world == 1:
             return ctx.render_device(cam, depth, frame_ptr, want_stats=want_stats)
@@ -337,6 +340,26 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         rays_total = float(rays_local)
     value = rays_total / (ms * 1e-3) / 1e6
 
+    # ---- N > 1 diagnostics: where does a frame's time go on this rank? (p2p path without stealing)
+    if world > 1 and assemble == "p2p" and not cursor_ptr and os.environ.get("RT_BENCH_PHASES"):
+        acc = np.zeros(3)
+        for _ in range(10):
+            k = frame_no[0]
+            frame_no[0] += 1
+            torch.distributed.all_reduce(tick)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record(stream)
+            ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES, want_stats=False)
+            e[1].record(stream)
+            ctx.peer_sync(sync_ptr, rank, world, k, 0)
+            ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr)
+            e[2].record(stream)
+            ctx.peer_sync(sync_ptr, rank, world, k, 1)
+            e[3].record(stream)
+            torch.cuda.synchronize()
+            acc += np.array([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])])
+        print(f"[phases rank {rank}] render {acc[0]/10:.3f} ms, wait+push {acc[1]/10:.3f} ms, handshake {acc[2]/10:.3f} ms", file=sys.stderr, flush=True)
+
     # ---- e2e: host buffers through rt_render (N = 1) / render + gather + D2H of the frame (N > 1)
     host_frame = torch.empty(H * W * 3, dtype=torch.uint8, pin_memory=True)
     host_np = host_frame.numpy().reshape(H, W, 3)
@@ -369,7 +392,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
 
     sampler.stop()
     out = {"value": value, "ms_per_step": ms / steps, "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
-           "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "cam": cam, "depth": depth,
+           "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "cam": cam_py, "depth": depth,
            "scene": scene, "build": bstats, "commit_s": commit_s, "last": stats[-1], "rays_per_frame": rays_total / steps}
 
     # ---- roofline of the dominant kernel + work counts (single GPU, rank 0)

@@ -125,7 +125,10 @@ def _ptr(a):
 
 
 def camera_struct(cam) -> RtCamera:
-    """Flatten a scene.Camera exactly like Camera's constructor does (camera.cpp:4-25)."""
+    """Flatten a scene.Camera exactly like Camera's constructor does (camera.cpp:4-25).  An RtCamera is
+    passed through, so per-frame callers can build it once."""
+    if isinstance(cam, RtCamera):
+        return cam
     u, v, w, focal, aspect = cam.basis()
     c = RtCamera()
     c.pos = (C.c_float * 3)(*[float(x) for x in cam.pos])
