@@ -236,3 +236,35 @@ def test_dynamic_tile_stealing_is_bit_identical(world, pool_div):
         assert stolen > 0
         assert np.array_equal(out, full), frame_index
     ctx.close()
+
+
+def test_peer_handshake_and_tile_push_logical_ranks():
+    """bench.py's N > 1 frame loop with logical ranks on one GPU and one stream: each rank renders its tiles
+    into a local packed buffer (direct RGB8), pushes them into the shared frame and goes through the
+    peer-memory handshake.  Ranks 1..N-1 are enqueued before rank 0, so no kernel ever has to spin."""
+    import torch
+    scene, cam, depth, _ = build_case("synth_small_d1")      # no bounces: direct RGB8 path
+    cam.width, cam.height = 328, 200
+    world = 4
+    ctx = make_ctx(scene)
+    full = ctx.render(cam, depth)[0]
+    frame_ptr, _ = ctx.shared_buffer_create(cam.width * cam.height * 3)
+    sync_ptr, _ = ctx.shared_buffer_create(1024)
+    _, _, tb = api.tile_layout(cam.width, cam.height)
+    for k in range(3):
+        for r in list(range(1, world)) + [0]:
+            _, owned, _ = api.tile_layout(cam.width, cam.height, 0, 0, r, world)
+            packed = torch.zeros(max(owned * tb, 1), dtype=torch.uint8, device="cuda")
+            ctx.render_device(cam, depth, packed.data_ptr(), rank=r, world=world, flags=api.FLAG_PACKED_TILES,
+                              want_stats=False)
+            ctx.peer_sync(sync_ptr, r, world, k, 0)
+            ctx.assemble_tiles(packed.data_ptr(), r, world, cam.width, cam.height, frame_ptr)
+            ctx.peer_sync(sync_ptr, r, world, k, 1)
+        ctx.synchronize()                                     # raises on a handshake time-out
+        out = np.zeros((cam.height, cam.width, 3), np.uint8)
+        ctx.download(frame_ptr, out)
+        assert np.array_equal(out, full), k
+    sync = np.zeros(256, np.uint32)
+    ctx.download(sync_ptr, sync)
+    ctx.close()
+    assert sync[64] == 3                                      # three frames consumed
