@@ -268,3 +268,26 @@ def test_peer_handshake_and_tile_push_logical_ranks():
     ctx.download(sync_ptr, sync)
     ctx.close()
     assert sync[64] == 3                                      # three frames consumed
+
+
+@pytest.mark.parametrize("name,col_step", [("synth1m", 240), ("blub4k", 120)])
+def test_full_size_frames_against_oracle_column_sample(oracle, name, col_step):
+    """BASELINE configs 4 and 3 at their full 3840x2160 size: the GPU frame against the CPU oracle (grid as
+    shipped) on every col_step-th column, plus size-independent properties (idempotence, ray accounting)."""
+    scene, cam, depth, _ = scenes.workload(name)
+    ctx = make_ctx(scene)
+    rgb, prim, t, st = ctx.render(cam, depth, aux=True)
+    rgb2, _, _, st2 = ctx.render(cam, depth)
+    ctx.close()
+    assert np.array_equal(rgb, rgb2)
+    assert st["rays_primary"] == cam.width * cam.height
+    assert st["rays_shadow"] == st2["rays_shadow"] and st["rays_secondary"] == st2["rays_secondary"]
+    begin = col_step // 2 + 1
+    ref_rgb, ref_prim, ref_t, info = oracle.render(scene, cam, depth, ob.MODE_AS_SHIPPED, col_begin=begin, col_step=col_step)
+    cols = slice(begin, None, col_step)
+    m = parity.compare(rgb[:, cols], prim[:, cols], t[:, cols], ref_rgb[:, cols], ref_prim[:, cols], ref_t[:, cols])
+    assert m["hit_pixels"] > 1000, m
+    parity.assert_parity(m, name + " column sample vs oracle")
+    if name == "synth1m":       # no dielectrics: the GPU traces exactly the oracle's rays on those columns
+        hits = int((prim[:, cols] >= 0).sum())
+        assert info["rays_total"] == m["pixels"] + hits * len(scene.lights)
