@@ -569,6 +569,214 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
     if (__any_sync(0xffffffffu, qfull) && lane == 0) atomicOr(a.sticky, 1u);
 }
 
+
+// ---- k_paths: every bounce generation in ONE launch --------------------------------------------------
+// The wave loop pays two kernel launches (and, with dielectrics, a host round trip) per generation,
+// each bounded by the latency of its slowest 32-ray batch; mirror/dielectric scenes have few bounce
+// rays (10^4-10^6), so that latency is all there is.  Here a lane takes one ray of the first bounce
+// generation and follows its whole subtree by itself: nearest hit -> shadow rays (fused as in
+// k_traverse) -> shade_hit inline -> continue with the first child, park a second child (dielectrics,
+// world.cpp:97-99) on a small per-lane stack of pending rays.  No queue between lanes, no spinning,
+// no host involvement; idle lanes pull new rays from the cursor.  The arithmetic per ray is the wave
+// path's, and pixel sums are integer atomics, so the frame is bit-identical to the wave loop's.
+#define RT_PATH_STACK 24      // pending rays per lane (binary dielectric tree, depth-first)
+
+struct PathArgs {
+    SceneDev s;
+    RayQueue q;               // the first bounce generation (written by k_shade of wave 0)
+    const WaveCounters* wave; // wave->n_rays = its population
+    uint32_t* cursor;
+    long long* accum;
+    FrameCounters* fc;
+    uint32_t* sticky;
+    uint32_t cap;
+    int max_depth;
+    int refill_min;
+    int loop_style;
+    uint32_t brute;
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ PathArgs a) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t n = min(a.wave->n_rays, a.cap);
+    const f3 bg = mk3(a.s.background[0], a.s.background[1], a.s.background[2]);
+    const bool use_bvh = !a.brute && a.s.n_bvh_tris > 0;
+    const int burst = a.loop_style > 0 ? a.loop_style : 64;
+
+    RayPrep r;
+    HitRec hit, nh;
+    int stack[RT_STACK_SIZE];
+    float4 pend[3 * RT_PATH_STACK];           // parked rays: (o, pix) (d, level) (w, -)
+    int node = RT_DONE, sp = 0, psp = 0;
+    bool active = false, found = false, exhausted = false, overflow = false, pend_overflow = false;
+    int phase = -1;                           // < 0 nearest-hit query, li >= 0 shadow ray of light li
+    f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 1), w = mk3(1, 1, 1), P = mk3(0, 0, 0);
+    int level = 0;
+    uint32_t pix = 0, occl_mask = 0;
+    uint32_t n_secondary = 0, n_shadow = 0;
+    WorkCount wc, wcs;
+    wc.nodes = wc.tris = wcs.nodes = wcs.tris = 0;
+    hit.t = nh.t = RT_FLT_MAX; hit.prim = nh.prim = RT_MISS; hit.beta = hit.gamma = nh.beta = nh.gamma = 0.0f;
+
+    auto start_nearest = [&]() {              // (ro, rd) is the lane's current ray
+        bool finite = rd.x == rd.x && rd.y == rd.y && rd.z == rd.z;
+        r = prep_ray(ro, rd);
+        hit.t = RT_FLT_MAX; hit.prim = RT_MISS; hit.beta = hit.gamma = 0.0f;
+        found = false;
+        phase = -1;
+        sp = 0;
+        node = (use_bvh && finite) ? 0 : RT_DONE;
+        active = true;
+        n_secondary++;
+    };
+    auto start_shadow = [&](int li) {
+        f3 toL = mk3(__ldg(a.s.lights + 2 * li)) - P;
+        f3 sd = normalize(toL);
+        r = prep_ray(fma3(toL, 0.01f, P), sd);
+        hit.t = RT_FLT_MAX; hit.prim = RT_MISS;
+        found = false;
+        sp = 0;
+        node = (use_bvh && sd.x == sd.x && sd.y == sd.y && sd.z == sd.z) ? 0 : RT_DONE;
+        n_shadow++;
+    };
+    auto next_ray = [&]() {                   // current ray is finished: continue with a parked one or go idle
+        if (psp > 0) {
+            psp--;
+            float4 p0 = pend[3 * psp], p1 = pend[3 * psp + 1], p2 = pend[3 * psp + 2];
+            ro = mk3(p0); pix = __float_as_uint(p0.w);
+            rd = mk3(p1); level = __float_as_int(p1.w);
+            w = mk3(p2);
+            start_nearest();
+        } else {
+            active = false;
+        }
+    };
+
+    for (;;) {
+        uint32_t need = __ballot_sync(FULL, !active);
+        if (!exhausted && (__popc(need) >= a.refill_min || need == FULL)) {
+            int cnt = __popc(need), leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(a.cursor, (uint32_t)cnt);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + (uint32_t)cnt >= n) exhausted = true;
+            uint32_t my = base + __popc(need & lt);
+            if (!active && my < n) {
+                float4 q0 = a.q.o_pix[my], q1 = a.q.d_lvl[my], q2 = a.q.w[my];
+                ro = mk3(q0); pix = __float_as_uint(q0.w);
+                rd = mk3(q1); level = __float_as_int(q1.w);
+                w = mk3(q2);
+                psp = 0;
+                start_nearest();
+            }
+        }
+        if (!__any_sync(FULL, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        const bool any = phase >= 0;
+        WorkCount* wcp = COUNT ? (any ? &wcs : &wc) : nullptr;
+        if (active) {
+            for (int it = 0; it < burst && node != RT_DONE; it++) {
+                if (rt_is_internal(node)) {
+                    if (COUNT) wcp->nodes++;
+                    node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
+                } else {
+                    if (leaf_test(a.s, node, r, hit, any, wcp)) {
+                        found = true;
+                        if (any) { node = RT_DONE; break; }
+                    }
+                    node = sp ? stack[--sp] : RT_DONE;
+                }
+            }
+        }
+        if (active && node == RT_DONE) {
+            bool finite = r.d.x == r.d.x && r.d.y == r.d.y && r.d.z == r.d.z;
+            if (finite && !(any && found)) {
+                if (a.brute) found |= any ? brute_walk<true>(a.s, r, hit, wcp) : brute_walk<false>(a.s, r, hit, wcp);
+                for (int k = 0; k < a.s.n_analytic && !(any && found); k++) {
+                    const AnalyticPrim p = a.s.analytic[k];
+                    if (COUNT) wcp->tris++;
+                    if (analytic_test(p, r.o, r.d, hit.t, hit.beta, hit.gamma)) {
+                        hit.prim = rt_analytic_code(k);
+                        found = true;
+                    }
+                }
+            }
+            bool shade_now = false;
+            if (any) {
+                occl_mask |= (found ? 1u : 0u) << phase;
+                phase++;
+                if (phase < a.s.n_lights) start_shadow(phase);
+                else shade_now = true;
+            } else if (!found) {
+                accumulate<false>(a.accum, pix, w * bg);           // world.cpp:110
+                next_ray();
+            } else {
+                nh = hit;
+                occl_mask = 0;
+                shade_now = true;
+                if (a.s.n_lights > 0) {
+                    uint32_t mat = hit.prim >= 0 ? __float_as_uint(__ldg(a.s.tris + 3 * (size_t)hit.prim + 1).w)
+                                                 : a.s.analytic[rt_analytic_index(hit.prim)].material;
+                    float4 m1 = __ldg(a.s.materials + 3 * mat + 1);
+                    if (!(m1.z > 0.0f && m1.w > 0.0f)) {           // dielectrics discard the local colour
+                        P = fma3(rd, hit.t, ro);
+                        phase = 0;
+                        start_shadow(0);
+                        shade_now = false;
+                    }
+                }
+            }
+            if (shade_now) {
+                ShadeOut out;
+                uint32_t li = 0;
+                auto occluded = [&](f3, f3) -> bool { bool o2 = ((occl_mask >> li) & 1u) != 0; li++; return o2; };
+                shade_hit(a.s, ro, rd, level, nh, a.max_depth, occluded, out);
+                accumulate<false>(a.accum, pix, w * (out.local + out.bg_weight * bg));
+                if (out.n_children == 2) {                         // park the second child
+                    if (psp < RT_PATH_STACK) {
+                        const ShadeChild& c1 = out.child[1];
+                        f3 cw = w * c1.w;
+                        pend[3 * psp] = make_float4(c1.o.x, c1.o.y, c1.o.z, __uint_as_float(pix));
+                        pend[3 * psp + 1] = make_float4(c1.d.x, c1.d.y, c1.d.z, __int_as_float(c1.level));
+                        pend[3 * psp + 2] = make_float4(cw.x, cw.y, cw.z, 0.0f);
+                        psp++;
+                    } else {
+                        pend_overflow = true;
+                    }
+                }
+                if (out.n_children >= 1) {
+                    const ShadeChild& c0 = out.child[0];
+                    ro = c0.o; rd = c0.d; w = w * c0.w; level = c0.level;
+                    start_nearest();
+                } else {
+                    next_ray();
+                }
+            }
+        }
+    }
+    uint32_t s1 = warp_sum(n_secondary), s2 = warp_sum(n_shadow);
+    if (lane == 0) {
+        if (s1) atomicAdd(&a.fc->rays_secondary, (unsigned long long)s1);
+        if (s2) atomicAdd(&a.fc->rays_shadow, (unsigned long long)s2);
+    }
+    if (COUNT) {
+        uint32_t nn = warp_sum(wc.nodes), nt = warp_sum(wc.tris), sn = warp_sum(wcs.nodes), st = warp_sum(wcs.tris);
+        if (lane == 0) {
+            atomicAdd(&a.fc->node_visits[0], (unsigned long long)nn);
+            atomicAdd(&a.fc->tri_tests[0], (unsigned long long)nt);
+            atomicAdd(&a.fc->node_visits[1], (unsigned long long)sn);
+            atomicAdd(&a.fc->tri_tests[1], (unsigned long long)st);
+        }
+    }
+    uint32_t fl = (__any_sync(FULL, overflow) ? 2u : 0u) | (__any_sync(FULL, pend_overflow) ? 8u : 0u);
+    if (fl && lane == 0) atomicOr(a.sticky, fl);
+}
+
 // Heavy tiles first: reorders this rank's tile list by the cost measured in the frame that just ended
 // (slowest 32-pixel batch of the tile, descending), so that the LAST batches the persistent warps pick
 // up are cheap ones and the kernel does not end on a long tail of expensive batches.  One CTA, bitonic sort of <= 4096 keys
@@ -906,6 +1114,27 @@ struct WaveResult {
     uint64_t secondary = 0;
 };
 
+// All bounce generations in one launch: the rays sit in queue `cur`, their count in wave slot `slot`.
+void launch_paths(rt_ctx* c, int slot, int cur, int max_depth, uint32_t brute, bool count) {
+    PathArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.s = c->scene;
+    pa.q = queue_of(c, cur);
+    pa.wave = c->d_waves.p + slot;
+    pa.cursor = &c->d_waves.p[slot].fetch_trace;
+    pa.accum = c->d_accum.p;
+    pa.fc = c->d_frame.p;
+    pa.sticky = c->d_sticky.p;
+    pa.cap = (uint32_t)c->queue_cap;
+    pa.max_depth = max_depth;
+    pa.refill_min = c->refill_queue;
+    pa.loop_style = c->loop_queue;
+    pa.brute = brute;
+    if (count) k_paths<true><<<c->path_blocks, TRAV_TPB, 0, c->stream>>>(pa);
+    else k_paths<false><<<c->path_blocks, TRAV_TPB, 0, c->stream>>>(pa);
+    RT_CUDA(cudaGetLastError());
+}
+
 // Runs waves first_wave.. over rays already sitting in queue `cur`.  Mirror-only scenes need no
 // host round trip: a ray of wave w has level w, so exactly max_depth waves can be populated and
 // they are launched blind (empty ones exit at once).  With dielectrics (level*2, world.cpp:98) the
@@ -948,6 +1177,7 @@ void rt_sync_and_check(rt_ctx* c) {
         RT_CUDA(cudaMemsetAsync(c->d_sticky.p, 0, sizeof(uint32_t), st));
         if (fl & 4u) throw RtError{RT_ERR_CUDA, "peer frame handshake timed out (a rank did not arrive within ~2 s)"};
         if (fl & 1u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow: a wave spawned more rays than the queue holds"};
+        if (fl & 8u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "pending-ray stack overflow in k_paths (dielectric chain deeper than RT_PATH_STACK); set RT_PATH_KERNEL=0"};
         throw RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow (BVH deeper than RT_STACK_SIZE)"};
     }
 }
@@ -959,6 +1189,7 @@ void rt_render_init(rt_ctx* c) {
     c->fused_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false, true>, TRAV_TPB, c->sm_count),
                          persistent_blocks(k_traverse<MODE_QUEUE, false, true>, TRAV_TPB, c->sm_count));
     c->shadow_blocks = persistent_blocks(k_traverse<MODE_SHADOW, false, false>, TRAV_TPB, c->sm_count);
+    c->path_blocks = persistent_blocks(k_paths<false>, TRAV_TPB, c->sm_count);
     c->shade_blocks = lo(persistent_blocks(k_shade<true>, SHADE_TPB, c->sm_count),
                          persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
     if (c->blocks_per_sm > 0) {   // RT_BLOCKS_PER_SM: cap the persistent grids (tuning)
@@ -966,6 +1197,7 @@ void rt_render_init(rt_ctx* c) {
         c->trace_blocks = lo(c->trace_blocks, cap);
         c->fused_blocks = lo(c->fused_blocks, cap);
         c->shadow_blocks = lo(c->shadow_blocks, cap);
+        c->path_blocks = lo(c->path_blocks, cap);
     }
     c->d_waves.reserve(RT_WAVE_SLOTS);
     c->d_frame.reserve(1);
@@ -1024,12 +1256,19 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     RT_CUDA(cudaEventRecord(c->ev[3], st));
 
     WaveResult wr;
+    const bool use_paths = c->path_kernel && c->scene.n_lights <= 8;
     if (bounce && has_work) {
         ta.aux_prim = nullptr; ta.aux_t = nullptr;
         ta.warp_times = nullptr;
         // wave 0 wrote its children into queue 1
-        wr = run_bounce_waves(c, ta, sa, 1, 1, p->max_depth, count, true);
-        launches += wr.launches;
+        if (use_paths) {
+            launch_paths(c, 1, 1, p->max_depth, ta.brute, count);
+            launches++;
+            wr.waves = 1;
+        } else {
+            wr = run_bounce_waves(c, ta, sa, 1, 1, p->max_depth, count, true);
+            launches += wr.launches;
+        }
     }
     RT_CUDA(cudaEventRecord(c->ev[6], st));
 
@@ -1059,7 +1298,10 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     rt_sync_and_check(c);
     uint64_t secondary = wr.secondary;
     uint32_t max_queue = wr.max_queue;
-    if (bounce && !c->has_dielectric && p->max_depth <= 16) {   // blind mode: read populations now
+    if (bounce && use_paths) {
+        secondary = c->h_frame->rays_secondary;
+        max_queue = c->h_waves[1].n_rays;
+    } else if (bounce && !c->has_dielectric && p->max_depth <= 16) {   // blind mode: read populations now
         for (int w = 1; w <= p->max_depth && w < RT_WAVE_SLOTS; w++) {
             secondary += c->h_waves[w].n_rays;
             if (c->h_waves[w].n_rays > max_queue) max_queue = c->h_waves[w].n_rays;
@@ -1137,7 +1379,8 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
     launch_wave<false>(c, ta, sa, 0, 1, 0, count, shade, nullptr, nullptr);
     if (bounce) {
         ta.aux_prim = nullptr; ta.aux_t = nullptr;
-        run_bounce_waves(c, ta, sa, 1, 1, max_depth, count, false);
+        if (c->path_kernel && c->scene.n_lights <= 8) launch_paths(c, 1, 1, max_depth, ta.brute, count);
+        else run_bounce_waves(c, ta, sa, 1, 1, max_depth, count, false);
     }
     if (prim_out) RT_CUDA(cudaMemcpyAsync(prim_out, c->d_aux_prim.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (t_out) RT_CUDA(cudaMemcpyAsync(t_out, c->d_aux_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -70,7 +70,7 @@ struct WaveCounters {
 #define RT_WAVE_SLOTS 64
 
 struct FrameCounters {
-    unsigned long long rays_primary, rays_shadow;
+    unsigned long long rays_primary, rays_shadow, rays_secondary;
     unsigned int stolen_blocks, pad;
     unsigned long long node_visits[2], tri_tests[2];   // [0] nearest-hit rays, [1] any-hit (shadow) rays
 };
@@ -158,7 +158,8 @@ struct rt_ctx {
     std::vector<void*> ipc_opened, ipc_created;
     cudaEvent_t ev[10] = {};               // 0-3,6,7 frame; 4,5 build; 8,9 refit
     bool refit_pending = false;
-    int trace_blocks = 0, fused_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
+    int trace_blocks = 0, fused_blocks = 0, shadow_blocks = 0, shade_blocks = 0, path_blocks = 0;
+    int path_kernel = 1;                   // bounce generations in one k_paths launch (RT_PATH_KERNEL=0: wave loop)
     int fuse_shadow = 1;                   // shadow rays ride in the lane that found the hit (RT_FUSE_SHADOW)
     int refill_primary_fused = 32;
     int blocks_per_sm = 0;                 // 0 = as many persistent CTAs as fit
