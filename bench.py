@@ -403,7 +403,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         ms_k = {"k_traverse<primary> (nearest hit)": np.mean([s["ms_trace"] for s in stats]),
                 "k_traverse<shadow> (any hit)": np.mean([s["ms_shadow"] for s in stats]),
                 "k_shade<primary>": np.mean([s["ms_shade"] for s in stats]),
-                "bounce waves (k_traverse + k_shade)": np.mean([s["ms_secondary"] for s in stats]),
+                "k_paths (all bounce generations)": np.mean([s["ms_secondary"] for s in stats]),
                 "k_resolve": np.mean([s["ms_resolve"] for s in stats])}
         out["kernel_ms"] = {k: float(v) for k, v in ms_k.items()}
         nodes_all = cnt["node_visits"] + cnt["shadow_node_visits"]
