@@ -400,7 +400,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         cnt = ctx.render_device(cam, depth, frame_ptr, flags=api.FLAG_COUNT_WORK)
         n_rays = total_rays(cnt)
         n_near = cnt["rays_primary"] + cnt["rays_secondary"]
-        ms_k = {"k_traverse<primary> (nearest hit)": np.mean([s["ms_trace"] for s in stats]),
+        ms_k = {"k_traverse<primary> (nearest hit + fused shadow rays)": np.mean([s["ms_trace"] for s in stats]),
                 "k_traverse<shadow> (any hit)": np.mean([s["ms_shadow"] for s in stats]),
                 "k_shade<primary>": np.mean([s["ms_shade"] for s in stats]),
                 "k_paths (all bounce generations)": np.mean([s["ms_secondary"] for s in stats]),
@@ -469,7 +469,18 @@ def run_gpu_arm(args):
         dom = max(kms, key=kms.get)
         # algorithmic bytes / FMA lane-instructions per ray: SURVEY §8(d), applied to the rays the dominant
         # kernel traces (nearest-hit rays for k_traverse<primary>, any-hit rays for k_traverse<shadow>)
-        cls = work["shadow"] if "shadow" in dom else work["nearest"]
+        fused = kms.get("k_traverse<shadow> (any hit)", 0.0) < 0.01     # shadow rays ride in the primary kernel
+        if "k_traverse<primary>" in dom and fused:
+            cls = {"rays": work["nearest"]["rays"] + work["shadow"]["rays"] - main["last"]["rays_secondary"],
+                   "node_visits_per_ray": None, "tri_tests_per_ray": None}
+            # wave-0 rays only: primary + their shadow rays (bounce rays are traced by k_paths)
+            if main["last"]["rays_secondary"] == 0:
+                cls = {"rays": work["rays"], "node_visits_per_ray": work["node_visits_per_ray"],
+                       "tri_tests_per_ray": work["tri_tests_per_ray"]}
+            else:
+                cls = work["nearest"]          # approximation for bounce scenes: per-ray work of nearest-hit rays
+        else:
+            cls = work["shadow"] if "k_traverse<shadow>" in dom else work["nearest"]
         bytes_per_ray = 64.0 * cls["node_visits_per_ray"] + 48.0 * cls["tri_tests_per_ray"] + 84.0
         fma_per_ray = 12.0 * cls["node_visits_per_ray"] + 30.0 * cls["tri_tests_per_ray"] + 60.0
         dom_ms = kms[dom]
@@ -481,7 +492,7 @@ def run_gpu_arm(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            traffic = tj.get(args.workload, {}).get("k_traverse<shadow>" if "shadow" in dom else "k_traverse<primary>")
+            traffic = tj.get(args.workload, {}).get("k_traverse<shadow>" if "k_traverse<shadow>" in dom else "k_traverse<primary>")
         line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                             "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
                             "kernel": dom, "kernel_ms": kms, "rays_in_kernel": cls["rays"],
