@@ -291,3 +291,31 @@ def test_full_size_frames_against_oracle_column_sample(oracle, name, col_step):
     if name == "synth1m":       # no dielectrics: the GPU traces exactly the oracle's rays on those columns
         hits = int((prim[:, cols] >= 0).sum())
         assert info["rays_total"] == m["pixels"] + hits * len(scene.lights)
+
+
+def test_reference_default_depth_10_with_dielectrics(oracle):
+    """RECURSION_DEPTH 10 (world.h:11) on the dielectric/mirror scene: deep level*2 chains through k_paths."""
+    scene, cam, _, _ = build_case("blubmixed_d5")
+    ctx = make_ctx(scene)
+    rgb, prim, t, st = ctx.render(cam, 10, aux=True)
+    ctx.close()
+    tr = oracle.render(scene, cam, 10, ob.MODE_TRUE_NEAREST)
+    parity.assert_parity(parity.compare(rgb, prim, t, tr[0], tr[1], tr[2]), "blub depth 10")
+    assert st["rays_secondary"] > 0
+
+
+def test_nine_lights_take_the_unfused_path(oracle):
+    """More than 8 lights: occlusion no longer fits the per-hit bit mask, so the separate any-hit kernel and
+    the wave loop are used — same frame as the oracle."""
+    scene, cam, depth, _ = build_case("bobtex_d3")
+    rng = np.random.default_rng(5)
+    lights = np.concatenate([rng.uniform(-40, 40, (9, 3)) + np.array([0, 45, 0]), rng.uniform(0.05, 0.2, (9, 3))], axis=1)
+    scene.lights = lights.astype(np.float32)
+    scene.normalise()
+    ctx = make_ctx(scene)
+    rgb, prim, t, st = ctx.render(cam, depth, aux=True)
+    ctx.close()
+    tr = oracle.render(scene, cam, depth, ob.MODE_TRUE_NEAREST)
+    parity.assert_parity(parity.compare(rgb, prim, t, tr[0], tr[1], tr[2]), "nine lights")
+    hits = int((prim >= 0).sum())
+    assert st["rays_shadow"] >= 9 * hits
