@@ -1,6 +1,6 @@
 // lumina_headless.cpp — what Serial/lumina.cpp does, minus the window: same includes, same scene
 // set-up calls (lumina.cpp:302-370), same command line `[width] [height]` with even rounding
-// (:480-486), one frame through RenderEngine, saved as a binary PPM instead of DevIL's PNG (:424-439).
+// (:480-486), one frame through RenderEngine, saved as PNG (own zlib writer, SaveImage) or binary PPM instead of going through DevIL (:424-439).
 // It exists to show that host code written against the reference's headers builds and runs
 // unchanged on top of the GPU core.
 #include <cstdio>
@@ -48,12 +48,9 @@ int main(int argc, char* argv[]) {
         float ms;
         engine->frameStats(p, s, c, ms);
         fprintf(stderr, "%llu primary + %llu shadow + %llu secondary rays, %.3f ms on the GPU\n", p, s, c, ms);
-        FILE* f = fopen(out.c_str(), "wb");
-        if (!f) { fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
-        fprintf(f, "P6\n%d %d\n255\n", screen_width, screen_height);
-        for (int j = screen_height - 1; j >= 0; j--)      // bitmap row 0 is the bottom row (camera.cpp:46-52)
-            fwrite(camera->getBitmap() + (size_t)j * screen_width * 3, 1, (size_t)screen_width * 3, f);
-        fclose(f);
+        bool png = out.size() > 4 && out.substr(out.size() - 4) == ".png";
+        bool ok = png ? SaveImage(camera, out) : save_ppm(out, camera->getBitmap(), screen_width, screen_height);
+        if (!ok) { fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
         fprintf(stderr, "Image saved as: %s\n", out.c_str());
     } catch (const std::exception& e) {
         fprintf(stderr, "error: %s\n", e.what());

@@ -323,4 +323,32 @@ void load_image_from_obj(World* world, std::string file_name, std::string textur
                          std::string occlusion_map_file_name = "", int max_faces = -1);
 void init_material_from_obj(Material* m);                   // lumina.cpp:163-172
 
+// ---- lumina.cpp:424-439 SaveImage: the frame as an image file.  The reference goes through DevIL
+// (ilTexImage + ilSave(IL_PNG)); here a self-contained writer (zlib deflate, 8-bit RGB, no interlace).
+// Row 0 of Camera::getBitmap() is the BOTTOM row on screen (vshader.vs:8), so rows are written top-down.
+bool save_png(const std::string& file_name, const unsigned char* rgb_bottom_up, int width, int height);
+bool save_ppm(const std::string& file_name, const unsigned char* rgb_bottom_up, int width, int height);
+inline bool SaveImage(Camera* camera, const std::string& file_name) {
+    return save_png(file_name, camera->getBitmap(), camera->getWidth(), camera->getHeight());
+}
+
+// ---- Parellel/interactive_camera.cu:7-102: the orbit camera of the reference's CUDA app (BASELINE
+// config 5).  Same fields, clamps and eye-position formula (float arithmetic, :64-72); makeCamera()
+// returns a Serial-style Camera looking at centerPosition.
+class InteractiveCamera {
+public:
+    float centerPosition[3];
+    float yaw, pitch, radius, apertureRadius;
+    float resolution[2], fov[2];
+    InteractiveCamera();
+    void changeYaw(float m);
+    void changePitch(float m);
+    void changeRadius(float m);
+    void changeAltitude(float m);
+    void setResolution(float x, float y);
+    void setFOVX(float fovx);
+    void eyePosition(float out[3]) const;                   // buildRenderCamera, :64-70
+    Camera* makeCamera() const;                             // caller owns the result
+};
+
 #endif

@@ -352,6 +352,114 @@ void load_image_from_obj(World* world, std::string file_name, std::string textur
     world->uniform_grid = UniformGrid(all_triangles);                                       // lumina.cpp:289 (a no-op shim here)
 }
 
+// ---- image output (lumina.cpp:424-439) ---------------------------------------------------------------
+static void put_be32(std::vector<unsigned char>& v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); }
+static void png_chunk(std::vector<unsigned char>& out, const char* type, const std::vector<unsigned char>& data) {
+    put_be32(out, (uint32_t)data.size());
+    size_t start = out.size();
+    out.insert(out.end(), type, type + 4);
+    out.insert(out.end(), data.begin(), data.end());
+    put_be32(out, (uint32_t)crc32(0L, out.data() + start, (uInt)(out.size() - start)));
+}
+bool save_png(const std::string& file_name, const unsigned char* rgb, int width, int height) {
+    if (!rgb || width <= 0 || height <= 0) return false;
+    std::vector<unsigned char> raw;
+    raw.reserve((size_t)(width * 3 + 1) * height);
+    for (int j = height - 1; j >= 0; j--) {                 // bitmap row 0 is the bottom row
+        raw.push_back(0);                                   // filter type 0
+        raw.insert(raw.end(), rgb + (size_t)j * width * 3, rgb + (size_t)(j + 1) * width * 3);
+    }
+    uLongf clen = compressBound((uLong)raw.size());
+    std::vector<unsigned char> comp(clen);
+    if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return false;
+    comp.resize(clen);
+    std::vector<unsigned char> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::vector<unsigned char> ihdr;
+    put_be32(ihdr, (uint32_t)width); put_be32(ihdr, (uint32_t)height);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
+    png_chunk(out, "IHDR", ihdr);
+    png_chunk(out, "IDAT", comp);
+    png_chunk(out, "IEND", {});
+    FILE* f = fopen(file_name.c_str(), "wb");
+    if (!f) return false;
+    bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    fclose(f);
+    return ok;
+}
+bool save_ppm(const std::string& file_name, const unsigned char* rgb, int width, int height) {
+    FILE* f = fopen(file_name.c_str(), "wb");
+    if (!f) return false;
+    fprintf(f, "P6\n%d %d\n255\n", width, height);
+    for (int j = height - 1; j >= 0; j--) fwrite(rgb + (size_t)j * width * 3, 1, (size_t)width * 3, f);
+    fclose(f);
+    return true;
+}
+
+// ---- orbit camera (Parellel/interactive_camera.cu) -----------------------------------------------------
+InteractiveCamera::InteractiveCamera() {                                                    // :7-17
+    centerPosition[0] = centerPosition[1] = centerPosition[2] = 0;
+    yaw = 0; pitch = 0.3f; radius = 10; apertureRadius = 0.04f;
+    resolution[0] = resolution[1] = 512; fov[0] = fov[1] = 45;
+}
+static float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+void InteractiveCamera::changeYaw(float m) { yaw += m; yaw -= 2 * M_PI * floor(yaw / (2 * M_PI)); }              // :21-24,:83-85
+void InteractiveCamera::changePitch(float m) { pitch += m; float pad = 0.05f; pitch = clampf(pitch, -(M_PI / 2) + pad, (M_PI / 2) - pad); }   // :26-29,:87-90
+void InteractiveCamera::changeRadius(float m) { radius += radius * m; radius = clampf(radius, 0.2f, 100.0f); }   // :31-34,:92-96
+void InteractiveCamera::changeAltitude(float m) { centerPosition[1] += m; }                                       // :36-39
+void InteractiveCamera::setResolution(float x, float y) { resolution[0] = x; resolution[1] = y; setFOVX(fov[0]); }   // :53-56
+void InteractiveCamera::setFOVX(float fovx) {                                                                      // :58-62
+    fov[0] = fovx;
+    fov[1] = (atan(tan((fovx * M_PI / 180.0) * 0.5) * (resolution[1] / resolution[0])) * 2.0) * 180.0 / M_PI;
+}
+void InteractiveCamera::eyePosition(float out[3]) const {                                                          // :64-70
+    float x = sin(yaw) * cos(pitch), y = sin(pitch), z = cos(yaw) * cos(pitch);
+    out[0] = centerPosition[0] + x * radius; out[1] = centerPosition[1] + y * radius; out[2] = centerPosition[2] + z * radius;
+}
+Camera* InteractiveCamera::makeCamera() const {
+    float e[3];
+    eyePosition(e);
+    return new Camera(Vector3D(e[0], e[1], e[2]), Vector3D(centerPosition[0], centerPosition[1], centerPosition[2]),
+                      Vector3D(0, 1, 0), fov[1], (int)resolution[0], (int)resolution[1]);
+}
+
+// ---- CPU-testable entry points: what the loader, the image writer and the orbit camera produce --------
+extern "C" int rt_host_load_obj(const char* obj, const char* texture, int max_faces, float* tri_v, float* tri_rgb,
+                                int capacity, char* err, int err_len) {
+    try {
+        World world;
+        load_image_from_obj(&world, obj, texture ? texture : "", "", max_faces);
+        int n = 0;
+        for (Object* o : world.getObjectList()) {
+            Triangle* t = static_cast<Triangle*>(o);
+            if (n < capacity) {
+                for (int k = 0; k < 3; k++) { Vector3D v = t->getVertex(k); for (int a = 0; a < 3; a++) tri_v[9 * n + 3 * k + a] = (float)v.e[a]; }
+                if (tri_rgb && t->getMaterial()->isBarycentric()) {
+                    const BarycentricMaterial* bm = static_cast<const BarycentricMaterial*>(t->getMaterial());
+                    for (int k = 0; k < 3; k++) { const Color& c = bm->vertexColor(k); tri_rgb[9 * n + 3 * k] = (float)c.r; tri_rgb[9 * n + 3 * k + 1] = (float)c.g; tri_rgb[9 * n + 3 * k + 2] = (float)c.b; }
+                }
+            }
+            n++;
+        }
+        for (Object* o : world.getObjectList()) delete o;
+        return n;
+    } catch (const std::exception& e) {
+        if (err && err_len > 0) { strncpy(err, e.what(), err_len - 1); err[err_len - 1] = 0; }
+        return -1;
+    }
+}
+extern "C" int rt_host_save_png(const char* file, const unsigned char* rgb, int w, int h) { return save_png(file, rgb, w, h) ? 0 : -1; }
+extern "C" void rt_host_orbit_eye(float yaw, float pitch, float radius, float out[3]) {
+    InteractiveCamera ic;
+    ic.yaw = yaw; ic.pitch = pitch; ic.radius = radius;
+    ic.eyePosition(out);
+}
+extern "C" void rt_host_camera_ray(const double pos[3], const double target[3], const double up[3], float fovy, int w, int h,
+                                   int i, int j, double out[3]) {
+    Camera cam(Vector3D(pos[0], pos[1], pos[2]), Vector3D(target[0], target[1], target[2]), Vector3D(up[0], up[1], up[2]), fovy, w, h);
+    Vector3D d = cam.get_ray_direction(i, j);
+    out[0] = d.X(); out[1] = d.Y(); out[2] = d.Z();
+}
+
 // ---- demo entry points for the tests: scenes built through the class API exactly as
 // Serial/lumina.cpp:302-370 does, rendered with RenderEngine. ------------------------------------------
 extern "C" int rt_host_demo(const char* which, const char* assets_dir, int width, int height, int depth,
