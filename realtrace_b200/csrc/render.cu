@@ -580,6 +580,7 @@ __global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ Sha
 // no host involvement; idle lanes pull new rays from the cursor.  The arithmetic per ray is the wave
 // path's, and pixel sums are integer atomics, so the frame is bit-identical to the wave loop's.
 #define RT_PATH_STACK 24      // pending rays per lane (binary dielectric tree, depth-first)
+#pragma nv_diag_suppress 549  // `pend` is only read below psp, i.e. after it was written
 
 struct PathArgs {
     SceneDev s;
