@@ -340,25 +340,27 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         rays_total = float(rays_local)
     value = rays_total / (ms * 1e-3) / 1e6
 
-    # ---- N > 1 diagnostics: where does a frame's time go on this rank? (p2p path without stealing)
+    # ---- N > 1 diagnostics (RT_BENCH_PHASES=1): where does a frame's time go on each rank?  Same asynchronous
+    # frame loop as the timed one, with extra events between the phases (p2p path without stealing).
     if world > 1 and assemble == "p2p" and not cursor_ptr and os.environ.get("RT_BENCH_PHASES"):
-        acc = np.zeros(3)
-        for _ in range(10):
+        nfr = 20
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nfr)]
+        for f_ in range(nfr):
             k = frame_no[0]
             frame_no[0] += 1
+            flush.fill_(f_ & 0xff)
             torch.distributed.all_reduce(tick)
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            e[0].record(stream)
+            ev[f_][0].record(stream)
             ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES, want_stats=False)
-            e[1].record(stream)
+            ev[f_][1].record(stream)
             ctx.peer_sync(sync_ptr, rank, world, k, 0)
             ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr)
-            e[2].record(stream)
+            ev[f_][2].record(stream)
             ctx.peer_sync(sync_ptr, rank, world, k, 1)
-            e[3].record(stream)
-            torch.cuda.synchronize()
-            acc += np.array([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])])
-        print(f"[phases rank {rank}] render {acc[0]/10:.3f} ms, wait+push {acc[1]/10:.3f} ms, handshake {acc[2]/10:.3f} ms", file=sys.stderr, flush=True)
+            ev[f_][3].record(stream)
+        barrier()
+        acc = np.array([[e[a].elapsed_time(e[a + 1]) for a in range(3)] for e in ev]).mean(axis=0)
+        print(f"[phases rank {rank}] render {acc[0]:.3f} ms, wait+push {acc[1]:.3f} ms, handshake {acc[2]:.3f} ms", file=sys.stderr, flush=True)
 
     # ---- e2e: host buffers through rt_render (N = 1) / render + gather + D2H of the frame (N > 1)
     host_frame = torch.empty(H * W * 3, dtype=torch.uint8, pin_memory=True)
