@@ -257,10 +257,21 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
                 frame = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
                 frame_ptr = frame.data_ptr()
 
+    push_params = api.Context._params(depth, rank=rank, world=world, flags=api.FLAG_PACKED_TILES)
+    align_epoch = [0]
+
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
+
+    def align_ranks():
+        """Untimed line-up of the ranks on the device (peer-memory barrier kernel, or NCCL without IPC)."""
+        if sync_ptr is not None:
+            ctx.peer_barrier(sync_ptr, world, align_epoch[0])
+            align_epoch[0] += 1
+        else:
+            torch.distributed.all_reduce(tick)
 
     orbit = workload == "orbit"
     orbit_k = [0]
@@ -286,12 +297,16 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
                 ctx.peer_sync(sync_ptr, rank, world, k, 0)
                 st = ctx.render_device(cam, depth, frame_ptr, rank=rank, world=world, want_stats=want_stats,
                                        steal=(args.steal_div, k, cursor_ptr))
-            else:               # own tiles into a local packed buffer, then one kernel pushes them over NVLink
+                ctx.peer_sync(sync_ptr, rank, world, k, 1)   # completion handshake: after it, rank 0 holds the frame
+            elif want_stats:    # own tiles into a local packed buffer, then one kernel pushes them over NVLink
                 st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world,
-                                       flags=api.FLAG_PACKED_TILES, want_stats=want_stats)
+                                       flags=api.FLAG_PACKED_TILES, want_stats=True)
                 ctx.peer_sync(sync_ptr, rank, world, k, 0)
                 ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr)
-            ctx.peer_sync(sync_ptr, rank, world, k, 1)       # completion handshake: after it, rank 0 holds the frame
+                ctx.peer_sync(sync_ptr, rank, world, k, 1)
+            else:               # the same four steps in one library call (one ctypes transition per frame)
+                st = None
+                ctx.render_push(cam, push_params, packed.data_ptr(), frame_ptr, sync_ptr, k)
             return st
         st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES,
                                want_stats=want_stats)
@@ -316,7 +331,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         if world > 1:
             # untimed alignment: without it the L2 flush of a lagging rank (outside its own event pair) would be
             # counted inside the event pair of every rank that waits for it
-            torch.distributed.all_reduce(tick)
+            align_ranks()
         evs[k][0].record(stream)
         step_device(False)
         evs[k][1].record(stream)
@@ -349,7 +364,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
             k = frame_no[0]
             frame_no[0] += 1
             flush.fill_(f_ & 0xff)
-            torch.distributed.all_reduce(tick)
+            align_ranks()
             ev[f_][0].record(stream)
             ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES, want_stats=False)
             ev[f_][1].record(stream)

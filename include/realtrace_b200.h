@@ -192,6 +192,13 @@ int rt_download(rt_ctx* ctx, const void* dev_ptr, void* host, uint64_t bytes);
  * frame is complete there; ranks > 0 never run more than one frame ahead of rank 0.  frame_index must
  * count 0, 1, 2, ... identically on all ranks.                                                    */
 int rt_peer_sync(rt_ctx* ctx, void* sync_buf, int32_t rank, int32_t world_size, uint32_t frame_index, int32_t phase);
+/* A symmetric barrier over the same buffer: every rank enqueues it with the same epoch = 0, 1, 2, ...     */
+int rt_peer_barrier(rt_ctx* ctx, void* sync_buf, int32_t world_size, uint32_t epoch);
+/* One call for a whole multi-GPU frame step, all of it only enqueued: render this rank's tiles into the local
+ * packed buffer (p->flags must carry RT_FLAG_PACKED_TILES), rt_peer_sync phase 0, push the tiles into the
+ * shared frame, rt_peer_sync phase 1.                                                                     */
+int rt_render_push(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, void* packed_dev, void* frame_dev,
+                   void* sync_buf, uint32_t frame_index);
 /* tile helpers for the gather-based assembly (the gather itself is NCCL, outside)               */
 /* number of tiles in the frame / owned by `rank`, and bytes of one packed tile                  */
 int rt_tile_layout(int32_t width, int32_t height, int32_t tile_w, int32_t tile_h, int32_t rank, int32_t world_size,

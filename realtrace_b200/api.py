@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "rt_scene_set_planes", "rt_scene_set_cylinders", "rt_scene_set_materials", "rt_scene_set_lights",
     "rt_scene_set_environment", "rt_scene_commit", "rt_scene_update_vertices", "rt_scene_build_stats", "rt_render",
     "rt_render_device", "rt_tile_layout", "rt_assemble_tiles", "rt_trace_rays", "rt_shade_rays", "rt_bvh_download",
-    "rt_debug_sort_pairs", "rt_debug_warp_times", "rt_synchronize", "rt_peer_sync", "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_download",
+    "rt_debug_sort_pairs", "rt_debug_warp_times", "rt_synchronize", "rt_peer_sync", "rt_peer_barrier", "rt_render_push", "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_download",
 ]
 
 _lib = None
@@ -104,6 +104,8 @@ def load_library():
     lib.rt_debug_warp_times.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
     lib.rt_synchronize.argtypes = [vp]
     lib.rt_peer_sync.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_uint32, C.c_int32]
+    lib.rt_peer_barrier.argtypes = [vp, vp, C.c_int32, C.c_uint32]
+    lib.rt_render_push.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp, vp, vp, C.c_uint32]
     lib.rt_shared_buffer_create.argtypes = [vp, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
     lib.rt_shared_buffer_open.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.rt_download.argtypes = [vp, vp, vp, C.c_uint64]
@@ -269,6 +271,15 @@ class Context:
 
     def peer_sync(self, sync_ptr, rank, world, frame_index, phase):
         self._check(self.lib.rt_peer_sync(self.h, sync_ptr, rank, world, frame_index, phase))
+
+    def peer_barrier(self, sync_ptr, world, epoch):
+        self._check(self.lib.rt_peer_barrier(self.h, sync_ptr, world, epoch))
+
+    def render_push(self, cam_struct, params_struct, packed_ptr, frame_ptr, sync_ptr, frame_index):
+        """One multi-GPU frame step (render packed -> handshake -> push -> handshake), only enqueued.  Takes
+        prebuilt RtCamera / RtRenderParams so that the per-frame host cost is one ctypes call."""
+        self._check(self.lib.rt_render_push(self.h, C.byref(cam_struct), C.byref(params_struct), packed_ptr, frame_ptr,
+                                            sync_ptr, frame_index))
 
     def download(self, dev_ptr, host_array):
         self._check(self.lib.rt_download(self.h, dev_ptr, host_array.ctypes.data, host_array.nbytes))

@@ -355,6 +355,28 @@ int rt_peer_sync(rt_ctx* ctx, void* sync_buf, int32_t rank, int32_t world_size, 
     });
 }
 
+int rt_peer_barrier(rt_ctx* ctx, void* sync_buf, int32_t world_size, uint32_t epoch) {
+    return guarded(ctx, [&] {
+        need(sync_buf && world_size >= 1, "rt_peer_barrier: bad arguments");
+        rt_peer_barrier_enqueue(ctx, sync_buf, world_size, epoch);
+    });
+}
+
+int rt_render_push(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, void* packed_dev, void* frame_dev,
+                   void* sync_buf, uint32_t frame_index) {
+    return guarded(ctx, [&] {
+        check_render_args(ctx, cam, p);
+        need(packed_dev && frame_dev && sync_buf, "rt_render_push: NULL buffer");
+        need((p->flags & RT_FLAG_PACKED_TILES) != 0 && p->world_size >= 1, "rt_render_push: needs RT_FLAG_PACKED_TILES and a world size");
+        int world = p->world_size > 1 ? p->world_size : 1, rank = world > 1 ? p->rank : 0;
+        rt_render_frame(ctx, cam, p, packed_dev, nullptr, nullptr);
+        rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 0);
+        rt_assemble(ctx, packed_dev, rank, world, cam->width, cam->height, p->tile_w > 0 ? p->tile_w : 64,
+                    p->tile_h > 0 ? p->tile_h : 32, frame_dev);
+        rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 1);
+    });
+}
+
 int rt_download(rt_ctx* ctx, const void* dev_ptr, void* host, uint64_t bytes) {
     return guarded(ctx, [&] {
         need(dev_ptr && host, "rt_download: NULL buffer");

@@ -930,6 +930,19 @@ __global__ void k_peer_wait_all(volatile uint32_t* sync, uint32_t frame, uint32_
     __threadfence_system();
 }
 
+// Symmetric barrier over the same buffer (sync[80] counts arrivals of all epochs): used to line ranks up.
+__global__ void k_peer_barrier(uint32_t* sync, uint32_t target, uint32_t* sticky) {
+    __threadfence_system();
+    atomicAdd_system(sync + 80, 1u);
+    volatile uint32_t* v = sync + 80;
+    long long t0 = clock64();
+    while (*v < target) {
+        if (clock64() - t0 > 4000000000ll) { atomicOr(sticky, 4u); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 CamDev make_cam(const rt_camera* c) {
     CamDev d;
     for (int k = 0; k < 3; k++) { d.pos[k] = c->pos[k]; d.u[k] = c->u[k]; d.v[k] = c->v[k]; d.w[k] = c->w[k]; }
@@ -1404,6 +1417,12 @@ void rt_peer_sync_enqueue(rt_ctx* c, void* sync_buf, int rank, int world, uint32
         if (rank != 0) k_peer_arrive<<<1, 1, 0, st>>>(sync, frame_index);
         else k_peer_wait_all<<<1, 1, 0, st>>>(sync, frame_index, (uint32_t)(world - 1), c->d_sticky.p);
     }
+    RT_CUDA(cudaGetLastError());
+}
+
+void rt_peer_barrier_enqueue(rt_ctx* c, void* sync_buf, int world, uint32_t epoch) {
+    if (world <= 1) return;
+    k_peer_barrier<<<1, 1, 0, c->stream>>>((uint32_t*)sync_buf, (uint32_t)world * (epoch + 1u), c->d_sticky.p);
     RT_CUDA(cudaGetLastError());
 }
 

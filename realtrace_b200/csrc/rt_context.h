@@ -178,6 +178,7 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
                    int32_t* prim_out, float* t_out, float* rgb_out);      // render.cu
 void rt_render_init(rt_ctx* c);                                     // render.cu
 void rt_sync_and_check(rt_ctx* c);                                  // render.cu
+void rt_peer_barrier_enqueue(rt_ctx* c, void* sync_buf, int world, uint32_t epoch);   // render.cu
 void rt_peer_sync_enqueue(rt_ctx* c, void* sync_buf, int rank, int world, uint32_t frame_index, int phase);   // render.cu
 void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int width, int height, int tile_w,
                  int tile_h, void* frame);                          // render.cu
