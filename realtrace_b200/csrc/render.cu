@@ -943,6 +943,32 @@ __global__ void k_peer_barrier(uint32_t* sync, uint32_t target, uint32_t* sticky
     __threadfence_system();
 }
 
+// Same scatter with 16-byte transactions (what NVLink peer stores want): one thread per 16 B of a tile row.
+// Requires rows of the frame and of the tile to be 16-byte multiples; partial edge rows fall back to bytes.
+__global__ void __launch_bounds__(256) k_assemble16(const uint8_t* __restrict__ packed, uint8_t* __restrict__ frame,
+                                                   int W, int H, int tile_w, int tile_h, int tiles_x,
+                                                   uint32_t tiles_total, int src, int world) {
+    const uint32_t chunks_per_row = (uint32_t)(tile_w * 3) >> 4, chunks_per_tile = chunks_per_row * (uint32_t)tile_h;
+    uint32_t n_owned = tiles_total > (uint32_t)src ? (tiles_total - (uint32_t)src + (uint32_t)world - 1) / (uint32_t)world : 0u;
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_owned * chunks_per_tile) return;
+    uint32_t tl = q / chunks_per_tile, r = q % chunks_per_tile;
+    uint32_t tile = (uint32_t)src + tl * (uint32_t)world;
+    int y = (int)(r / chunks_per_row), cb = (int)(r % chunks_per_row) * 16;     // byte offset inside the tile row
+    int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
+    int j = ty * tile_h + y;
+    if (j >= H) return;
+    int row_bytes = min(tile_w, W - tx * tile_w) * 3;                           // valid bytes of this tile row
+    if (cb >= row_bytes) return;
+    size_t src0 = ((size_t)tl * tile_w * tile_h + (size_t)y * tile_w) * 3 + cb;
+    size_t dst0 = ((size_t)tx * tile_w + (size_t)j * W) * 3 + cb;
+    if (cb + 16 <= row_bytes) {
+        *reinterpret_cast<uint4*>(frame + dst0) = *reinterpret_cast<const uint4*>(packed + src0);
+    } else {
+        for (int k = 0; k < row_bytes - cb; k++) frame[dst0 + k] = packed[src0 + k];
+    }
+}
+
 CamDev make_cam(const rt_camera* c) {
     CamDev d;
     for (int k = 0; k < 3; k++) { d.pos[k] = c->pos[k]; d.u[k] = c->u[k]; d.v[k] = c->v[k]; d.w[k] = c->w[k]; }
@@ -1432,8 +1458,15 @@ void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int wid
     uint32_t total = (uint32_t)tiles_x * (uint32_t)tiles_y;
     uint32_t n_owned = total > (uint32_t)src_rank ? (total - (uint32_t)src_rank + (uint32_t)world - 1) / (uint32_t)world : 0u;
     if (!n_owned) return;
-    uint32_t quads = n_owned * (uint32_t)(tile_w * tile_h / 4);
-    k_assemble<<<(quads + 255) / 256, 256, 0, c->stream>>>((const uint8_t*)packed, (uint8_t*)frame, width, height,
-                                                           tile_w, tile_h, tiles_x, total, src_rank, world);
+    bool wide = (width * 3) % 16 == 0 && (tile_w * 3) % 16 == 0 && ((uintptr_t)packed & 15) == 0 && ((uintptr_t)frame & 15) == 0;
+    if (wide) {
+        uint32_t chunks = n_owned * (uint32_t)(tile_w * 3 / 16) * (uint32_t)tile_h;
+        k_assemble16<<<(chunks + 255) / 256, 256, 0, c->stream>>>((const uint8_t*)packed, (uint8_t*)frame, width, height,
+                                                                  tile_w, tile_h, tiles_x, total, src_rank, world);
+    } else {
+        uint32_t quads = n_owned * (uint32_t)(tile_w * tile_h / 4);
+        k_assemble<<<(quads + 255) / 256, 256, 0, c->stream>>>((const uint8_t*)packed, (uint8_t*)frame, width, height,
+                                                               tile_w, tile_h, tiles_x, total, src_rank, world);
+    }
     RT_CUDA(cudaGetLastError());
 }
