@@ -321,7 +321,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     # asynchronously and only the final barrier synchronises.
     sampler = ClockSampler(dist_ctx["local_rank"])
     sampler.start()
-    stats = [step_device(True) for _ in range(max(warmup, 3))]
+    stats = [step_device(True) for _ in range(max(warmup, 3) + 2)]   # statistics frames; the first (cold) one is dropped from the per-kernel medians
     barrier()
     sampler.t_begin = time.perf_counter()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -417,11 +417,11 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         cnt = ctx.render_device(cam, depth, frame_ptr, flags=api.FLAG_COUNT_WORK)
         n_rays = total_rays(cnt)
         n_near = cnt["rays_primary"] + cnt["rays_secondary"]
-        ms_k = {"k_traverse<primary> (nearest hit + fused shadow rays)": np.mean([s["ms_trace"] for s in stats]),
-                "k_traverse<shadow> (any hit)": np.mean([s["ms_shadow"] for s in stats]),
-                "k_shade<primary>": np.mean([s["ms_shade"] for s in stats]),
-                "k_paths (all bounce generations)": np.mean([s["ms_secondary"] for s in stats]),
-                "k_resolve": np.mean([s["ms_resolve"] for s in stats])}
+        ms_k = {"k_traverse<primary> (nearest hit + fused shadow rays)": float(np.median([s["ms_trace"] for s in stats[1:]])),
+                "k_traverse<shadow> (any hit)": float(np.median([s["ms_shadow"] for s in stats[1:]])),
+                "k_shade<primary>": float(np.median([s["ms_shade"] for s in stats[1:]])),
+                "k_paths (all bounce generations)": float(np.median([s["ms_secondary"] for s in stats[1:]])),
+                "k_resolve": float(np.median([s["ms_resolve"] for s in stats[1:]]))}
         out["kernel_ms"] = {k: float(v) for k, v in ms_k.items()}
         nodes_all = cnt["node_visits"] + cnt["shadow_node_visits"]
         tris_all = cnt["tri_tests"] + cnt["shadow_tri_tests"]
