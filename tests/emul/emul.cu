@@ -30,6 +30,64 @@ struct EmulScene {
 
 f3 vtx(const float* v, uint32_t i, int k) { const float* p = v + 9 * (size_t)i + 3 * k; return mk3(p[0], p[1], p[2]); }
 
+// ---- experiment only: top-down binned-SAH build over the Morton-sorted triangles (same node format), to
+// measure how far the LBVH is from a high-quality tree.  Leaves hold one triangle.
+struct SahTmp { Aabb box; f3 ctr; uint32_t k; };
+static float half_area(const Aabb& b) { f3 d = b.hi - b.lo; return d.x * d.y + d.y * d.z + d.z * d.x; }
+static int sah_build(std::vector<SahTmp>& prims, int lo, int hi, std::vector<float4>& nodes, Aabb& out_box, float pad_abs) {
+    // returns child code for the range [lo, hi)
+    Aabb box; box.lo = mk3(RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX); box.hi = mk3(-RT_FLT_MAX, -RT_FLT_MAX, -RT_FLT_MAX);
+    Aabb cb = box;
+    for (int i = lo; i < hi; i++) { box = aabb_union(box, prims[i].box); Aabb c; c.lo = c.hi = prims[i].ctr; cb = aabb_union(cb, c); }
+    out_box = box;
+    if (hi - lo == 1) return rt_leaf_code(prims[lo].k, 1u);
+    int best_axis = -1, best_split = -1; float best_cost = RT_FLT_MAX;
+    const int NB = 16;
+    float ext[3] = {cb.hi.x - cb.lo.x, cb.hi.y - cb.lo.y, cb.hi.z - cb.lo.z};
+    float clo[3] = {cb.lo.x, cb.lo.y, cb.lo.z};
+    for (int ax = 0; ax < 3; ax++) {
+        if (!(ext[ax] > 0)) continue;
+        Aabb bb[NB]; int cnt[NB];
+        for (int b = 0; b < NB; b++) { bb[b].lo = mk3(RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX); bb[b].hi = mk3(-RT_FLT_MAX, -RT_FLT_MAX, -RT_FLT_MAX); cnt[b] = 0; }
+        for (int i = lo; i < hi; i++) {
+            float c = ax == 0 ? prims[i].ctr.x : ax == 1 ? prims[i].ctr.y : prims[i].ctr.z;
+            int b = (int)((c - clo[ax]) / ext[ax] * NB); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
+            bb[b] = aabb_union(bb[b], prims[i].box); cnt[b]++;
+        }
+        float la[NB], ra[NB]; int lc[NB], rc[NB];
+        Aabb acc; acc.lo = mk3(RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX); acc.hi = mk3(-RT_FLT_MAX, -RT_FLT_MAX, -RT_FLT_MAX); int c = 0;
+        for (int b = 0; b < NB; b++) { if (cnt[b]) acc = aabb_union(acc, bb[b]); c += cnt[b]; la[b] = c ? half_area(acc) : 0; lc[b] = c; }
+        acc.lo = mk3(RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX); acc.hi = mk3(-RT_FLT_MAX, -RT_FLT_MAX, -RT_FLT_MAX); c = 0;
+        for (int b = NB - 1; b >= 0; b--) { if (cnt[b]) acc = aabb_union(acc, bb[b]); c += cnt[b]; ra[b] = c ? half_area(acc) : 0; rc[b] = c; }
+        for (int b = 0; b < NB - 1; b++) {
+            if (lc[b] == 0 || rc[b + 1] == 0) continue;
+            float cost = la[b] * lc[b] + ra[b + 1] * rc[b + 1];
+            if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = b; }
+        }
+    }
+    int mid;
+    if (best_axis < 0) mid = (lo + hi) / 2;
+    else {
+        auto it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const SahTmp& p) {
+            float c = best_axis == 0 ? p.ctr.x : best_axis == 1 ? p.ctr.y : p.ctr.z;
+            int b = (int)((c - clo[best_axis]) / ext[best_axis] * NB); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
+            return b <= best_split; });
+        mid = (int)(it - prims.begin());
+        if (mid == lo || mid == hi) mid = (lo + hi) / 2;
+    }
+    int me = (int)(nodes.size() / 4);
+    nodes.resize(nodes.size() + 4);
+    Aabb L, R;
+    int cl = sah_build(prims, lo, mid, nodes, L, pad_abs), cr = sah_build(prims, mid, hi, nodes, R, pad_abs);
+    auto padded = [&](Aabb b) { Aabb r = aabb_pad(b); r.lo = r.lo - mk3(pad_abs, pad_abs, pad_abs); r.hi = r.hi + mk3(pad_abs, pad_abs, pad_abs); return r; };
+    Aabb Lp = padded(L), Rp = padded(R);
+    nodes[4 * me] = make_float4(Lp.lo.x, Lp.hi.x, Lp.lo.y, Lp.hi.y);
+    nodes[4 * me + 1] = make_float4(Rp.lo.x, Rp.hi.x, Rp.lo.y, Rp.hi.y);
+    nodes[4 * me + 2] = make_float4(Lp.lo.z, Lp.hi.z, Rp.lo.z, Rp.hi.z);
+    nodes[4 * me + 3] = make_float4(as_float((uint32_t)cl), as_float((uint32_t)cr), 0, 0);
+    return me;
+}
+
 void build(const oracle_scene* in, int leaf_size, EmulScene& S) {
     uint32_t n = in->n_tri;
     // analytic list: spheres, planes, cylinders (object ids default to after the triangles)
@@ -163,6 +221,19 @@ void build(const oracle_scene* in, int leaf_size, EmulScene& S) {
         S.nodes = {make_float4(p.lo.x, p.hi.x, p.lo.y, p.hi.y), make_float4(RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX),
                    make_float4(p.lo.z, p.hi.z, RT_FLT_MAX, RT_FLT_MAX),
                    make_float4(as_float((uint32_t)rt_leaf_code(0, 1)), as_float((uint32_t)RT_EMPTY_CODE), 0, 0)};
+    }
+    if (getenv("EMUL_SAH") && nb >= 2) {
+        std::vector<SahTmp> prims(nb);
+        for (uint32_t k = 0; k < nb; k++) {
+            uint32_t i = S.order[k];
+            prims[k].box = tri_aabb(vtx(in->tri_v, i, 0), vtx(in->tri_v, i, 1), vtx(in->tri_v, i, 2));
+            prims[k].ctr = (prims[k].box.lo + prims[k].box.hi) * 0.5f;
+            prims[k].k = k;
+        }
+        std::vector<float4> nodes;
+        Aabb rb;
+        sah_build(prims, 0, (int)nb, nodes, rb, pad_abs);
+        S.nodes.swap(nodes);
     }
     SceneDev& d = S.dev;
     d.nodes = S.nodes.data(); d.tris = S.tris.data(); d.tri_rgb = S.tri_rgb.empty() ? nullptr : S.tri_rgb.data();
