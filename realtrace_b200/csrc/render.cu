@@ -498,8 +498,11 @@ struct ShadeArgs {
 };
 
 // Shading proper: no traversal in here, the shadow answers come from k_traverse<SHADOW>.
+#ifndef RT_SHADE_MIN_BLOCKS
+#define RT_SHADE_MIN_BLOCKS 1
+#endif
 template <bool PRIMARY>
-__global__ void __launch_bounds__(SHADE_TPB) k_shade(const __grid_constant__ ShadeArgs a) {
+__global__ void __launch_bounds__(SHADE_TPB, RT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ ShadeArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t n = a.wave->n_hits;
     const f3 bg = mk3(a.s.background[0], a.s.background[1], a.s.background[2]);

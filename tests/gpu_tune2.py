@@ -1,7 +1,7 @@
 """Development probe: loop style / leaf size / refill sweeps, full frame and a 1/8 share."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-configs = [dict()]
+configs = [dict(RT_LIB_PATH=os.path.join(ROOT, "tests", "emul", f"librt_sh{mb}.so")) for mb in (1, 10, 12, 16)]
 code = f"""
 import sys, os; sys.path.insert(0, {ROOT!r})
 from realtrace_b200 import api, scenes
@@ -13,7 +13,7 @@ for world in (1, 8):
     for r in range(5):
         st = ctx.render(cam, depth, world=world, rank=0)[3]
         if best is None or st['ms_device'] < best['ms_device']: best = st
-    out.append('w%d: %.3f (tr %.3f sh %.3f)' % (world, best['ms_device'], best['ms_trace'], best['ms_shadow']))
+    out.append('w%d: %.3f (tr %.3f shade %.3f)' % (world, best['ms_device'], best['ms_trace'], best['ms_shade']))
 print(os.environ.get('TAG'), ' | '.join(out), flush=True)
 """
 for cfg in configs:
