@@ -208,6 +208,16 @@ __global__ void __launch_bounds__(TPB) k_refit(const float* __restrict__ v, cons
     }
 }
 
+// 4-wide view of the finished binary tree (rt_bvh.h: build_wide_node), one thread per binary node.
+__global__ void __launch_bounds__(TPB) k_collapse4(const float4* __restrict__ nodes, int n_nodes, float4* __restrict__ nodes4) {
+    int i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= n_nodes) return;
+    float4 q[RT_NODE4_FLOAT4S];
+    build_wide_node(nodes, i, q);
+#pragma unroll
+    for (int k = 0; k < RT_NODE4_FLOAT4S; k++) nodes4[RT_NODE4_FLOAT4S * (size_t)i + k] = q[k];
+}
+
 // A BVH of one triangle: root with one leaf child and one empty child.
 __global__ void k_single_leaf(const float* __restrict__ v, const uint32_t* __restrict__ order,
                               float4* __restrict__ nodes, float pad_abs) {
@@ -290,6 +300,7 @@ static void upload_static_scene(rt_ctx* c) {
 static void publish_scene(rt_ctx* c) {
     SceneDev& s = c->scene;
     s.nodes = c->d_nodes.p;
+    s.nodes4 = (c->wide_bvh && c->n_bvh >= 1) ? c->d_nodes4.p : nullptr;
     s.tris = c->d_tris.p;
     s.tri_rgb = c->h_tri_rgb.empty() ? nullptr : c->d_tri_rgb.p;
     s.analytic = c->d_analytic.p;
@@ -323,6 +334,12 @@ static void run_refit(rt_ctx* c) {
         RT_CUDA(cudaGetLastError());
     } else if (nb == 1) {
         k_single_leaf<<<1, 1, 0, st>>>(c->d_tri_v.p, order, c->d_nodes.p, pad_abs);
+        RT_CUDA(cudaGetLastError());
+    }
+    if (c->wide_bvh && nb >= 1) {
+        int nn = nb >= 2 ? (int)nb - 1 : 1;
+        c->d_nodes4.reserve(RT_NODE4_FLOAT4S * (size_t)nn);
+        k_collapse4<<<blocks_for((uint32_t)nn), TPB, 0, st>>>(c->d_nodes.p, nn, c->d_nodes4.p);
         RT_CUDA(cudaGetLastError());
     }
 }

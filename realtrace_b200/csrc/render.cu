@@ -178,10 +178,13 @@ struct TravArgs {
 // the shadow ray(s) of that hit (one per light, same walk with early exit) and only then emits the
 // hit together with its occlusion bits.  One kernel and one tail per wave instead of two, no second
 // derivation of the hit point, and lanes whose rays missed keep pulling new rays meanwhile.
-template <int MODE, bool COUNT, bool FUSE>
+// WIDE: walk the 4-wide view of the tree (SceneDev::nodes4); a template parameter so that the binary walk
+// keeps its register budget (72 vs 96 registers with both compiled in).
+template <int MODE, bool COUNT, bool FUSE, bool WIDE = false>
 __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ TravArgs a) {
     constexpr bool ANY = MODE == MODE_SHADOW;
     static_assert(!(FUSE && ANY), "FUSE applies to the nearest-hit modes");
+    static_assert(!WIDE || FUSE, "the wide walk is instantiated for the fused kernels only");
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -343,7 +346,8 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
             if (a.loop_style == 0) {
                 while (rt_is_internal(node)) {
                     if (COUNT) wcp->nodes++;
-                    node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
+                    node = WIDE ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
+                                 : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                 }
                 while (node < 0) {
                     if (leaf_test(a.s, node, r, hit, any, wcp)) {
@@ -358,7 +362,8 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
                 for (int it = 0; it < a.loop_style && node != RT_DONE; it++) {
                     if (rt_is_internal(node)) {
                         if (COUNT) wcp->nodes++;
-                        node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
+                        node = WIDE ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
+                                 : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                     } else {
                         if (leaf_test(a.s, node, r, hit, any, wcp)) {
                             found = true;
@@ -600,7 +605,7 @@ struct PathArgs {
     uint32_t brute;
 };
 
-template <bool COUNT>
+template <bool COUNT, bool WIDE = false>
 __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ PathArgs a) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -687,7 +692,8 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
             for (int it = 0; it < burst && node != RT_DONE; it++) {
                 if (rt_is_internal(node)) {
                     if (COUNT) wcp->nodes++;
-                    node = bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
+                    node = WIDE ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
+                                 : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                 } else {
                     if (leaf_test(a.s, node, r, hit, any, wcp)) {
                         found = true;
@@ -1098,8 +1104,14 @@ RayQueue queue_of(rt_ctx* c, int b) {
 template <int MODE, bool FUSE>
 void launch_traverse(rt_ctx* c, const TravArgs& a, bool count) {
     int blocks = MODE == MODE_SHADOW ? c->shadow_blocks : (FUSE ? c->fused_blocks : c->trace_blocks);
-    if (count) k_traverse<MODE, true, FUSE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
-    else k_traverse<MODE, false, FUSE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+    if (FUSE && a.s.nodes4 != nullptr) {
+        constexpr bool W = FUSE;   // only the fused kernels have a wide instantiation
+        if (count) k_traverse<MODE, true, FUSE, W><<<c->wide_blocks, TRAV_TPB, 0, c->stream>>>(a);
+        else k_traverse<MODE, false, FUSE, W><<<c->wide_blocks, TRAV_TPB, 0, c->stream>>>(a);
+    } else {
+        if (count) k_traverse<MODE, true, FUSE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+        else k_traverse<MODE, false, FUSE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+    }
     RT_CUDA(cudaGetLastError());
 }
 template <bool PRIMARY>
@@ -1132,6 +1144,7 @@ uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot
     sa.occl_bits = fuse ? 1 : 0;
     if (!fuse && c->scene.n_lights > 0) {
         TravArgs sh = ta;
+        sh.s.nodes4 = nullptr;
         sh.hits_in = c->d_hits.p; sh.hitq_in = c->d_hitq.p; sh.occl = c->d_occl.p;
         sh.primary_wave = PRIMARY ? 1u : 0u;
         sh.refill_min = c->refill_shadow;
@@ -1173,8 +1186,13 @@ void launch_paths(rt_ctx* c, int slot, int cur, int max_depth, uint32_t brute, b
     pa.refill_min = c->refill_queue;
     pa.loop_style = c->loop_queue;
     pa.brute = brute;
-    if (count) k_paths<true><<<c->path_blocks, TRAV_TPB, 0, c->stream>>>(pa);
-    else k_paths<false><<<c->path_blocks, TRAV_TPB, 0, c->stream>>>(pa);
+    if (pa.s.nodes4) {
+        if (count) k_paths<true, true><<<c->path_wide_blocks, TRAV_TPB, 0, c->stream>>>(pa);
+        else k_paths<false, true><<<c->path_wide_blocks, TRAV_TPB, 0, c->stream>>>(pa);
+    } else {
+        if (count) k_paths<true><<<c->path_blocks, TRAV_TPB, 0, c->stream>>>(pa);
+        else k_paths<false><<<c->path_blocks, TRAV_TPB, 0, c->stream>>>(pa);
+    }
     RT_CUDA(cudaGetLastError());
 }
 
@@ -1233,6 +1251,9 @@ void rt_render_init(rt_ctx* c) {
                          persistent_blocks(k_traverse<MODE_QUEUE, false, true>, TRAV_TPB, c->sm_count));
     c->shadow_blocks = persistent_blocks(k_traverse<MODE_SHADOW, false, false>, TRAV_TPB, c->sm_count);
     c->path_blocks = persistent_blocks(k_paths<false>, TRAV_TPB, c->sm_count);
+    c->path_wide_blocks = persistent_blocks(k_paths<false, true>, TRAV_TPB, c->sm_count);
+    c->wide_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false, true, true>, TRAV_TPB, c->sm_count),
+                        persistent_blocks(k_traverse<MODE_QUEUE, false, true, true>, TRAV_TPB, c->sm_count));
     c->shade_blocks = lo(persistent_blocks(k_shade<true>, SHADE_TPB, c->sm_count),
                          persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
     if (c->blocks_per_sm > 0) {   // RT_BLOCKS_PER_SM: cap the persistent grids (tuning)

@@ -97,3 +97,37 @@ RT_HD Aabb aabb_pad(Aabb b) {
                b.hi.z + (fabsf(b.hi.z) * rel + absv));
     return r;
 }
+
+// ---- 4-wide collapse ---------------------------------------------------------------------------------
+// Wide node of binary node i: each child of i that is itself an internal node is replaced by its two
+// children.  Everything needed sits in the finished binary records: nodes[i] holds the (padded) boxes and
+// codes of i's children, nodes[c] those of c's children.
+RT_HD void wide_slot(float4* q, int k, float lox, float hix, float loy, float hiy, float loz, float hiz, int code) {
+    float* p;
+    p = (float*)&q[0]; p[k] = lox;  p = (float*)&q[1]; p[k] = hix;
+    p = (float*)&q[2]; p[k] = loy;  p = (float*)&q[3]; p[k] = hiy;
+    p = (float*)&q[4]; p[k] = loz;  p = (float*)&q[5]; p[k] = hiz;
+    p = (float*)&q[6]; p[k] = as_float((uint32_t)code);
+}
+RT_HD void build_wide_node(const float4* nodes, int i, float4* q /*8*/) {
+    const float big = RT_FLT_MAX;
+    for (int k = 0; k < 4; k++) wide_slot(q, k, big, big, big, big, big, big, RT_EMPTY_CODE);
+    q[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const float4* n = nodes + RT_NODE_FLOAT4S * (size_t)i;
+    float4 n0 = n[0], n1 = n[1], n2 = n[2], n3 = n[3];
+    int code[2] = {(int)as_uint(n3.x), (int)as_uint(n3.y)};
+    int k = 0;
+    for (int c = 0; c < 2; c++) {
+        if (code[c] == RT_EMPTY_CODE) continue;
+        if (code[c] < 0) {   // leaf child of i: keep it with the box i stores for it
+            if (c == 0) wide_slot(q, k++, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, code[c]);
+            else wide_slot(q, k++, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, code[c]);
+        } else {             // internal child: its two children move up
+            const float4* m = nodes + RT_NODE_FLOAT4S * (size_t)code[c];
+            float4 m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+            int g0 = (int)as_uint(m3.x), g1 = (int)as_uint(m3.y);
+            if (g0 != RT_EMPTY_CODE) wide_slot(q, k++, m0.x, m0.y, m0.z, m0.w, m2.x, m2.y, g0);
+            if (g1 != RT_EMPTY_CODE) wide_slot(q, k++, m1.x, m1.y, m1.z, m1.w, m2.z, m2.w, g1);
+        }
+    }
+}

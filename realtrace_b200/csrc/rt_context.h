@@ -114,7 +114,8 @@ struct rt_ctx {
     uint32_t n_tri = 0, n_bvh = 0, n_large = 0, n_fixed_analytic = 0;
     DevBuf<float> d_tri_v;
     DevBuf<uint32_t> d_tri_mat, d_tri_obj;
-    DevBuf<float4> d_tri_rgb, d_tris, d_nodes, d_box_lo, d_box_hi, d_materials, d_lights;
+    DevBuf<float4> d_tri_rgb, d_tris, d_nodes, d_nodes4, d_box_lo, d_box_hi, d_materials, d_lights;
+    int wide_bvh = 0;                      // traverse the 4-wide collapse of the tree (RT_WIDE_BVH)
     DevBuf<AnalyticPrim> d_analytic;
     DevBuf<uint64_t> d_keys[2];
     DevBuf<uint32_t> d_vals[2];
@@ -159,6 +160,7 @@ struct rt_ctx {
     cudaEvent_t ev[10] = {};               // 0-3,6,7 frame; 4,5 build; 8,9 refit
     bool refit_pending = false;
     int trace_blocks = 0, fused_blocks = 0, shadow_blocks = 0, shade_blocks = 0, path_blocks = 0;
+    int wide_blocks = 0, path_wide_blocks = 0;
     int path_kernel = 1;                   // bounce generations in one k_paths launch (RT_PATH_KERNEL=0: wave loop)
     int fuse_shadow = 1;                   // shadow rays ride in the lane that found the hit (RT_FUSE_SHADOW)
     int refill_primary_fused = 32;

@@ -20,6 +20,11 @@
 // n3 = (as_float(code0), as_float(code1), as_float(first), as_float(last))   [first,last] = sorted range
 // child code >= 0: internal node index; < 0: leaf, ~code = (first << 3) | (count - 1)
 #define RT_NODE_FLOAT4S 4
+// 4-wide node (128 B = 8 x float4), indexed by the binary node it was collapsed from (grandchildren become
+// children; only nodes at even depth are ever reached):
+//   q0 = lo.x[0..3]  q1 = hi.x[0..3]  q2 = lo.y  q3 = hi.y  q4 = lo.z  q5 = hi.z  q6 = child codes  q7 = unused
+// Empty slots carry the point box (+FLT_MAX)^3 and RT_EMPTY_CODE.
+#define RT_NODE4_FLOAT4S 8
 #define RT_LEAF_MAX 8
 #define RT_LEAF_SHIFT 3
 
@@ -58,6 +63,7 @@ RT_HD int rt_analytic_index(int code) { return -2 - code; }
 // ---- the scene as the kernels see it -------------------------------------------------------------
 struct SceneDev {
     const float4* nodes;          // RT_NODE_FLOAT4S per node; node 0 = root
+    const float4* nodes4;         // optional 4-wide view of the same tree (RT_NODE4_FLOAT4S per node), or nullptr
     const float4* tris;           // 3 per triangle, Morton order
     const float4* tri_rgb;        // 3 per ORIGINAL triangle, or nullptr
     const AnalyticPrim* analytic;

@@ -20,7 +20,7 @@
 namespace {
 
 struct EmulScene {
-    std::vector<float4> nodes, tris, tri_rgb, materials, lights;
+    std::vector<float4> nodes, nodes4, tris, tri_rgb, materials, lights;
     std::vector<AnalyticPrim> analytic;
     std::vector<uint64_t> keys;
     std::vector<uint32_t> order;
@@ -235,7 +235,13 @@ void build(const oracle_scene* in, int leaf_size, EmulScene& S) {
         sah_build(prims, 0, (int)nb, nodes, rb, pad_abs);
         S.nodes.swap(nodes);
     }
+    if (getenv("EMUL_WIDE") && !S.nodes.empty()) {      // 4-wide view (k_collapse4 of the GPU build)
+        size_t nn = S.nodes.size() / 4;
+        S.nodes4.resize(8 * nn);
+        for (size_t i = 0; i < nn; i++) build_wide_node(S.nodes.data(), (int)i, &S.nodes4[8 * i]);
+    }
     SceneDev& d = S.dev;
+    d.nodes4 = S.nodes4.empty() ? nullptr : S.nodes4.data();
     d.nodes = S.nodes.data(); d.tris = S.tris.data(); d.tri_rgb = S.tri_rgb.empty() ? nullptr : S.tri_rgb.data();
     d.analytic = S.analytic.data(); d.materials = S.materials.data(); d.lights = S.lights.data();
     d.n_bvh_tris = (int)nb; d.n_nodes = nb >= 2 ? (int)nb - 1 : (int)nb; d.n_analytic = (int)S.analytic.size();
