@@ -73,7 +73,7 @@ int rt_create(rt_ctx** out, int device) {
         env_int("RT_REFILL_QUEUE", 1, 32, c->refill_queue);
         env_int("RT_REFILL_SHADOW", 1, 32, c->refill_shadow);
         env_int("RT_BLOCKS_PER_SM", 1, 32, c->blocks_per_sm);
-        env_int("RT_WIDE_BVH", 0, 1, c->wide_bvh);
+        env_int("RT_WIDE_BVH", 0, 2, c->wide_bvh);
         env_int("RT_FUSE_SHADOW", 0, 1, c->fuse_shadow);
         env_int("RT_PATH_KERNEL", 0, 1, c->path_kernel);
         env_int("RT_TILE_FEEDBACK", 0, 1, c->tile_feedback);

@@ -1104,7 +1104,7 @@ RayQueue queue_of(rt_ctx* c, int b) {
 template <int MODE, bool FUSE>
 void launch_traverse(rt_ctx* c, const TravArgs& a, bool count) {
     int blocks = MODE == MODE_SHADOW ? c->shadow_blocks : (FUSE ? c->fused_blocks : c->trace_blocks);
-    if (FUSE && a.s.nodes4 != nullptr) {
+    if (FUSE && a.s.nodes4 != nullptr && c->wide_bvh == 2) {
         constexpr bool W = FUSE;   // only the fused kernels have a wide instantiation
         if (count) k_traverse<MODE, true, FUSE, W><<<c->wide_blocks, TRAV_TPB, 0, c->stream>>>(a);
         else k_traverse<MODE, false, FUSE, W><<<c->wide_blocks, TRAV_TPB, 0, c->stream>>>(a);

@@ -115,7 +115,7 @@ struct rt_ctx {
     DevBuf<float> d_tri_v;
     DevBuf<uint32_t> d_tri_mat, d_tri_obj;
     DevBuf<float4> d_tri_rgb, d_tris, d_nodes, d_nodes4, d_box_lo, d_box_hi, d_materials, d_lights;
-    int wide_bvh = 0;                      // traverse the 4-wide collapse of the tree (RT_WIDE_BVH)
+    int wide_bvh = 1;                      // 4-wide collapse of the tree: 0 off, 1 for k_paths (bounce paths), 2 everywhere (RT_WIDE_BVH)
     DevBuf<AnalyticPrim> d_analytic;
     DevBuf<uint64_t> d_keys[2];
     DevBuf<uint32_t> d_vals[2];

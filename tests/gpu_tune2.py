@@ -1,7 +1,7 @@
 """Development probe: loop style / leaf size / refill sweeps, full frame and a 1/8 share."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-configs = [dict(), dict(RT_WIDE_BVH=1)]
+configs = [dict(RT_WIDE_BVH=0), dict(RT_WIDE_BVH=1), dict(RT_WIDE_BVH=2)]
 code = f"""
 import sys, os; sys.path.insert(0, {ROOT!r})
 from realtrace_b200 import api, scenes
