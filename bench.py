@@ -339,7 +339,8 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     barrier()
     ctx.synchronize()                                   # raises if any timed frame flagged an error
     sampler.t_end = time.perf_counter()
-    ms = sum(a.elapsed_time(b) for a, b in evs)
+    per_step = np.array([a.elapsed_time(b) for a, b in evs])
+    ms = float(per_step.sum())
     rays_local = total_rays(stats[-1]) * steps          # static scene + camera: every frame casts the same rays
     if orbit:                                           # moving camera: count the rays of the timed frames exactly
         orbit_k[0] -= steps
@@ -408,7 +409,8 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     e2e_value = e_rays / e_s / 1e6
 
     sampler.stop()
-    out = {"value": value, "ms_per_step": ms / steps, "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
+    out = {"value": value, "ms_per_step": ms / steps,
+           "ms_per_step_p50": float(np.percentile(per_step, 50)), "ms_per_step_p99": float(np.percentile(per_step, 99)), "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
            "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "cam": cam_py, "depth": depth,
            "scene": scene, "build": bstats, "commit_s": commit_s, "last": stats[-1], "rays_per_frame": rays_total / steps}
 
@@ -461,7 +463,8 @@ def run_gpu_arm(args):
     cam, scene, depth = main["cam"], main["scene"], main["depth"]
 
     line = {"metric": METRIC, "value": main["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "ms_per_step_p50": main["ms_per_step_p50"],
+            "ms_per_step_p99": main["ms_per_step_p99"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "description": main["desc"], "width": cam.width, "height": cam.height,
                        "max_depth": depth, "triangles": int(len(scene.tri_v)), "lights": int(len(scene.lights)),
