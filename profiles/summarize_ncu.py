@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Turns gpurun_out ncu artefacts into the committed summaries under profiles/.
-usage: summarize_ncu.py <tag> <launches.csv> <prof.ncu-rep> [workload]"""
+usage: summarize_ncu.py <tag> <launches.csv> <prof.ncu-rep | -> [workload]   ("-": launch list only)"""
 import collections, csv, json, os, subprocess, sys
 tag, launches, rep = sys.argv[1:4]
 workload = sys.argv[4] if len(sys.argv) > 4 else "synth1m"
@@ -21,6 +21,8 @@ with open(os.path.join(here, f"{tag}_launches.md"), "w") as f:
     f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES.\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
         f.write(f"| `{k}` | {n} | {t:.1f} | {100 * t / tot:.1f}% |\n")
+if rep == "-":
+    print(open(os.path.join(here, f"{tag}_launches.md")).read()); sys.exit(0)
 # ---- full capture -> key metrics + DRAM traffic
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
