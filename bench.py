@@ -202,8 +202,9 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     commit_s = time.time() - t0
 
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    _, owned, tile_bytes = api.tile_layout(W, H, 0, 0, rank, world)
-    max_owned = max(api.tile_layout(W, H, 0, 0, r, world)[1] for r in range(world))
+    tile = tuple(args.tile) if world > 1 else (0, 0)     # N = 1 keeps the library default (64x32)
+    _, owned, tile_bytes = api.tile_layout(W, H, tile[0], tile[1], rank, world)
+    max_owned = max(api.tile_layout(W, H, tile[0], tile[1], r, world)[1] for r in range(world))
     frame = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev) if world == 1 else None
     frame_ptr = frame.data_ptr() if world == 1 else None
     tick = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -257,7 +258,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
                 frame = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
                 frame_ptr = frame.data_ptr()
 
-    push_params = api.Context._params(depth, rank=rank, world=world, flags=api.FLAG_PACKED_TILES)
+    push_params = api.Context._params(depth, tile=tile, rank=rank, world=world, flags=api.FLAG_PACKED_TILES)
     align_epoch = [0]
 
     def barrier():
@@ -295,25 +296,25 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
             frame_no[0] += 1
             if cursor_ptr:      # stealing: any rank may render any pool tile -> resolve straight into the shared frame
                 ctx.peer_sync(sync_ptr, rank, world, k, 0)
-                st = ctx.render_device(cam, depth, frame_ptr, rank=rank, world=world, want_stats=want_stats,
+                st = ctx.render_device(cam, depth, frame_ptr, tile=tile, rank=rank, world=world, want_stats=want_stats,
                                        steal=(args.steal_div, k, cursor_ptr))
                 ctx.peer_sync(sync_ptr, rank, world, k, 1)   # completion handshake: after it, rank 0 holds the frame
             elif want_stats:    # own tiles into a local packed buffer, then one kernel pushes them over NVLink
-                st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world,
+                st = ctx.render_device(cam, depth, packed.data_ptr(), tile=tile, rank=rank, world=world,
                                        flags=api.FLAG_PACKED_TILES, want_stats=True)
                 ctx.peer_sync(sync_ptr, rank, world, k, 0)
-                ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr)
+                ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr, tile=tile)
                 ctx.peer_sync(sync_ptr, rank, world, k, 1)
             else:               # the same four steps in one library call (one ctypes transition per frame)
                 st = None
                 ctx.render_push(cam, push_params, packed.data_ptr(), frame_ptr, sync_ptr, k)
             return st
-        st = ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES,
+        st = ctx.render_device(cam, depth, packed.data_ptr(), tile=tile, rank=rank, world=world, flags=api.FLAG_PACKED_TILES,
                                want_stats=want_stats)
         multigpu.gather_packed(packed, rank, world, gathered)
         if rank == 0:
             for r in range(world):
-                ctx.assemble_tiles(gathered[r].data_ptr(), r, world, W, H, frame_ptr)
+                ctx.assemble_tiles(gathered[r].data_ptr(), r, world, W, H, frame_ptr, tile=tile)
         return st
 
     # ---- value: device-resident frames, CUDA events around every step, L2 flushed between steps.
@@ -326,6 +327,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     sampler.t_begin = time.perf_counter()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     t_host0 = time.perf_counter()
+    launches0 = ctx.frame_launches()
     for k in range(steps):
         flush.fill_(k & 0xff)
         if world > 1:
@@ -341,11 +343,11 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     sampler.t_end = time.perf_counter()
     per_step = np.array([a.elapsed_time(b) for a, b in evs])
     ms = float(per_step.sum())
+    launches = ctx.frame_launches() - launches0          # kernels the library enqueued between the event pairs (NCCL's gather kernels not included)
     rays_local = total_rays(stats[-1]) * steps          # static scene + camera: every frame casts the same rays
     if orbit:                                           # moving camera: count the rays of the timed frames exactly
         orbit_k[0] -= steps
         rays_local = sum(total_rays(step_device(True)) for _ in range(steps))
-    launches = stats[-1]["kernel_launches"] * steps + ((world if rank == 0 else 0) * steps if assemble == "gather" else 0)
     if world > 1:
         t = torch.tensor([ms, float(rays_local), float(launches)], dtype=torch.float64, device=dev)
         tmax = t.clone()
@@ -367,10 +369,10 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
             flush.fill_(f_ & 0xff)
             align_ranks()
             ev[f_][0].record(stream)
-            ctx.render_device(cam, depth, packed.data_ptr(), rank=rank, world=world, flags=api.FLAG_PACKED_TILES, want_stats=False)
+            ctx.render_device(cam, depth, packed.data_ptr(), tile=tile, rank=rank, world=world, flags=api.FLAG_PACKED_TILES, want_stats=False)
             ev[f_][1].record(stream)
             ctx.peer_sync(sync_ptr, rank, world, k, 0)
-            ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr)
+            ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr, tile=tile)
             ev[f_][2].record(stream)
             ctx.peer_sync(sync_ptr, rank, world, k, 1)
             ev[f_][3].record(stream)
@@ -563,6 +565,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "gather"], help="N > 1 frame assembly")
+    ap.add_argument("--tile", type=int, nargs=2, default=[32, 16], metavar=("W", "H"),
+                    help="N > 1: screen tile size of the interleaved ownership (finer tiles = finer heavy-first order)")
     ap.add_argument("--steal-div", type=int, default=0,
                     help="N > 1 with p2p assembly: every k-th tile group forms the shared pool ranks steal from (0 = off)")
     args = ap.parse_args()

@@ -219,6 +219,12 @@ int rt_shade_rays(rt_ctx* ctx, const float* rays, uint32_t n, int32_t max_depth,
 int rt_bvh_download(rt_ctx* ctx, float* nodes, uint32_t* tri_order, uint64_t* keys, uint32_t* n_nodes,
                     uint32_t* n_bvh_triangles);
 
+/* Kernels enqueued so far by rt_render / rt_render_device / rt_render_push / rt_peer_sync / rt_assemble_tiles
+ * and the refit kernels of rt_scene_commit (a host-side running count, no synchronisation; rt_peer_barrier, the
+ * sort/hierarchy kernels of a full build and per-ray queries are not counted):
+ * the difference across a timed loop of asynchronous frames is its exact launch count.          */
+int rt_debug_frame_launches(rt_ctx* ctx, uint64_t* n_kernels);
+
 /* Debug timeline (RT_FLAG_WARP_TIMES): out receives {start_ns, end_ns} per warp of the last primary
  * traversal kernel; *n_warps in: capacity, out: warps written.                                   */
 int rt_debug_warp_times(rt_ctx* ctx, uint64_t* out, uint32_t* n_warps);

@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "rt_scene_set_planes", "rt_scene_set_cylinders", "rt_scene_set_materials", "rt_scene_set_lights",
     "rt_scene_set_environment", "rt_scene_commit", "rt_scene_update_vertices", "rt_scene_build_stats", "rt_render",
     "rt_render_device", "rt_tile_layout", "rt_assemble_tiles", "rt_trace_rays", "rt_shade_rays", "rt_bvh_download",
-    "rt_debug_sort_pairs", "rt_debug_warp_times", "rt_synchronize", "rt_peer_sync", "rt_peer_barrier", "rt_render_push", "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_download",
+    "rt_debug_sort_pairs", "rt_debug_warp_times", "rt_debug_frame_launches", "rt_synchronize", "rt_peer_sync", "rt_peer_barrier", "rt_render_push", "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_download",
 ]
 
 _lib = None
@@ -102,6 +102,7 @@ def load_library():
     lib.rt_bvh_download.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rt_debug_sort_pairs.argtypes = [vp, vp, vp, C.c_uint32]
     lib.rt_debug_warp_times.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
+    lib.rt_debug_frame_launches.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.rt_synchronize.argtypes = [vp]
     lib.rt_peer_sync.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_uint32, C.c_int32]
     lib.rt_peer_barrier.argtypes = [vp, vp, C.c_int32, C.c_uint32]
@@ -311,6 +312,12 @@ class Context:
         keys = np.zeros(nb.value, np.uint64)
         self._check(self.lib.rt_bvh_download(self.h, _ptr(nodes), _ptr(order), _ptr(keys), C.byref(nn), C.byref(nb)))
         return nodes, order, keys
+
+    def frame_launches(self):
+        """Running count of the kernels enqueued by render / render_device / render_push / peer_sync / assemble_tiles."""
+        n = C.c_uint64(0)
+        self._check(self.lib.rt_debug_frame_launches(self.h, C.byref(n)))
+        return n.value
 
     def warp_times(self, max_warps=1 << 16):
         """(n, 2) uint64 {start_ns, end_ns} per warp of the last primary traversal kernel (FLAG_WARP_TIMES)."""

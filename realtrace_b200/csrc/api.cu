@@ -75,6 +75,7 @@ int rt_create(rt_ctx** out, int device) {
         env_int("RT_BLOCKS_PER_SM", 1, 32, c->blocks_per_sm);
         env_int("RT_WIDE_BVH", 0, 2, c->wide_bvh);
         env_int("RT_FUSE_SHADOW", 0, 1, c->fuse_shadow);
+        env_int("RT_FUSE_SHADE", 0, 2, c->fuse_shade);
         env_int("RT_PATH_KERNEL", 0, 1, c->path_kernel);
         env_int("RT_TILE_FEEDBACK", 0, 1, c->tile_feedback);
         env_int("RT_REFILL_PRIMARY_FUSED", 1, 32, c->refill_primary_fused);
@@ -370,6 +371,19 @@ int rt_render_push(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p,
         need(packed_dev && frame_dev && sync_buf, "rt_render_push: NULL buffer");
         need((p->flags & RT_FLAG_PACKED_TILES) != 0 && p->world_size >= 1, "rt_render_push: needs RT_FLAG_PACKED_TILES and a world size");
         int world = p->world_size > 1 ? p->world_size : 1, rank = world > 1 ? p->rank : 0;
+        if (rt_frame_pushes_inline(ctx, p)) {
+            // bounce-free scene: one kernel traces, shades and sends every finished tile on its way over NVLink
+            rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 0);
+            ctx->push_frame = frame_dev;
+            try { rt_render_frame(ctx, cam, p, packed_dev, nullptr, nullptr); }
+            catch (...) { ctx->push_frame = nullptr; throw; }
+            ctx->push_frame = nullptr;
+            if (!ctx->pushed_inline)
+                rt_assemble(ctx, packed_dev, rank, world, cam->width, cam->height, p->tile_w > 0 ? p->tile_w : 64,
+                            p->tile_h > 0 ? p->tile_h : 32, frame_dev);
+            rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 1);
+            return;
+        }
         rt_render_frame(ctx, cam, p, packed_dev, nullptr, nullptr);
         rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 0);
         rt_assemble(ctx, packed_dev, rank, world, cam->width, cam->height, p->tile_w > 0 ? p->tile_w : 64,
@@ -438,6 +452,13 @@ int rt_bvh_download(rt_ctx* ctx, float* nodes, uint32_t* tri_order, uint64_t* ke
         if (tri_order && nb) RT_CUDA(cudaMemcpyAsync(tri_order, ctx->d_vals[ctx->sorted_buf].p, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (keys && nb) RT_CUDA(cudaMemcpyAsync(keys, ctx->d_keys[ctx->sorted_buf].p, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         RT_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int rt_debug_frame_launches(rt_ctx* ctx, uint64_t* n_kernels) {
+    return guarded(ctx, [&] {
+        need(n_kernels, "rt_debug_frame_launches: NULL argument");
+        *n_kernels = ctx->launch_total;
     });
 }
 

@@ -320,10 +320,12 @@ static void run_refit(rt_ctx* c) {
     if (n) {
         k_tri_records<<<blocks_for(n), TPB, 0, st>>>(c->d_tri_v.p, c->d_tri_mat.p, c->d_tri_obj.p, order, n, c->d_tris.p);
         RT_CUDA(cudaGetLastError());
+        c->launch_total++;
     }
     if (c->n_large) {
         k_emit_large<<<1, 32, 0, st>>>(c->d_tris.p, nb, c->n_large, c->d_analytic.p + c->n_fixed_analytic);
         RT_CUDA(cudaGetLastError());
+        c->launch_total++;
     }
     float pad_abs = c->scene_abs_max * 4.0e-6f;
     if (nb >= 2) {
@@ -332,9 +334,11 @@ static void run_refit(rt_ctx* c) {
                                                 c->d_node_parent.p, c->d_visit.p, c->d_box_lo.p, c->d_box_hi.p,
                                                 c->d_nodes.p, c->leaf_size, pad_abs);
         RT_CUDA(cudaGetLastError());
+        c->launch_total++;
     } else if (nb == 1) {
         k_single_leaf<<<1, 1, 0, st>>>(c->d_tri_v.p, order, c->d_nodes.p, pad_abs);
         RT_CUDA(cudaGetLastError());
+        c->launch_total++;
     }
     // the 4-wide view serves k_paths (latency-bound bounce paths; mode 1, only built when something reflects)
     // or every fused walk (mode 2)
@@ -343,6 +347,7 @@ static void run_refit(rt_ctx* c) {
         c->d_nodes4.reserve(RT_NODE4_FLOAT4S * (size_t)nn);
         k_collapse4<<<blocks_for((uint32_t)nn), TPB, 0, st>>>(c->d_nodes.p, nn, c->d_nodes4.p);
         RT_CUDA(cudaGetLastError());
+        c->launch_total++;
     }
 }
 

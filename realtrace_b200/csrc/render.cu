@@ -41,7 +41,7 @@ struct CamDev {
 };
 
 struct FrameDev {
-    int W, H, tile_w, tile_h, tiles_x, tile_pix;
+    int W, H, tile_w, tile_h, tiles_x, tile_pix, world;
     uint32_t n_tiles_owned, n_local_pix;   // the statically owned tiles and their pixel count
     const uint32_t* tile_ids;
     // dynamic tile stealing: blocks of 8x4 pixels of the pool tiles, claimed through steal_cursor
@@ -80,13 +80,14 @@ __device__ __forceinline__ uint32_t pixel_in_tile_to_local(const FrameDev& f, ui
     return tl * (uint32_t)f.tile_pix + (uint32_t)(b * 32 + l);
 }
 
-// Output byte offset of an owned pixel: frame layout (camera.cpp:48) or this rank's packed tiles.
-__device__ __forceinline__ size_t pixel_byte_offset(const FrameDev& f, uint32_t lp, int i, int j, int packed) {
+// Output byte offset of an owned pixel: frame layout (camera.cpp:48) or this rank's packed tiles.  The
+// packed slot of tile t is t / world (ascending owned order, what k_assemble expects) whatever order the
+// tiles are processed in.
+__device__ __forceinline__ size_t pixel_byte_offset(const FrameDev& f, int i, int j, int packed) {
     if (!packed) return ((size_t)i + (size_t)j * f.W) * 3;
-    uint32_t tl = lp / (uint32_t)f.tile_pix, p = lp % (uint32_t)f.tile_pix;
-    int bpr = f.tile_w >> 3, b = (int)(p >> 5), l = (int)(p & 31);
-    int x = (b % bpr) * 8 + (l & 7), y = (b / bpr) * 4 + (l >> 3);
-    return ((size_t)tl * f.tile_pix + (size_t)y * f.tile_w + x) * 3;
+    int tx = i / f.tile_w, ty = j / f.tile_h;
+    uint32_t slot = (uint32_t)(ty * f.tiles_x + tx) / (uint32_t)f.world;
+    return ((size_t)slot * f.tile_pix + (size_t)(j - ty * f.tile_h) * f.tile_w + (size_t)(i - tx * f.tile_w)) * 3;
 }
 
 // Camera::get_ray_direction (camera.cpp:33-44) + the Ray constructor's normalisation (ray.h:25-29),
@@ -172,7 +173,92 @@ struct TravArgs {
     unsigned long long* warp_times;   // debug (RT_FLAG_WARP_TIMES): per warp {start, end} in ns, 2 per warp
     uint8_t* direct_rgb;      // PRIMARY, scene without bounces: RGB8 output written in place of the accumulator
     int direct_packed;
+    RayQueue qout;            // SHADE: bounce rays of the shaded hits
+    WaveCounters* next;       // SHADE: their counter
+    int max_depth;            // SHADE
+    uint8_t* push_frame;      // SHADE + direct packed output: finished tiles are copied into this frame (rank 0's,
+                              // over NVLink) by the warp that completes them; nullptr = no in-kernel push
+    uint32_t* tile_done;      // ... per owned tile (position in tile_ids): finished 32-pixel batches this frame
+    int push_wide;            // ... rows can move as 16-byte chunks
 };
+
+// Appends the bounce rays of this warp's shaded hits to the next wave's queue: exclusive prefix over the
+// warp, one atomic per warp.  w is the throughput of the shaded ray.
+__device__ __forceinline__ void append_children(const RayQueue& qout, WaveCounters* next, uint32_t cap, const ShadeOut& out,
+                                                bool valid, f3 w, uint32_t pix, int lane, bool& qfull) {
+    uint32_t k = valid ? (uint32_t)out.n_children : 0u;
+    uint32_t incl = k;
+#pragma unroll
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o2);
+        if (lane >= o2) incl += t;
+    }
+    uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+        uint32_t qbase = 0;
+        if (lane == 31) qbase = atomicAdd(&next->n_rays, total);
+        qbase = __shfl_sync(0xffffffffu, qbase, 31);
+        uint32_t at = qbase + incl - k;
+        for (uint32_t c = 0; c < k; c++) {
+            if (at + c >= cap) { qfull = true; break; }
+            const ShadeChild& ch = out.child[c];
+            f3 cw = w * ch.w;
+            qout.o_pix[at + c] = make_float4(ch.o.x, ch.o.y, ch.o.z, __uint_as_float(pix));
+            qout.d_lvl[at + c] = make_float4(ch.d.x, ch.d.y, ch.d.z, __int_as_float(ch.level));
+            qout.w[at + c] = make_float4(cw.x, cw.y, cw.z, 0.0f);
+        }
+    }
+}
+
+// One warp copies a finished tile of this rank's packed buffer into the frame (camera.cpp:48 layout).  The
+// packed bytes were written by other warps: they are read past L1 (ld.cg) after the caller's fence.
+__device__ __forceinline__ void push_tile(const TravArgs& a, uint32_t tl, int lane) {
+    const FrameDev& f = a.f;
+    uint32_t tile = __ldg(f.tile_ids + tl), slot = tile / (uint32_t)f.world;
+    int tx = (int)(tile % (uint32_t)f.tiles_x), ty = (int)(tile / (uint32_t)f.tiles_x);
+    int rows = min(f.tile_h, f.H - ty * f.tile_h);
+    int row_bytes = min(f.tile_w, f.W - tx * f.tile_w) * 3;
+    const uint8_t* src = a.direct_rgb + (size_t)slot * f.tile_pix * 3;
+    uint8_t* dst = a.push_frame + ((size_t)tx * f.tile_w + (size_t)ty * f.tile_h * f.W) * 3;
+    if (a.push_wide) {
+        int cpr = (f.tile_w * 3) >> 4, n = cpr * rows;                 // 16-byte chunks per tile row / in the tile
+        for (int q = lane; q < n; q += 32) {
+            int y = q / cpr, cb = (q - y * cpr) << 4;
+            if (cb >= row_bytes) continue;
+            const uint8_t* s = src + (size_t)y * f.tile_w * 3 + cb;
+            uint8_t* d = dst + (size_t)y * f.W * 3 + cb;
+            if (cb + 16 <= row_bytes) *reinterpret_cast<uint4*>(d) = __ldcg(reinterpret_cast<const uint4*>(s));
+            else for (int k = 0; k < row_bytes - cb; k++) d[k] = __ldcg(s + k);
+        }
+    } else {
+        for (int y = 0; y < rows; y++)
+            for (int b = lane; b < row_bytes; b += 32)
+                dst[(size_t)y * f.W * 3 + b] = __ldcg(src + (size_t)y * f.tile_w * 3 + b);
+    }
+}
+
+// SHADE mode of k_traverse: the warp's batch is done, shade its pending primary hits together.
+// Returns true if the bounce-ray queue overflowed.
+__device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uint32_t pm, HitRec nh, uint32_t occl_mask,
+                                         f3 pd, int pi, int pj, uint32_t pix) {
+    const int lane = threadIdx.x & 31;
+    bool qfull = false;
+    ShadeOut out;
+    out.n_children = 0;
+    if (pending) {
+        const f3 bg = mk3(a.s.background[0], a.s.background[1], a.s.background[2]);
+        f3 po = mk3((float)a.cam.pos[0], (float)a.cam.pos[1], (float)a.cam.pos[2]);   // primary_ray's origin
+        uint32_t li = 0;
+        auto any_hit = [&](f3, f3) -> bool { bool o2 = ((occl_mask >> li) & 1u) != 0; li++; return o2; };
+        shade_hit(a.s, po, pd, 0, nh, a.max_depth, any_hit, out);
+        f3 contrib = out.local + out.bg_weight * bg;
+        if (a.direct_rgb) write_pixel_direct(a.direct_rgb, pixel_byte_offset(a.f, pi, pj, a.direct_packed), contrib);
+        else accumulate<true>(a.accum, pix, contrib);
+    }
+    append_children(a.qout, a.next, a.cap, out, pending, mk3(1, 1, 1), pix, lane, qfull);
+    if (lane == 0) atomicAdd(&a.wave->n_hits, (uint32_t)__popc(pm));
+    return qfull;
+}
 
 // FUSE (nearest-hit modes only): a lane whose ray hit something does not go idle — it turns into
 // the shadow ray(s) of that hit (one per light, same walk with early exit) and only then emits the
@@ -180,11 +266,20 @@ struct TravArgs {
 // derivation of the hit point, and lanes whose rays missed keep pulling new rays meanwhile.
 // WIDE: walk the 4-wide view of the tree (SceneDev::nodes4); a template parameter so that the binary walk
 // keeps its register budget (72 vs 96 registers with both compiled in).
-template <int MODE, bool COUNT, bool FUSE, bool WIDE = false>
-__global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ TravArgs a) {
+// SHADE (fused primary rays, whole-batch refill): the hit is not queued for k_shade either.  A lane keeps its
+// hit and occlusion bits until the warp's 32-pixel batch is done, then the warp shades all its hits together
+// (World::shade_ray, world.cpp:32-111, same shade_hit as k_shade), writes the pixels and queues the bounce
+// rays.  One kernel per primary wave: no hit queue traffic, no second launch, no second tail.
+#ifndef RT_SHADE_FUSED_MIN_BLOCKS
+#define RT_SHADE_FUSED_MIN_BLOCKS 7     // SHADE: hold the kernel to the traversal loop's 72 registers (the once-per-batch shading spills)
+#endif
+template <int MODE, bool COUNT, bool FUSE, bool WIDE = false, bool SHADE = false>
+__global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 0) k_traverse(const __grid_constant__ TravArgs a) {
     constexpr bool ANY = MODE == MODE_SHADOW;
     static_assert(!(FUSE && ANY), "FUSE applies to the nearest-hit modes");
     static_assert(!WIDE || FUSE, "the wide walk is instantiated for the fused kernels only");
+    static_assert(!SHADE || (FUSE && MODE == MODE_PRIMARY), "in-kernel shading is for the fused primary wave");
+    __shared__ float s_pdir[SHADE ? 3 * TRAV_TPB : 1];   // SHADE: primary direction of the lane's pending hit
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -220,6 +315,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
     nh.t = RT_FLT_MAX; nh.prim = RT_MISS; nh.beta = nh.gamma = 0.0f;
     f3 P = mk3(0, 0, 0);
     uint32_t occl_mask = 0;
+    bool pending = false, qfull = false;   // SHADE: this lane's hit waits for the end of the batch
     auto start_shadow = [&](int li) {
         f3 toL = mk3(__ldg(a.s.lights + 2 * li)) - P;
         f3 sd = normalize(toL);
@@ -231,24 +327,52 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
         traced_shadow++;
     };
 
+    // the warp has just finished a whole 32-pixel batch (all lanes idle, hits shaded)
+    auto finish_batch = [&]() {
+        if (batch_tile == 0xffffffffu) return;
+        // charge its duration to the tile
+        if (a.f.tile_cost && lane == 0) atomicMax(a.f.tile_cost + batch_tile, (uint32_t)((clock64() - batch_t0) >> 6));
+        if (SHADE && a.push_frame) {
+            // ... and count it; whoever completes a tile sends it on its way while the others keep tracing.
+            // The warp barrier + lane 0's RELEASE add order every lane's pixel stores (performed at L2) before
+            // the count.  No __threadfence anywhere here: it compiles to MEMBAR.SC + CCTL.IVALL, and throwing
+            // the SM's L1 — the BVH working set — away at every batch cost 10 % of the frame.  The warp that
+            // sees the last count reads the pixels straight from L2 (ld.cg in push_tile), behind the branch
+            // on the atomic's result.
+            __syncwarp();
+            uint32_t done = 0;
+            if (lane == 0) {
+                asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(done) : "l"(a.tile_done + batch_tile) : "memory");
+                done += 1u;
+            }
+            done = __shfl_sync(FULL, done, 0);
+            if (done == (uint32_t)a.f.tile_pix >> 5) push_tile(a, batch_tile, lane);
+        }
+        batch_tile = 0xffffffffu;
+    };
+
     for (;;) {
         // ---- refill idle lanes from the global cursor
         uint32_t need = __ballot_sync(FULL, !active);
         uint32_t my = 0;
         bool have = false;
-        if (MODE == MODE_PRIMARY && a.f.tile_cost && need == FULL && batch_tile != 0xffffffffu) {
-            // the warp has just finished a whole 32-pixel batch: charge its duration to the tile
-            if (lane == 0) atomicMax(a.f.tile_cost + batch_tile, (uint32_t)((clock64() - batch_t0) >> 6));
-            batch_tile = 0xffffffffu;
+        if (SHADE && need == FULL) {
+            uint32_t pm = __ballot_sync(FULL, pending);
+            if (pm) {
+                f3 pd = mk3(s_pdir[threadIdx.x], s_pdir[TRAV_TPB + threadIdx.x], s_pdir[2 * TRAV_TPB + threadIdx.x]);
+                if (shade_batch(a, pending, pm, nh, occl_mask, pd, pi, pj, pix)) qfull = true;
+                pending = false;
+            }
         }
-        if (!exhausted && (__popc(need) >= a.refill_min || need == FULL)) {
+        if (MODE == MODE_PRIMARY && need == FULL) finish_batch();
+        if (!exhausted && ((!SHADE && __popc(need) >= a.refill_min) || need == FULL)) {
             int cnt = __popc(need), leader = __ffs(need) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(cursor, (uint32_t)cnt);
             base = __shfl_sync(FULL, base, leader);
-            if (MODE == MODE_PRIMARY && a.f.tile_cost && need == FULL && base < n) {
+            if (MODE == MODE_PRIMARY && (a.f.tile_cost || (SHADE && a.push_frame)) && need == FULL && base < n) {
                 batch_tile = base / (uint32_t)a.f.tile_pix;
-                batch_t0 = clock64();
+                if (a.f.tile_cost) batch_t0 = clock64();
             }
             if (base + (uint32_t)cnt >= n) exhausted = true;
             my = base + __popc(need & lt);
@@ -336,7 +460,10 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
             }
         }
         if (!__any_sync(FULL, active)) {
-            if (exhausted && steal_done) break;
+            if (exhausted && steal_done) {
+                if (MODE == MODE_PRIMARY) finish_batch();      // a last batch that lies outside the frame
+                break;
+            }
             continue;
         }
         // ---- traversal of the lanes that own a ray
@@ -412,13 +539,16 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
                 }
                 if (!found) {
                     if (MODE == MODE_PRIMARY && a.direct_rgb)
-                        write_pixel_direct(a.direct_rgb, pixel_byte_offset(a.f, pix, pi, pj, a.direct_packed), w * bg);
+                        write_pixel_direct(a.direct_rgb, pixel_byte_offset(a.f, pi, pj, a.direct_packed), w * bg);
                     else
                         accumulate<MODE == MODE_PRIMARY>(a.accum, pix, w * bg);      // world.cpp:110
                 } else {
                     nh = hit;
                     occl_mask = 0;
                     emit = true;
+                    if (SHADE) {
+                        s_pdir[threadIdx.x] = r.d.x; s_pdir[TRAV_TPB + threadIdx.x] = r.d.y; s_pdir[2 * TRAV_TPB + threadIdx.x] = r.d.z;
+                    }
                     if (FUSE && a.s.n_lights > 0) {
                         // dielectric hits discard their local colour (world.cpp:77-100): no shadow query
                         uint32_t mat = hit.prim >= 0 ? __float_as_uint(__ldg(a.s.tris + 3 * (size_t)hit.prim + 1).w)
@@ -436,7 +566,9 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
             }
             if (fin) active = false;
         }
-        if (!ANY) {
+        if (SHADE) {
+            pending |= emit;
+        } else if (!ANY) {
             // hits: one atomic per warp reserves a run of the hit queue
             uint32_t mask = __ballot_sync(FULL, emit);
             if (mask) {
@@ -474,6 +606,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_traverse(const __grid_constant__ T
         }
     }
     if (__any_sync(FULL, overflow) && lane == 0) atomicOr(a.sticky, 2u);
+    if (SHADE && __any_sync(FULL, qfull) && lane == 0) atomicOr(a.sticky, 1u);
     if (a.warp_times && lane == 0) {
         unsigned long long t_end;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -547,32 +680,10 @@ __global__ void __launch_bounds__(SHADE_TPB, RT_SHADE_MIN_BLOCKS) k_shade(const 
             };
             shade_hit(a.s, o, d, level, h, a.max_depth, any_hit, out);
             f3 contrib = w * (out.local + out.bg_weight * bg);
-            if (PRIMARY && a.direct_rgb) write_pixel_direct(a.direct_rgb, pixel_byte_offset(a.f, pix, pi, pj, a.direct_packed), contrib);
+            if (PRIMARY && a.direct_rgb) write_pixel_direct(a.direct_rgb, pixel_byte_offset(a.f, pi, pj, a.direct_packed), contrib);
             else accumulate<PRIMARY>(a.accum, pix, contrib);
         }
-        // append children: exclusive prefix over the warp, one atomic
-        uint32_t k = valid ? (uint32_t)out.n_children : 0u;
-        uint32_t incl = k;
-#pragma unroll
-        for (int o2 = 1; o2 < 32; o2 <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o2);
-            if (lane >= o2) incl += t;
-        }
-        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-            uint32_t qbase = 0;
-            if (lane == 31) qbase = atomicAdd(&a.next->n_rays, total);
-            qbase = __shfl_sync(0xffffffffu, qbase, 31);
-            uint32_t at = qbase + incl - k;
-            for (uint32_t c = 0; c < k; c++) {
-                if (at + c >= a.cap) { qfull = true; break; }
-                const ShadeChild& ch = out.child[c];
-                f3 cw = w * ch.w;
-                a.qout.o_pix[at + c] = make_float4(ch.o.x, ch.o.y, ch.o.z, __uint_as_float(pix));
-                a.qout.d_lvl[at + c] = make_float4(ch.d.x, ch.d.y, ch.d.z, __int_as_float(ch.level));
-                a.qout.w[at + c] = make_float4(cw.x, cw.y, cw.z, 0.0f);
-            }
-        }
+        append_children(a.qout, a.next, a.cap, out, valid, w, pix, lane, qfull);
     }
     if (__any_sync(0xffffffffu, qfull) && lane == 0) atomicOr(a.sticky, 1u);
 }
@@ -866,8 +977,7 @@ __global__ void __launch_bounds__(256) k_resolve(FrameDev f, const long long* __
         px[3 * k + 1] = in ? to_u8(a[1]) : 0u;
         px[3 * k + 2] = in ? to_u8(a[2]) : 0u;
     }
-    size_t byte0 = packed ? ((size_t)tl * f.tile_pix + (size_t)y * f.tile_w + x0) * 3
-                          : ((size_t)i0 + (size_t)j * f.W) * 3;
+    size_t byte0 = pixel_byte_offset(f, i0, j, packed);
     if (npx == 4 && (byte0 & 3) == 0) {
         uint32_t* o32 = reinterpret_cast<uint32_t*>(out + byte0);
         o32[0] = px[0] | px[1] << 8 | px[2] << 16 | px[3] << 24;
@@ -911,9 +1021,10 @@ __global__ void __launch_bounds__(256) k_assemble(const uint8_t* __restrict__ pa
 
 // ---- frame-completion handshake between ranks through peer memory (NVLink), no collective library:
 // sync[0..63] arrival counters (slot = frame % 64), sync[64] = number of frames rank 0 has consumed.
-//   phase 0 (before a rank writes frame k into rank 0's buffer): ranks > 0 wait until consumed >= k
-//   phase 1 (after the write): ranks > 0 add 1 to slot k; rank 0 waits for world-1 arrivals, clears the
-//   slot that comes into use 32 frames later and publishes consumed = k + 1
+//   phase 0 (before a rank writes frame k into rank 0's buffer): rank 0 publishes consumed = k — everything
+//   it enqueued on its stream for frame k-1 (a download, say) has finished by then; ranks > 0 wait for it
+//   phase 1 (after the write): ranks > 0 add 1 to slot k; rank 0 waits for world-1 arrivals and clears the
+//   slot that comes into use 32 frames later
 // The spinning kernels are single threads on DIFFERENT GPUs and give up after ~2 s (sticky bit 4).
 __global__ void k_peer_wait_consumed(volatile uint32_t* sync, uint32_t frame, uint32_t* sticky) {
     long long t0 = clock64();
@@ -935,7 +1046,10 @@ __global__ void k_peer_wait_all(volatile uint32_t* sync, uint32_t frame, uint32_
     }
     __threadfence_system();
     sync[(frame + 32u) % 64u] = 0u;
-    sync[64] = frame + 1u;
+    __threadfence_system();
+}
+__global__ void k_peer_publish_consumed(volatile uint32_t* sync, uint32_t frame) {
+    if (sync[64] < frame) sync[64] = frame;
     __threadfence_system();
 }
 
@@ -1040,6 +1154,7 @@ FrameDev frame_dev(rt_ctx* c, const rt_render_params* p) {
     FrameDev f;
     f.W = L.width; f.H = L.height; f.tile_w = L.tile_w; f.tile_h = L.tile_h; f.tiles_x = L.tiles_x;
     f.tile_pix = L.tile_w * L.tile_h;
+    f.world = L.world;
     f.n_tiles_owned = L.n_tiles_owned;
     f.n_local_pix = L.n_tiles_owned * (uint32_t)f.tile_pix;
     f.tile_ids = c->d_tile_ids.p;
@@ -1048,7 +1163,7 @@ FrameDev frame_dev(rt_ctx* c, const rt_render_params* p) {
     f.stolen_map = c->d_stolen_map.p;
     f.tile_cost = nullptr;
     if (c->tile_feedback && L.n_tiles_owned > 1 && L.n_tiles_owned <= RT_SORT_TILES_MAX && c->refill_primary == 32 &&
-        (!c->fuse_shadow || c->refill_primary_fused == 32) && !(p->flags & RT_FLAG_PACKED_TILES)) {
+        (!c->fuse_shadow || c->refill_primary_fused == 32)) {
         c->d_tile_cost.reserve(L.n_tiles_owned);
         if (!c->tile_cost_valid) {
             RT_CUDA(cudaMemsetAsync(c->d_tile_cost.p, 0, L.n_tiles_owned * sizeof(uint32_t), c->stream));
@@ -1101,16 +1216,23 @@ RayQueue queue_of(rt_ctx* c, int b) {
     return q;
 }
 
-template <int MODE, bool FUSE>
+// Does the primary wave shade its hits inside the traversal kernel?  (RT_FUSE_SHADE: 0 never, 1 when the
+// kernel also pushes finished tiles into a remote frame, 2 always.)
+bool wave0_shades_inline(const rt_ctx* c, bool pushing) {
+    return c->fuse_shadow && c->scene.n_lights > 0 && c->scene.n_lights <= 8 && c->refill_primary_fused == 32 &&
+           (c->fuse_shade == 2 || (c->fuse_shade == 1 && pushing));
+}
+template <int MODE, bool FUSE, bool SHADE = false>
 void launch_traverse(rt_ctx* c, const TravArgs& a, bool count) {
-    int blocks = MODE == MODE_SHADOW ? c->shadow_blocks : (FUSE ? c->fused_blocks : c->trace_blocks);
+    int blocks = MODE == MODE_SHADOW ? c->shadow_blocks : (FUSE ? (SHADE ? c->fused_shade_blocks : c->fused_blocks) : c->trace_blocks);
     if (FUSE && a.s.nodes4 != nullptr && c->wide_bvh == 2) {
         constexpr bool W = FUSE;   // only the fused kernels have a wide instantiation
-        if (count) k_traverse<MODE, true, FUSE, W><<<c->wide_blocks, TRAV_TPB, 0, c->stream>>>(a);
-        else k_traverse<MODE, false, FUSE, W><<<c->wide_blocks, TRAV_TPB, 0, c->stream>>>(a);
+        blocks = SHADE ? c->wide_shade_blocks : c->wide_blocks;
+        if (count) k_traverse<MODE, true, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+        else k_traverse<MODE, false, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
     } else {
-        if (count) k_traverse<MODE, true, FUSE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
-        else k_traverse<MODE, false, FUSE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+        if (count) k_traverse<MODE, true, FUSE, false, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+        else k_traverse<MODE, false, FUSE, false, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
     }
     RT_CUDA(cudaGetLastError());
 }
@@ -1131,6 +1253,19 @@ uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot
     ta.refill_min = PRIMARY ? c->refill_primary : c->refill_queue;
     ta.loop_style = PRIMARY ? c->loop_primary : c->loop_queue;
     const bool fuse = shade && c->fuse_shadow && c->scene.n_lights > 0 && c->scene.n_lights <= 8;
+    // primary wave, whole-batch refill: shading happens inside the traversal kernel too
+    const bool fuse_shade = PRIMARY && fuse && wave0_shades_inline(c, ta.push_frame != nullptr);
+    if (fuse_shade) {
+        ta.refill_min = 32;
+        ta.qout = queue_of(c, cur ^ 1);
+        ta.next = c->d_waves.p + slot_out;
+        ta.max_depth = sa.max_depth;
+        launch_traverse<MODE_PRIMARY, true, PRIMARY>(c, ta, count);     // (PRIMARY is true here)
+        launches++;
+        if (after_trace) RT_CUDA(cudaEventRecord(after_trace, c->stream));
+        if (after_shadow) RT_CUDA(cudaEventRecord(after_shadow, c->stream));
+        return launches;
+    }
     if (fuse) {
         ta.occl = c->d_occl.p;
         ta.refill_min = PRIMARY ? c->refill_primary_fused : c->refill_queue;
@@ -1228,6 +1363,15 @@ WaveResult run_bounce_waves(rt_ctx* c, const TravArgs& ta, const ShadeArgs& sa, 
 
 }  // namespace
 
+// rt_render_push: can the frame's only kernel push its tiles itself?  Bounce-free scenes only: their pixels are
+// final the moment the batch is shaded.
+bool rt_frame_pushes_inline(const rt_ctx* c, const rt_render_params* p) {
+    const bool bounce = c->has_reflective && p->max_depth >= 1;
+    return !bounce && (p->flags & RT_FLAG_PACKED_TILES) && !(p->world_size > 1 && p->steal_pool_div > 0) &&
+           wave0_shades_inline(c, true);
+}
+
+
 // Waits for the context's stream and turns the sticky device error word into an exception.
 void rt_sync_and_check(rt_ctx* c) {
     cudaStream_t st = c->stream;
@@ -1254,12 +1398,15 @@ void rt_render_init(rt_ctx* c) {
     c->path_wide_blocks = persistent_blocks(k_paths<false, true>, TRAV_TPB, c->sm_count);
     c->wide_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false, true, true>, TRAV_TPB, c->sm_count),
                         persistent_blocks(k_traverse<MODE_QUEUE, false, true, true>, TRAV_TPB, c->sm_count));
+    c->fused_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, false, true>, TRAV_TPB, c->sm_count);
+    c->wide_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, true, true>, TRAV_TPB, c->sm_count);
     c->shade_blocks = lo(persistent_blocks(k_shade<true>, SHADE_TPB, c->sm_count),
                          persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
     if (c->blocks_per_sm > 0) {   // RT_BLOCKS_PER_SM: cap the persistent grids (tuning)
         int cap = c->blocks_per_sm * c->sm_count;
         c->trace_blocks = lo(c->trace_blocks, cap);
         c->fused_blocks = lo(c->fused_blocks, cap);
+        c->fused_shade_blocks = lo(c->fused_shade_blocks, cap);
         c->shadow_blocks = lo(c->shadow_blocks, cap);
         c->path_blocks = lo(c->path_blocks, cap);
     }
@@ -1303,7 +1450,9 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     sa.max_depth = p->max_depth;
 
     if (p->flags & RT_FLAG_WARP_TIMES) {
-        c->d_warp_times.reserve(2 * (size_t)(c->trace_blocks > c->fused_blocks ? c->trace_blocks : c->fused_blocks) * (TRAV_TPB / 32));
+        int mb = c->trace_blocks;
+        for (int b : {c->fused_blocks, c->fused_shade_blocks, c->wide_blocks, c->wide_shade_blocks}) mb = b > mb ? b : mb;
+        c->d_warp_times.reserve(2 * (size_t)mb * (TRAV_TPB / 32));
         ta.warp_times = c->d_warp_times.p;
     }
     // no bounces => one contribution per pixel => RGB8 straight from the wave-0 kernels (stolen blocks keep
@@ -1312,6 +1461,16 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     if (direct) {
         ta.direct_rgb = sa.direct_rgb = (uint8_t*)rgb_dev;
         ta.direct_packed = sa.direct_packed = (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0;
+    }
+    c->pushed_inline = false;
+    if (c->push_frame && direct && ta.direct_packed && rt_frame_pushes_inline(c, p)) {
+        c->d_tile_done.reserve(f.n_tiles_owned ? f.n_tiles_owned : 1);
+        RT_CUDA(cudaMemsetAsync(c->d_tile_done.p, 0, (f.n_tiles_owned ? f.n_tiles_owned : 1) * sizeof(uint32_t), st));
+        ta.push_frame = (uint8_t*)c->push_frame;
+        ta.tile_done = c->d_tile_done.p;
+        ta.push_wide = ((f.W * 3) % 16 == 0 && (f.tile_w * 3) % 16 == 0 && ((uintptr_t)rgb_dev & 15) == 0 &&
+                        ((uintptr_t)c->push_frame & 15) == 0) ? 1 : 0;
+        c->pushed_inline = true;
     }
     uint32_t launches = 0;
     const bool has_work = f.n_local_pix > 0 || f.steal_cursor != nullptr;
@@ -1352,6 +1511,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         launches++;
     }
     c->frames_in_layout++;
+    c->launch_total += launches;
     RT_CUDA(cudaEventRecord(c->ev[7], st));
 
     // Without a stats request the frame is left in flight: nothing below synchronises, errors stay in
@@ -1463,7 +1623,10 @@ void rt_peer_sync_enqueue(rt_ctx* c, void* sync_buf, int rank, int world, uint32
     if (world <= 1) return;
     if (phase == 0) {
         if (rank != 0) k_peer_wait_consumed<<<1, 1, 0, st>>>(sync, frame_index, c->d_sticky.p);
+        else k_peer_publish_consumed<<<1, 1, 0, st>>>(sync, frame_index);
+        c->launch_total++;
     } else {
+        c->launch_total++;
         if (rank != 0) k_peer_arrive<<<1, 1, 0, st>>>(sync, frame_index);
         else k_peer_wait_all<<<1, 1, 0, st>>>(sync, frame_index, (uint32_t)(world - 1), c->d_sticky.p);
     }
@@ -1492,5 +1655,6 @@ void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int wid
         k_assemble<<<(quads + 255) / 256, 256, 0, c->stream>>>((const uint8_t*)packed, (uint8_t*)frame, width, height,
                                                                tile_w, tile_h, tiles_x, total, src_rank, world);
     }
+    c->launch_total++;
     RT_CUDA(cudaGetLastError());
 }

@@ -160,7 +160,13 @@ struct rt_ctx {
     cudaEvent_t ev[10] = {};               // 0-3,6,7 frame; 4,5 build; 8,9 refit
     bool refit_pending = false;
     int trace_blocks = 0, fused_blocks = 0, shadow_blocks = 0, shade_blocks = 0, path_blocks = 0;
-    int wide_blocks = 0, path_wide_blocks = 0;
+    int wide_blocks = 0, path_wide_blocks = 0, fused_shade_blocks = 0, wide_shade_blocks = 0;
+    int fuse_shade = 1;                    // primary hits shaded inside the fused traversal kernel (RT_FUSE_SHADE): 0 never,
+                                           // 1 when that kernel also pushes finished tiles to a remote frame, 2 always
+    void* push_frame = nullptr;            // rt_render_push: frame the primary kernel may push finished tiles into
+    bool pushed_inline = false;            // ... and whether the last frame did
+    uint64_t launch_total = 0;             // kernels enqueued by frame-level calls since rt_create (rt_debug_frame_launches)
+    DevBuf<uint32_t> d_tile_done;
     int path_kernel = 1;                   // bounce generations in one k_paths launch (RT_PATH_KERNEL=0: wave loop)
     int fuse_shadow = 1;                   // shadow rays ride in the lane that found the hit (RT_FUSE_SHADOW)
     int refill_primary_fused = 32;
@@ -182,5 +188,6 @@ void rt_render_init(rt_ctx* c);                                     // render.cu
 void rt_sync_and_check(rt_ctx* c);                                  // render.cu
 void rt_peer_barrier_enqueue(rt_ctx* c, void* sync_buf, int world, uint32_t epoch);   // render.cu
 void rt_peer_sync_enqueue(rt_ctx* c, void* sync_buf, int rank, int world, uint32_t frame_index, int phase);   // render.cu
+bool rt_frame_pushes_inline(const rt_ctx* c, const rt_render_params* p);   // render.cu
 void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int width, int height, int tile_w,
                  int tile_h, void* frame);                          // render.cu

@@ -7,9 +7,14 @@ from realtrace_b200 import api, scenes
 scene, cam, depth, desc = scenes.workload("synth1m")
 ctx = api.Context(0); ctx.set_scene(scene); ctx.commit()
 buf = torch.zeros(cam.width * cam.height * 3, dtype=torch.uint8, device="cuda")
-for world in (1, 8):
-    for rep in range(3):
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+ctx.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+for world, cold in ((1, 0), (8, 0), (8, 1), (16, 0), (16, 1)):
+    for rep in range(4):
+        if cold:
+            flush.fill_(rep)
         st = ctx.render_device(cam, depth, buf.data_ptr(), rank=0, world=world, flags=api.FLAG_WARP_TIMES)
+    print(f"--- world {world} cold {cold}: ms_device {st['ms_device']:.4f} trace {st['ms_trace']:.4f} shade {st['ms_shade']:.4f} resolve {st['ms_resolve']:.4f}")
     t = ctx.warp_times().astype(np.int64)
     t = t[t[:, 1] > 0]
     t0 = t[:, 0].min()

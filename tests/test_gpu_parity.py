@@ -175,6 +175,31 @@ def test_tile_sharding_is_bit_identical(world):
     assert np.array_equal(out, full)
 
 
+@pytest.mark.parametrize("name", ["blubmixed_d5", "synth_small_d1"])
+def test_packed_tiles_keep_their_slots_when_the_tile_order_changes(name):
+    """The heavy-tiles-first feedback re-sorts a rank's tile list after the first frames; the packed slot of a
+    tile (t / world) must not move with it.  Frames 1..5 of every logical rank assemble to the single-rank
+    frame (bounce scene: accumulator + k_resolve path; bounce-free scene: direct RGB8 stores)."""
+    import torch
+    scene, cam, depth, _ = build_case(name)
+    cam.width, cam.height = 712, 404          # 12 x 13 tiles, ragged right and bottom edges
+    world = 3
+    ctx = make_ctx(scene)
+    full, _, _, _ = ctx.render(cam, depth)
+    for frame_no in range(5):
+        frame = torch.zeros(cam.height * cam.width * 3, dtype=torch.uint8, device="cuda")
+        for r in range(world):
+            _, owned, tb = api.tile_layout(cam.width, cam.height, 0, 0, r, world)
+            packed = torch.zeros(max(owned * tb, 1), dtype=torch.uint8, device="cuda")
+            # the layout (and with it the learned order) is per context: give every logical rank its own frames
+            for _ in range(frame_no + 1):
+                ctx.render_device(cam, depth, packed.data_ptr(), rank=r, world=world, flags=api.FLAG_PACKED_TILES)
+            ctx.assemble_tiles(packed.data_ptr(), r, world, cam.width, cam.height, frame.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(frame.cpu().numpy().reshape(cam.height, cam.width, 3), full), frame_no
+    ctx.close()
+
+
 def test_full_size_property_checks():
     """Config-2 size (1920x1080, 2 lights, depth 3): size-independent properties — every ray kind is
     counted, rendering twice is bit-identical, brute force over the same rays gives the same frame on
@@ -241,7 +266,8 @@ def test_dynamic_tile_stealing_is_bit_identical(world, pool_div):
 def test_peer_handshake_and_tile_push_logical_ranks():
     """bench.py's N > 1 frame loop with logical ranks on one GPU and one stream: each rank renders its tiles
     into a local packed buffer (direct RGB8), pushes them into the shared frame and goes through the
-    peer-memory handshake.  Ranks 1..N-1 are enqueued before rank 0, so no kernel ever has to spin."""
+    peer-memory handshake.  Rank 0 opens the frame (phase 0 publishes "earlier frames consumed"), ranks 1..N-1
+    are enqueued before rank 0's completion wait, so no kernel ever has to spin."""
     import torch
     scene, cam, depth, _ = build_case("synth_small_d1")      # no bounces: direct RGB8 path
     cam.width, cam.height = 328, 200
@@ -252,6 +278,7 @@ def test_peer_handshake_and_tile_push_logical_ranks():
     sync_ptr, _ = ctx.shared_buffer_create(1024)
     _, _, tb = api.tile_layout(cam.width, cam.height)
     for k in range(3):
+        ctx.peer_sync(sync_ptr, 0, world, k, 0)
         for r in list(range(1, world)) + [0]:
             _, owned, _ = api.tile_layout(cam.width, cam.height, 0, 0, r, world)
             packed = torch.zeros(max(owned * tb, 1), dtype=torch.uint8, device="cuda")
@@ -267,7 +294,45 @@ def test_peer_handshake_and_tile_push_logical_ranks():
     sync = np.zeros(256, np.uint32)
     ctx.download(sync_ptr, sync)
     ctx.close()
-    assert sync[64] == 3                                      # three frames consumed
+    assert sync[64] == 2                                      # rank 0 opened frame 2: frames 0 and 1 consumed
+
+
+@pytest.mark.parametrize("name,tile", [("synth_small_d1", (0, 0)), ("synth_small_d1", (32, 16)), ("synth_small_d1", (8, 4)),
+                                       ("blubmixed_d5", (0, 0))])
+def test_render_push_one_call_per_rank(name, tile):
+    """rt_render_push with logical ranks on one GPU.  Bounce-free scene: ONE kernel traces, shades and copies
+    every finished tile into the shared frame (the warp that completes a tile pushes it); scene with bounces:
+    render + separate push.  One context per logical rank (all on ONE stream, enqueued in an order in which no
+    handshake kernel has to wait), five frames, so every rank's heavy-tiles-first re-sort happens in between;
+    8x4 tiles make every batch a tile of its own and leave 24-byte rows to the byte path."""
+    import torch
+    scene, cam, depth, _ = build_case(name)
+    cam.width, cam.height = 328, 203
+    world = 3
+    ctx = make_ctx(scene)
+    full = ctx.render(cam, depth)[0]
+    ctxs = [ctx] + [make_ctx(scene) for _ in range(world - 1)]
+    for c in ctxs:
+        c.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+    frame = torch.zeros(cam.width * cam.height * 3, dtype=torch.uint8, device="cuda")
+    frame_ptr = frame.data_ptr()
+    sync_ptr, _ = ctx.shared_buffer_create(1024)
+    cs = api.camera_struct(cam)
+    packed = []
+    for r in range(world):
+        _, owned, tb = api.tile_layout(cam.width, cam.height, tile[0], tile[1], r, world)
+        packed.append(torch.zeros(max(owned * tb, 1), dtype=torch.uint8, device="cuda"))
+    for k in range(5):
+        frame.fill_(0x5a)                                     # a tile that is not pushed shows
+        ctx.peer_sync(sync_ptr, 0, world, k, 0)
+        for r in list(range(1, world)) + [0]:
+            params = api.Context._params(depth, tile=tile, rank=r, world=world, flags=api.FLAG_PACKED_TILES)
+            ctxs[r].render_push(cs, params, packed[r].data_ptr(), frame_ptr, sync_ptr, k)
+        for c in ctxs:
+            c.synchronize()                                   # raises on a handshake time-out / queue overflow
+        assert np.array_equal(frame.cpu().numpy().reshape(cam.height, cam.width, 3), full), k
+    for c in ctxs:
+        c.close()
 
 
 @pytest.mark.parametrize("name,col_step", [("synth1m", 240), ("blub4k", 120)])
