@@ -202,7 +202,11 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     commit_s = time.time() - t0
 
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    tile = tuple(args.tile) if world > 1 else (0, 0)     # N = 1 keeps the library default (64x32)
+    # tile size of the interleaved ownership: the library default (64x32) up to 2 GPUs; from 4 GPUs on 32x16, whose
+    # finer heavy-tiles-first order shortens the tail of the primary kernel (profiles/r1_tuning.md section 13)
+    tile = (0, 0)
+    if world > 1:
+        tile = tuple(args.tile) if args.tile[0] > 0 else ((32, 16) if world >= 4 else (64, 32))
     _, owned, tile_bytes = api.tile_layout(W, H, tile[0], tile[1], rank, world)
     max_owned = max(api.tile_layout(W, H, tile[0], tile[1], r, world)[1] for r in range(world))
     frame = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev) if world == 1 else None
@@ -413,7 +417,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     sampler.stop()
     out = {"value": value, "ms_per_step": ms / steps,
            "ms_per_step_p50": float(np.percentile(per_step, 50)), "ms_per_step_p99": float(np.percentile(per_step, 99)), "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
-           "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "cam": cam_py, "depth": depth,
+           "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "tile": (tile[0] or 64, tile[1] or 32), "cam": cam_py, "depth": depth,
            "scene": scene, "build": bstats, "commit_s": commit_s, "last": stats[-1], "rays_per_frame": rays_total / steps}
 
     # ---- roofline of the dominant kernel + work counts (single GPU, rank 0)
@@ -471,8 +475,9 @@ def run_gpu_arm(args):
             "config": {"workload": args.workload, "description": main["desc"], "width": cam.width, "height": cam.height,
                        "max_depth": depth, "triangles": int(len(scene.tri_v)), "lights": int(len(scene.lights)),
                        "rays_per_frame": main["rays_per_frame"],
-                       "parallelism": (f"{world} GPUs, interleaved 64x32 tiles, scene replicated, frame assembly: "
-                                       + {"p2p": "every rank pushes its tiles into rank 0's frame over NVLink (CUDA IPC peer stores) + "
+                       "parallelism": (f"{world} GPUs, interleaved {main['tile'][0]}x{main['tile'][1]} tiles, scene replicated, frame assembly: "
+                                       + {"p2p": "every rank writes its pixels into rank 0's frame over NVLink (CUDA IPC peer stores: from "
+                                                 "inside the one trace+shade kernel on bounce-free scenes, else a push kernel per rank) + "
                                                  "flag handshake in peer memory (no collective)"
                                                  + (f", dynamic tile stealing (1/{args.steal_div} of the tile groups pooled)" if args.steal_div > 0 else ""),
                                           "gather": "packed tiles + NCCL gather + scatter kernel"}[main["assemble"]])
@@ -565,8 +570,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "gather"], help="N > 1 frame assembly")
-    ap.add_argument("--tile", type=int, nargs=2, default=[32, 16], metavar=("W", "H"),
-                    help="N > 1: screen tile size of the interleaved ownership (finer tiles = finer heavy-first order)")
+    ap.add_argument("--tile", type=int, nargs=2, default=[0, 0], metavar=("W", "H"),
+                    help="N > 1: screen tile size of the interleaved ownership (0 0 = 64x32 at N=2, 32x16 from N=4)")
     ap.add_argument("--steal-div", type=int, default=0,
                     help="N > 1 with p2p assembly: every k-th tile group forms the shared pool ranks steal from (0 = off)")
     args = ap.parse_args()

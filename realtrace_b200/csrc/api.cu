@@ -76,6 +76,7 @@ int rt_create(rt_ctx** out, int device) {
         env_int("RT_WIDE_BVH", 0, 2, c->wide_bvh);
         env_int("RT_FUSE_SHADOW", 0, 1, c->fuse_shadow);
         env_int("RT_FUSE_SHADE", 0, 2, c->fuse_shade);
+        env_int("RT_TILE_BUCKET_BITS", 0, 8, c->tile_bucket_bits);
         env_int("RT_PATH_KERNEL", 0, 1, c->path_kernel);
         env_int("RT_TILE_FEEDBACK", 0, 1, c->tile_feedback);
         env_int("RT_REFILL_PRIMARY_FUSED", 1, 32, c->refill_primary_fused);
@@ -372,15 +373,15 @@ int rt_render_push(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p,
         need((p->flags & RT_FLAG_PACKED_TILES) != 0 && p->world_size >= 1, "rt_render_push: needs RT_FLAG_PACKED_TILES and a world size");
         int world = p->world_size > 1 ? p->world_size : 1, rank = world > 1 ? p->rank : 0;
         if (rt_frame_pushes_inline(ctx, p)) {
-            // bounce-free scene: one kernel traces, shades and sends every finished tile on its way over NVLink
+            // bounce-free scene: ONE kernel traces, shades and stores every finished 8x4 block straight into the
+            // shared frame (over NVLink on ranks > 0); the packed buffer is not used
+            rt_render_params q = *p;
+            q.flags &= ~(uint32_t)RT_FLAG_PACKED_TILES;
             rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 0);
-            ctx->push_frame = frame_dev;
-            try { rt_render_frame(ctx, cam, p, packed_dev, nullptr, nullptr); }
-            catch (...) { ctx->push_frame = nullptr; throw; }
-            ctx->push_frame = nullptr;
-            if (!ctx->pushed_inline)
-                rt_assemble(ctx, packed_dev, rank, world, cam->width, cam->height, p->tile_w > 0 ? p->tile_w : 64,
-                            p->tile_h > 0 ? p->tile_h : 32, frame_dev);
+            ctx->remote_output = true;
+            try { rt_render_frame(ctx, cam, &q, frame_dev, nullptr, nullptr); }
+            catch (...) { ctx->remote_output = false; throw; }
+            ctx->remote_output = false;
             rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 1);
             return;
         }

@@ -129,6 +129,10 @@ __device__ __forceinline__ void write_pixel_direct(uint8_t* out, size_t byte0, f
     out[byte0 + 2] = (uint8_t)to_u8(to_fixed(c.z));
 }
 
+__device__ __forceinline__ uint32_t pack_rgb8(f3 c) {      // the same three bytes, as R | G << 8 | B << 16
+    return to_u8(to_fixed(c.x)) | to_u8(to_fixed(c.y)) << 8 | to_u8(to_fixed(c.z)) << 16;
+}
+
 // FIRST: the wave-0 contribution of a pixel (exactly one per in-frame pixel: the primary miss in
 // k_traverse or the primary hit in k_shade) is a plain store, which also initialises the
 // accumulator — no memset of the frame; every later contribution is an integer atomic add.
@@ -176,10 +180,7 @@ struct TravArgs {
     RayQueue qout;            // SHADE: bounce rays of the shaded hits
     WaveCounters* next;       // SHADE: their counter
     int max_depth;            // SHADE
-    uint8_t* push_frame;      // SHADE + direct packed output: finished tiles are copied into this frame (rank 0's,
-                              // over NVLink) by the warp that completes them; nullptr = no in-kernel push
-    uint32_t* tile_done;      // ... per owned tile (position in tile_ids): finished 32-pixel batches this frame
-    int push_wide;            // ... rows can move as 16-byte chunks
+    int remote_out;           // SHADE: direct_rgb is another GPU's frame (informational: same code path)
 };
 
 // Appends the bounce rays of this warp's shaded hits to the next wave's queue: exclusive prefix over the
@@ -210,37 +211,37 @@ __device__ __forceinline__ void append_children(const RayQueue& qout, WaveCounte
     }
 }
 
-// One warp copies a finished tile of this rank's packed buffer into the frame (camera.cpp:48 layout).  The
-// packed bytes were written by other warps: they are read past L1 (ld.cg) after the caller's fence.
-__device__ __forceinline__ void push_tile(const TravArgs& a, uint32_t tl, int lane) {
-    const FrameDev& f = a.f;
-    uint32_t tile = __ldg(f.tile_ids + tl), slot = tile / (uint32_t)f.world;
-    int tx = (int)(tile % (uint32_t)f.tiles_x), ty = (int)(tile / (uint32_t)f.tiles_x);
-    int rows = min(f.tile_h, f.H - ty * f.tile_h);
-    int row_bytes = min(f.tile_w, f.W - tx * f.tile_w) * 3;
-    const uint8_t* src = a.direct_rgb + (size_t)slot * f.tile_pix * 3;
-    uint8_t* dst = a.push_frame + ((size_t)tx * f.tile_w + (size_t)ty * f.tile_h * f.W) * 3;
-    if (a.push_wide) {
-        int cpr = (f.tile_w * 3) >> 4, n = cpr * rows;                 // 16-byte chunks per tile row / in the tile
-        for (int q = lane; q < n; q += 32) {
-            int y = q / cpr, cb = (q - y * cpr) << 4;
-            if (cb >= row_bytes) continue;
-            const uint8_t* s = src + (size_t)y * f.tile_w * 3 + cb;
-            uint8_t* d = dst + (size_t)y * f.W * 3 + cb;
-            if (cb + 16 <= row_bytes) *reinterpret_cast<uint4*>(d) = __ldcg(reinterpret_cast<const uint4*>(s));
-            else for (int k = 0; k < row_bytes - cb; k++) d[k] = __ldcg(s + k);
-        }
-    } else {
-        for (int y = 0; y < rows; y++)
-            for (int b = lane; b < row_bytes; b += 32)
-                dst[(size_t)y * f.W * 3 + b] = __ldcg(src + (size_t)y * f.tile_w * 3 + b);
+// SHADE mode, RGB8 output: the warp owns an 8x4 pixel block (lane = x%8 + 8*(y%4)) whose colours are all final
+// at the end of the batch.  Instead of 96 single-byte stores scattered over the batch's lifetime, the four
+// 24-byte rows leave as twelve 8-byte stores of one instruction — what a frame that sits in another GPU's
+// memory (NVLink) needs, and cheaper for the local L2 too.  rgb: this lane's pixel as R | G<<8 | B<<16; have: the
+// lane's pixel is inside the frame; (i0, j0): the block's top-left pixel; row_stride in bytes.
+__device__ __forceinline__ void store_block_rgb8(uint8_t* out, size_t block_byte0, size_t row_stride, uint32_t rgb, bool have,
+                                                 bool aligned8, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    if (__all_sync(FULL, have) && aligned8) {
+        // lanes 0..11: row = lane / 3, bytes [8 * part, 8 * part + 8) of the row's 24, part = lane % 3
+        int row = (lane < 12 ? lane : 0) / 3, part = (lane < 12 ? lane : 0) % 3;
+        int p0 = (8 * part) / 3, off = (8 * part) % 3;                 // first pixel of the span, byte offset inside it
+        uint32_t c0 = __shfl_sync(FULL, rgb, row * 8 + p0);
+        uint32_t c1 = __shfl_sync(FULL, rgb, row * 8 + p0 + 1);
+        uint32_t c2 = __shfl_sync(FULL, rgb, row * 8 + p0 + 2);
+        uint32_t c3 = __shfl_sync(FULL, rgb, row * 8 + ((p0 + 3) & 7));
+        // 12 bytes of pixel data starting at pixel p0, as 96 bits; take 8 bytes from byte `off`
+        unsigned long long lo = (unsigned long long)c0 | ((unsigned long long)c1 << 24) | ((unsigned long long)c2 << 48);
+        unsigned long long hi = ((unsigned long long)c2 >> 16) | ((unsigned long long)c3 << 8);
+        unsigned long long v = off == 0 ? lo : (lo >> (8 * off)) | (hi << (64 - 8 * off));
+        if (lane < 12) *reinterpret_cast<unsigned long long*>(out + block_byte0 + (size_t)row * row_stride + 8 * part) = v;
+    } else if (have) {
+        uint8_t* o = out + block_byte0 + (size_t)(lane >> 3) * row_stride + (size_t)(lane & 7) * 3;
+        o[0] = (uint8_t)rgb; o[1] = (uint8_t)(rgb >> 8); o[2] = (uint8_t)(rgb >> 16);
     }
 }
 
 // SHADE mode of k_traverse: the warp's batch is done, shade its pending primary hits together.
 // Returns true if the bounce-ray queue overflowed.
 __device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uint32_t pm, HitRec nh, uint32_t occl_mask,
-                                         f3 pd, int pi, int pj, uint32_t pix) {
+                                         f3 pd, uint32_t pix, uint32_t& px_rgb, bool& px_have) {
     const int lane = threadIdx.x & 31;
     bool qfull = false;
     ShadeOut out;
@@ -252,7 +253,7 @@ __device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uin
         auto any_hit = [&](f3, f3) -> bool { bool o2 = ((occl_mask >> li) & 1u) != 0; li++; return o2; };
         shade_hit(a.s, po, pd, 0, nh, a.max_depth, any_hit, out);
         f3 contrib = out.local + out.bg_weight * bg;
-        if (a.direct_rgb) write_pixel_direct(a.direct_rgb, pixel_byte_offset(a.f, pi, pj, a.direct_packed), contrib);
+        if (a.direct_rgb) { px_rgb = pack_rgb8(contrib); px_have = true; }     // stored with the rest of the block
         else accumulate<true>(a.accum, pix, contrib);
     }
     append_children(a.qout, a.next, a.cap, out, pending, mk3(1, 1, 1), pix, lane, qfull);
@@ -316,6 +317,8 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
     f3 P = mk3(0, 0, 0);
     uint32_t occl_mask = 0;
     bool pending = false, qfull = false;   // SHADE: this lane's hit waits for the end of the batch
+    uint32_t px_rgb = 0;                   // SHADE, RGB8 output: the lane's finished pixel, stored with its 8x4 block
+    bool px_have = false;
     auto start_shadow = [&](int li) {
         f3 toL = mk3(__ldg(a.s.lights + 2 * li)) - P;
         f3 sd = normalize(toL);
@@ -329,25 +332,18 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
 
     // the warp has just finished a whole 32-pixel batch (all lanes idle, hits shaded)
     auto finish_batch = [&]() {
+        if (SHADE && a.direct_rgb && __any_sync(FULL, px_have)) {
+            // lane 0 is the block's top-left pixel (always inside the frame when any pixel of the block is)
+            int i0 = __shfl_sync(FULL, pi, 0), j0 = __shfl_sync(FULL, pj, 0);
+            size_t b0 = pixel_byte_offset(a.f, i0, j0, a.direct_packed);
+            size_t stride = (size_t)(a.direct_packed ? a.f.tile_w : a.f.W) * 3;
+            bool al = (((uintptr_t)a.direct_rgb + b0) & 7) == 0 && (stride & 7) == 0;
+            store_block_rgb8(a.direct_rgb, b0, stride, px_rgb, px_have, al, lane);
+            px_have = false;
+        }
         if (batch_tile == 0xffffffffu) return;
         // charge its duration to the tile
         if (a.f.tile_cost && lane == 0) atomicMax(a.f.tile_cost + batch_tile, (uint32_t)((clock64() - batch_t0) >> 6));
-        if (SHADE && a.push_frame) {
-            // ... and count it; whoever completes a tile sends it on its way while the others keep tracing.
-            // The warp barrier + lane 0's RELEASE add order every lane's pixel stores (performed at L2) before
-            // the count.  No __threadfence anywhere here: it compiles to MEMBAR.SC + CCTL.IVALL, and throwing
-            // the SM's L1 — the BVH working set — away at every batch cost 10 % of the frame.  The warp that
-            // sees the last count reads the pixels straight from L2 (ld.cg in push_tile), behind the branch
-            // on the atomic's result.
-            __syncwarp();
-            uint32_t done = 0;
-            if (lane == 0) {
-                asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(done) : "l"(a.tile_done + batch_tile) : "memory");
-                done += 1u;
-            }
-            done = __shfl_sync(FULL, done, 0);
-            if (done == (uint32_t)a.f.tile_pix >> 5) push_tile(a, batch_tile, lane);
-        }
         batch_tile = 0xffffffffu;
     };
 
@@ -360,7 +356,7 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
             uint32_t pm = __ballot_sync(FULL, pending);
             if (pm) {
                 f3 pd = mk3(s_pdir[threadIdx.x], s_pdir[TRAV_TPB + threadIdx.x], s_pdir[2 * TRAV_TPB + threadIdx.x]);
-                if (shade_batch(a, pending, pm, nh, occl_mask, pd, pi, pj, pix)) qfull = true;
+                if (shade_batch(a, pending, pm, nh, occl_mask, pd, pix, px_rgb, px_have)) qfull = true;
                 pending = false;
             }
         }
@@ -370,9 +366,9 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(cursor, (uint32_t)cnt);
             base = __shfl_sync(FULL, base, leader);
-            if (MODE == MODE_PRIMARY && (a.f.tile_cost || (SHADE && a.push_frame)) && need == FULL && base < n) {
+            if (MODE == MODE_PRIMARY && a.f.tile_cost && need == FULL && base < n) {
                 batch_tile = base / (uint32_t)a.f.tile_pix;
-                if (a.f.tile_cost) batch_t0 = clock64();
+                batch_t0 = clock64();
             }
             if (base + (uint32_t)cnt >= n) exhausted = true;
             my = base + __popc(need & lt);
@@ -538,7 +534,8 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
                     if (a.aux_t) a.aux_t[at] = found ? hit.t : RT_FLT_MAX;
                 }
                 if (!found) {
-                    if (MODE == MODE_PRIMARY && a.direct_rgb)
+                    if (SHADE && a.direct_rgb) { px_rgb = pack_rgb8(w * bg); px_have = true; }
+                    else if (MODE == MODE_PRIMARY && a.direct_rgb)
                         write_pixel_direct(a.direct_rgb, pixel_byte_offset(a.f, pi, pj, a.direct_packed), w * bg);
                     else
                         accumulate<MODE == MODE_PRIMARY>(a.accum, pix, w * bg);      // world.cpp:110
@@ -903,17 +900,19 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
 // up are cheap ones and the kernel does not end on a long tail of expensive batches.  One CTA, bitonic sort of <= 4096 keys
 // (cost << 32 | tile id) in shared memory.  Only the order of work changes, never a pixel.
 #define RT_SORT_TILES_MAX 4096
-__global__ void __launch_bounds__(1024) k_sort_tiles(uint32_t* __restrict__ tile_ids, uint32_t* __restrict__ cost, uint32_t n) {
+__global__ void __launch_bounds__(1024) k_sort_tiles(uint32_t* __restrict__ tile_ids, uint32_t* __restrict__ cost, uint32_t n,
+                                                     int sub_bits) {
     __shared__ unsigned long long key[RT_SORT_TILES_MAX];
     uint32_t m = 1;
     while (m < n) m <<= 1;
-    // key: half-octave bucket of the tile's slowest batch, then the tile id DEscending in the low word
+    // key: the cost of the tile's slowest batch rounded to a few mantissa bits, then the tile id DEscending in the low word
     // (stored inverted), so that tiles of similar cost keep their spatial (cache-friendly) order
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
         unsigned long long k = 0ull;
         if (i < n) {
             uint32_t c = cost[i], b = 0;
-            if (c) { int e = 31 - __clz((int)c); b = 2u * (uint32_t)e + ((e > 0 && (c >> (e - 1)) & 1u) ? 1u : 0u) + 1u; }
+            // bucket = exponent and the top sub_bits mantissa bits of the cost (1 bit: half octaves)
+            if (c) { int e = 31 - __clz((int)c); b = ((uint32_t)e << sub_bits) + (e >= sub_bits ? (c >> (e - sub_bits)) & ((1u << sub_bits) - 1u) : 0u) + 1u; }
             k = ((unsigned long long)b << 32) | (0xffffffffu - tile_ids[i]);
         }
         key[i] = k;
@@ -1254,7 +1253,7 @@ uint32_t launch_wave(rt_ctx* c, TravArgs ta, ShadeArgs sa, int slot_in, int slot
     ta.loop_style = PRIMARY ? c->loop_primary : c->loop_queue;
     const bool fuse = shade && c->fuse_shadow && c->scene.n_lights > 0 && c->scene.n_lights <= 8;
     // primary wave, whole-batch refill: shading happens inside the traversal kernel too
-    const bool fuse_shade = PRIMARY && fuse && wave0_shades_inline(c, ta.push_frame != nullptr);
+    const bool fuse_shade = PRIMARY && fuse && wave0_shades_inline(c, ta.remote_out != 0);
     if (fuse_shade) {
         ta.refill_min = 32;
         ta.qout = queue_of(c, cur ^ 1);
@@ -1462,16 +1461,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         ta.direct_rgb = sa.direct_rgb = (uint8_t*)rgb_dev;
         ta.direct_packed = sa.direct_packed = (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0;
     }
-    c->pushed_inline = false;
-    if (c->push_frame && direct && ta.direct_packed && rt_frame_pushes_inline(c, p)) {
-        c->d_tile_done.reserve(f.n_tiles_owned ? f.n_tiles_owned : 1);
-        RT_CUDA(cudaMemsetAsync(c->d_tile_done.p, 0, (f.n_tiles_owned ? f.n_tiles_owned : 1) * sizeof(uint32_t), st));
-        ta.push_frame = (uint8_t*)c->push_frame;
-        ta.tile_done = c->d_tile_done.p;
-        ta.push_wide = ((f.W * 3) % 16 == 0 && (f.tile_w * 3) % 16 == 0 && ((uintptr_t)rgb_dev & 15) == 0 &&
-                        ((uintptr_t)c->push_frame & 15) == 0) ? 1 : 0;
-        c->pushed_inline = true;
-    }
+    ta.remote_out = (c->remote_output && direct) ? 1 : 0;
     uint32_t launches = 0;
     const bool has_work = f.n_local_pix > 0 || f.steal_cursor != nullptr;
     if (has_work) launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, c->ev[1], c->ev[2]);
@@ -1506,7 +1496,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     // ~50 us; costs keep accumulating as maxima in between); it runs after the last kernel that indexes
     // pixels through tile_ids
     if (f.tile_cost && (c->frames_in_layout < 2 || c->frames_in_layout % 8 == 0)) {
-        k_sort_tiles<<<1, 1024, 0, st>>>(c->d_tile_ids.p, c->d_tile_cost.p, f.n_tiles_owned);
+        k_sort_tiles<<<1, 1024, 0, st>>>(c->d_tile_ids.p, c->d_tile_cost.p, f.n_tiles_owned, c->tile_bucket_bits);
         RT_CUDA(cudaGetLastError());
         launches++;
     }

@@ -161,12 +161,11 @@ struct rt_ctx {
     bool refit_pending = false;
     int trace_blocks = 0, fused_blocks = 0, shadow_blocks = 0, shade_blocks = 0, path_blocks = 0;
     int wide_blocks = 0, path_wide_blocks = 0, fused_shade_blocks = 0, wide_shade_blocks = 0;
+    int tile_bucket_bits = 5;              // heavy-tiles-first: mantissa bits of the cost kept in the sort key (RT_TILE_BUCKET_BITS)
     int fuse_shade = 1;                    // primary hits shaded inside the fused traversal kernel (RT_FUSE_SHADE): 0 never,
                                            // 1 when that kernel also pushes finished tiles to a remote frame, 2 always
-    void* push_frame = nullptr;            // rt_render_push: frame the primary kernel may push finished tiles into
-    bool pushed_inline = false;            // ... and whether the last frame did
+    bool remote_output = false;            // rt_render_push: the frame being rendered into sits in another GPU's memory
     uint64_t launch_total = 0;             // kernels enqueued by frame-level calls since rt_create (rt_debug_frame_launches)
-    DevBuf<uint32_t> d_tile_done;
     int path_kernel = 1;                   // bounce generations in one k_paths launch (RT_PATH_KERNEL=0: wave loop)
     int fuse_shadow = 1;                   // shadow rays ride in the lane that found the hit (RT_FUSE_SHADOW)
     int refill_primary_fused = 32;
