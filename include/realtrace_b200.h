@@ -188,15 +188,21 @@ int rt_shared_buffer_open(rt_ctx* ctx, const unsigned char handle[64], void** de
 int rt_download(rt_ctx* ctx, const void* dev_ptr, void* host, uint64_t bytes);
 /* Frame-completion handshake through a shared buffer (>= 1 KiB from rt_shared_buffer_create on rank 0,
  * opened by the others) instead of a collective: enqueue phase 0 before and phase 1 after the kernels
- * that write frame `frame_index` into rank 0's memory.  After phase 1 has run on rank 0's stream the
- * frame is complete there; ranks > 0 never run more than one frame ahead of rank 0.  frame_index must
- * count 0, 1, 2, ... identically on all ranks.                                                    */
+ * that write frame `frame_index` into rank 0's memory.
+ *   phase 0: rank 0 publishes "frames < frame_index are consumed" — in stream order, i.e. after everything it
+ *            enqueued for the previous frame (a download, a display copy); ranks > 0 wait for that.
+ *   phase 1: ranks > 0 signal their arrival; rank 0 waits for world_size - 1 arrivals.
+ * After phase 1 has run on rank 0's stream the frame is complete there; ranks > 0 never run more than one
+ * frame ahead of rank 0.  frame_index must count 0, 1, 2, ... identically on all ranks.  The waiting kernels
+ * are single threads that give up after ~2 s (reported by the next synchronising call).          */
 int rt_peer_sync(rt_ctx* ctx, void* sync_buf, int32_t rank, int32_t world_size, uint32_t frame_index, int32_t phase);
 /* A symmetric barrier over the same buffer: every rank enqueues it with the same epoch = 0, 1, 2, ...     */
 int rt_peer_barrier(rt_ctx* ctx, void* sync_buf, int32_t world_size, uint32_t epoch);
-/* One call for a whole multi-GPU frame step, all of it only enqueued: render this rank's tiles into the local
- * packed buffer (p->flags must carry RT_FLAG_PACKED_TILES), rt_peer_sync phase 0, push the tiles into the
- * shared frame, rt_peer_sync phase 1.                                                                     */
+/* One call for a whole multi-GPU frame step, all of it only enqueued (p->flags must carry RT_FLAG_PACKED_TILES).
+ * Scene with mirror/dielectric bounces: render this rank's tiles into the local packed buffer, rt_peer_sync
+ * phase 0, push the tiles into the shared frame, rt_peer_sync phase 1.  Bounce-free scene (1..8 lights): phase 0,
+ * ONE kernel that traces, shades and stores every finished 8x4 pixel block straight into frame_dev (packed_dev
+ * is not written), phase 1.                                                                               */
 int rt_render_push(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, void* packed_dev, void* frame_dev,
                    void* sync_buf, uint32_t frame_index);
 /* tile helpers for the gather-based assembly (the gather itself is NCCL, outside)               */
