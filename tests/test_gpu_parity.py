@@ -297,6 +297,43 @@ def test_peer_handshake_and_tile_push_logical_ranks():
     assert sync[64] == 2                                      # rank 0 opened frame 2: frames 0 and 1 consumed
 
 
+@pytest.mark.parametrize("name", ["synth_small_d1", "blubmixed_d5", "bobtex_d3"])
+def test_work_order_feedback_never_changes_a_pixel(name):
+    """Heavy-tiles-first re-sort: from the second frame on the kernel walks the tiles in the order of their
+    measured cost.  Twelve frames (re-sorts after frames 0, 1 and 8): every frame equals the first, and every
+    pixel is traced exactly once."""
+    scene, cam, depth, _ = build_case(name)
+    cam.width, cam.height = 648, 366
+    ctx = make_ctx(scene)
+    first = None
+    for k in range(12):
+        rgb, _, _, st = ctx.render(cam, depth)
+        assert st["rays_primary"] == cam.width * cam.height, k
+        if first is None:
+            first = rgb.copy()
+        else:
+            assert np.array_equal(rgb, first), k
+    # one third of the frame as a logical rank (packed output): same pixels
+    import torch
+    _, owned, tb = api.tile_layout(cam.width, cam.height, 32, 16, 1, 3)
+    packed = torch.zeros(owned * tb, dtype=torch.uint8, device="cuda")
+    outs = []
+    for k in range(10):
+        st = ctx.render_device(cam, depth, packed.data_ptr(), tile=(32, 16), rank=1, world=3, flags=api.FLAG_PACKED_TILES)
+        torch.cuda.synchronize()
+        outs.append(packed.cpu().numpy().copy())
+        assert np.array_equal(outs[-1], outs[0]), k
+    frame = torch.zeros(cam.height * cam.width * 3, dtype=torch.uint8, device="cuda")
+    ctx.assemble_tiles(packed.data_ptr(), 1, 3, cam.width, cam.height, frame.data_ptr(), tile=(32, 16))
+    torch.cuda.synchronize()
+    ctx.close()
+    got = frame.cpu().numpy().reshape(cam.height, cam.width, 3)
+    tx, ty = (cam.width + 31) // 32, (cam.height + 15) // 16
+    for t in range(1, tx * ty, 3):                         # rank 1's tiles
+        x0, y0 = (t % tx) * 32, (t // tx) * 16
+        assert np.array_equal(got[y0:y0 + 16, x0:x0 + 32], first[y0:y0 + 16, x0:x0 + 32]), t
+
+
 @pytest.mark.parametrize("name,tile", [("synth_small_d1", (0, 0)), ("synth_small_d1", (32, 16)), ("synth_small_d1", (8, 4)),
                                        ("blubmixed_d5", (0, 0))])
 def test_render_push_one_call_per_rank(name, tile):
