@@ -162,6 +162,10 @@ int rt_scene_set_environment(rt_ctx* ctx, const float ambient[3], const float ba
 #define RT_COMMIT_REFIT 1
 int rt_scene_commit(rt_ctx* ctx, int mode);
 int rt_scene_update_vertices(rt_ctx* ctx, const float* v, uint32_t n);
+/* The same from DEVICE memory (vertices deformed by the caller's own kernel): an asynchronous device-to-device
+ * copy on the context's stream, no host round trip; follow with rt_scene_commit(RT_COMMIT_REFIT).  A later
+ * RT_COMMIT_BUILD without new rt_scene_set_triangles rebuilds from these vertices.                  */
+int rt_scene_update_vertices_device(rt_ctx* ctx, const float* v_dev, uint32_t n);
 int rt_scene_build_stats(rt_ctx* ctx, rt_build_stats* out);
 
 /* ---- rendering: replaces `while(!engine->renderLoop()){}` (renderengine.cpp:10-26,

@@ -61,7 +61,7 @@ class RtBuildStats(C.Structure):
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_scene_set_triangles", "rt_scene_set_spheres",
     "rt_scene_set_planes", "rt_scene_set_cylinders", "rt_scene_set_materials", "rt_scene_set_lights",
-    "rt_scene_set_environment", "rt_scene_commit", "rt_scene_update_vertices", "rt_scene_build_stats", "rt_render",
+    "rt_scene_set_environment", "rt_scene_commit", "rt_scene_update_vertices", "rt_scene_update_vertices_device", "rt_scene_build_stats", "rt_render",
     "rt_render_device", "rt_tile_layout", "rt_assemble_tiles", "rt_trace_rays", "rt_shade_rays", "rt_bvh_download",
     "rt_debug_sort_pairs", "rt_debug_warp_times", "rt_debug_frame_launches", "rt_synchronize", "rt_peer_sync", "rt_peer_barrier", "rt_render_push", "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_download",
 ]
@@ -91,6 +91,7 @@ def load_library():
     lib.rt_scene_set_environment.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.rt_scene_commit.argtypes = [vp, C.c_int]
     lib.rt_scene_update_vertices.argtypes = [vp, fp, C.c_uint32]
+    lib.rt_scene_update_vertices_device.argtypes = [vp, vp, C.c_uint32]
     lib.rt_scene_build_stats.argtypes = [vp, C.POINTER(RtBuildStats)]
     lib.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp, C.POINTER(RtAuxOut),
                               C.POINTER(RtFrameStats)]
@@ -208,6 +209,10 @@ class Context:
     def update_vertices(self, tri_v):
         v = np.ascontiguousarray(tri_v, np.float32).reshape(-1, 9)
         self._check(self.lib.rt_scene_update_vertices(self.h, v.ctypes.data, len(v)))
+
+    def update_vertices_device(self, dev_ptr, n_triangles):
+        """Vertices (n x 9 float32) already in device memory: asynchronous D2D copy on the context's stream."""
+        self._check(self.lib.rt_scene_update_vertices_device(self.h, dev_ptr, n_triangles))
 
     def build_stats(self):
         st = RtBuildStats()

@@ -122,6 +122,7 @@ int rt_scene_set_triangles(rt_ctx* ctx, const float* v, const uint32_t* material
         need(n == 0 || (v && material_id), "rt_scene_set_triangles: v and material_id are required");
         need(n < (1u << 28), "rt_scene_set_triangles: at most 2^28 - 1 triangles");
         ctx->h_tri_v.assign(v, v + 9 * (size_t)n);
+        ctx->host_vertices_stale = false;
         ctx->h_tri_mat.assign(material_id, material_id + n);
         ctx->h_tri_obj.resize(n);
         for (uint32_t i = 0; i < n; i++) ctx->h_tri_obj[i] = object_id ? object_id[i] : i;
@@ -217,6 +218,12 @@ int rt_scene_commit(rt_ctx* ctx, int mode) {
             return;
         }
         need(!ctx->h_materials.empty(), "rt_scene_commit: no materials set");
+        if (ctx->host_vertices_stale && ctx->committed && ctx->n_tri && ctx->h_tri_v.size() == 9 * (size_t)ctx->n_tri) {
+            // vertices were last written on the device (rt_scene_update_vertices_device): a rebuild starts from them
+            RT_CUDA(cudaMemcpyAsync(ctx->h_tri_v.data(), ctx->d_tri_v.p, ctx->h_tri_v.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        ctx->host_vertices_stale = false;
         uint32_t nm = (uint32_t)ctx->h_materials.size();
         for (uint32_t m : ctx->h_tri_mat) need(m < nm, "rt_scene_commit: triangle material id out of range");
         bool any_bary = false;
@@ -245,8 +252,20 @@ int rt_scene_update_vertices(rt_ctx* ctx, const float* v, uint32_t n) {
         if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "rt_scene_update_vertices before commit"};
         need(v && n == ctx->n_tri, "rt_scene_update_vertices: vertex count must equal the committed triangle count");
         ctx->h_tri_v.assign(v, v + 9 * (size_t)n);
+        ctx->host_vertices_stale = false;
         RT_CUDA(cudaMemcpyAsync(ctx->d_tri_v.p, ctx->h_tri_v.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int rt_scene_update_vertices_device(rt_ctx* ctx, const float* v_dev, uint32_t n) {
+    return guarded(ctx, [&] {
+        if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "rt_scene_update_vertices_device before commit"};
+        need(v_dev && n == ctx->n_tri, "rt_scene_update_vertices_device: vertex count must equal the committed triangle count");
+        // device to device on the context's stream, nothing waits: the caller's deformation kernel must have been
+        // enqueued on the same stream (rt_set_stream) or be complete
+        RT_CUDA(cudaMemcpyAsync(ctx->d_tri_v.p, v_dev, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->host_vertices_stale = true;
     });
 }
 

@@ -101,6 +101,7 @@ struct rt_ctx {
 
     // ---- host staging of the scene (copied by the rt_scene_set_* calls)
     std::vector<float> h_tri_v;            // 9 per triangle
+    bool host_vertices_stale = false;      // the device copy is newer (rt_scene_update_vertices_device)
     std::vector<uint32_t> h_tri_mat, h_tri_obj;
     std::vector<float> h_tri_rgb;          // 9 per triangle or empty
     std::vector<AnalyticPrim> h_spheres, h_planes, h_cylinders;

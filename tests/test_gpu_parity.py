@@ -151,6 +151,39 @@ def test_refit_is_idempotent_and_tracks_vertices(oracle):
     parity.assert_parity(parity.compare(r[0], r[1], r[2], tr[0], tr[1], tr[2]), "refit after translation")
 
 
+def test_vertices_deformed_on_the_device_refit_and_rebuild():
+    """an animation step that never leaves the GPU.  The vertices are deformed by a device-side
+    op (torch stands in for the caller's kernel, on the context's stream), handed over with
+    rt_scene_update_vertices_device, and the LBVH is refitted; frames must equal those of a context that was built
+    from the same deformed vertices, and a later BUILD commit must start from the device-side vertices."""
+    import torch
+    scene, cam, depth, _ = build_case("bobtex_d3")
+    ctx = make_ctx(scene)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream or 1)
+    v = torch.from_numpy(np.ascontiguousarray(scene.tri_v, np.float32)).cuda().reshape(-1, 3, 3)
+    for step in (1, 2):
+        phase = 0.7 * step
+        d = v.clone()
+        d[:, :, 1] += 0.8 * torch.sin(0.35 * v[:, :, 0] + phase)         # a travelling wave along x
+        d[:, :, 2] += 0.5 * torch.cos(0.25 * v[:, :, 1] - phase)
+        ctx.update_vertices_device(d.data_ptr(), d.shape[0])
+        ctx.commit(api.COMMIT_REFIT, want_stats=False)
+        got = ctx.render(cam, depth, aux=True)
+        scene2, _, _, _ = build_case("bobtex_d3")
+        scene2.tri_v = d.reshape(-1, 9).cpu().numpy()
+        fresh = make_ctx(scene2)
+        want = fresh.render(cam, depth, aux=True)
+        fresh.close()
+        m = parity.compare(got[0], got[1], got[2], want[0], want[1], want[2])
+        parity.assert_parity(m, f"device-side deformation step {step}: refit vs fresh build")
+    # a rebuild without new rt_scene_set_triangles picks the device-side vertices up
+    ctx.commit(api.COMMIT_BUILD)
+    again = ctx.render(cam, depth, aux=True)
+    ctx.close()
+    assert np.array_equal(again[0], want[0]) and np.array_equal(again[1], want[1])
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_tile_sharding_is_bit_identical(world):
     """N logical ranks on one GPU: every rank renders its interleaved tiles; assembling the packed
