@@ -88,6 +88,48 @@ static int sah_build(std::vector<SahTmp>& prims, int lo, int hi, std::vector<flo
     return me;
 }
 
+// ---- experiment only: PLOC (Meister & Bittner 2018) over the Morton-sorted leaves — bottom-up merging of
+// mutual nearest neighbours (surface area of the union) inside a window of +-radius positions.  Same node
+// format; node 0 is the root (indices are handed out from the top down as merges happen last for the root).
+struct PlocCluster { Aabb box; int code; };
+static void ploc_build(std::vector<PlocCluster> c, int radius, std::vector<float4>& nodes, float pad_abs) {
+    int n = (int)c.size();
+    nodes.assign(4 * (size_t)(n - 1), make_float4(0, 0, 0, 0));
+    int next = n - 2;
+    auto padded = [&](Aabb b) { Aabb r = aabb_pad(b); r.lo = r.lo - mk3(pad_abs, pad_abs, pad_abs); r.hi = r.hi + mk3(pad_abs, pad_abs, pad_abs); return r; };
+    std::vector<int> nn(n);
+    std::vector<PlocCluster> out;
+    while ((int)c.size() > 1) {
+        int m = (int)c.size();
+        for (int i = 0; i < m; i++) {
+            float best = RT_FLT_MAX; int bj = -1;
+            for (int j = std::max(0, i - radius); j <= std::min(m - 1, i + radius); j++) {
+                if (j == i) continue;
+                float a = half_area(aabb_union(c[i].box, c[j].box));
+                if (a < best) { best = a; bj = j; }
+            }
+            nn[i] = bj;
+        }
+        out.clear();
+        for (int i = 0; i < m; i++) {
+            int j = nn[i];
+            if (nn[j] == i) {
+                if (i < j) {
+                    int me = next--;
+                    Aabb Lp = padded(c[i].box), Rp = padded(c[j].box);
+                    nodes[4 * (size_t)me] = make_float4(Lp.lo.x, Lp.hi.x, Lp.lo.y, Lp.hi.y);
+                    nodes[4 * (size_t)me + 1] = make_float4(Rp.lo.x, Rp.hi.x, Rp.lo.y, Rp.hi.y);
+                    nodes[4 * (size_t)me + 2] = make_float4(Lp.lo.z, Lp.hi.z, Rp.lo.z, Rp.hi.z);
+                    nodes[4 * (size_t)me + 3] = make_float4(as_float((uint32_t)c[i].code), as_float((uint32_t)c[j].code), 0, 0);
+                    PlocCluster p; p.box = aabb_union(c[i].box, c[j].box); p.code = me;
+                    out.push_back(p);
+                }
+            } else out.push_back(c[i]);
+        }
+        c.swap(out);
+    }
+}
+
 void build(const oracle_scene* in, int leaf_size, EmulScene& S) {
     uint32_t n = in->n_tri;
     // analytic list: spheres, planes, cylinders (object ids default to after the triangles)
@@ -233,6 +275,17 @@ void build(const oracle_scene* in, int leaf_size, EmulScene& S) {
         std::vector<float4> nodes;
         Aabb rb;
         sah_build(prims, 0, (int)nb, nodes, rb, pad_abs);
+        S.nodes.swap(nodes);
+    }
+    if (getenv("EMUL_PLOC") && nb >= 2) {
+        std::vector<PlocCluster> cl(nb);
+        for (uint32_t k = 0; k < nb; k++) {
+            uint32_t i = S.order[k];
+            cl[k].box = tri_aabb(vtx(in->tri_v, i, 0), vtx(in->tri_v, i, 1), vtx(in->tri_v, i, 2));
+            cl[k].code = rt_leaf_code(k, 1u);
+        }
+        std::vector<float4> nodes;
+        ploc_build(cl, atoi(getenv("EMUL_PLOC")) > 0 ? atoi(getenv("EMUL_PLOC")) : 8, nodes, pad_abs);
         S.nodes.swap(nodes);
     }
     if (getenv("EMUL_WIDE") && !S.nodes.empty()) {      // 4-wide view (k_collapse4 of the GPU build)

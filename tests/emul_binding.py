@@ -55,6 +55,18 @@ class Emulation:
         assert rc == 0, rc
         return prim, t
 
+    def primary_cost(self, scene, cam, leaf=1):
+        """Per-pixel (node visits, triangle tests) of the primary rays."""
+        s, keep = ob._scene_struct(scene)
+        W, H = cam.width, cam.height
+        nodes = np.zeros((H, W), np.uint32)
+        tris = np.zeros((H, W), np.uint32)
+        c = api.camera_struct(cam)
+        self.lib.emul_primary_cost.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2
+        rc = self.lib.emul_primary_cost(C.byref(s), C.byref(c), leaf, nodes.ctypes.data, tris.ctypes.data)
+        assert rc == 0, rc
+        return nodes, tris
+
     def bvh(self, scene, leaf=4):
         s, keep = ob._scene_struct(scene)
         n = len(scene.tri_v)
