@@ -405,10 +405,11 @@ def test_render_push_one_call_per_rank(name, tile):
         c.close()
 
 
-@pytest.mark.parametrize("name,col_step", [("synth1m", 240), ("blub4k", 120)])
+@pytest.mark.parametrize("name,col_step", [("synth1m", 240), ("blub4k", 120), ("bob1080", 30)])
 def test_full_size_frames_against_oracle_column_sample(oracle, name, col_step):
-    """BASELINE configs 4 and 3 at their full 3840x2160 size: the GPU frame against the CPU oracle (grid as
-    shipped) on every col_step-th column, plus size-independent properties (idempotence, ray accounting)."""
+    """BASELINE configs 4, 3 and 2 at their full size (3840x2160, 3840x2160, 1920x1080): the GPU frame against the
+    CPU oracle (grid as shipped) on every col_step-th column, plus size-independent properties (idempotence, ray
+    accounting)."""
     scene, cam, depth, _ = scenes.workload(name)
     ctx = make_ctx(scene)
     rgb, prim, t, st = ctx.render(cam, depth, aux=True)
