@@ -98,6 +98,30 @@ def test_bvh_structure(name, leaf):
     assert info["depth"] <= 64
 
 
+@pytest.mark.parametrize("name", ["synth_small_d1", "bobtex_d3"])
+def test_work_counters_match_a_cpu_walk_of_the_same_tree(name, monkeypatch):
+    """N_node / N_tri of the roofline come from counters in the traversal kernels
+    (RT_FLAG_COUNT_WORK); a CPU walk of the same tree over the same rays (tests/emul, the kernels' own RT_HD
+    functions run serially) must agree within 1 %.  The bounce paths walk the binary tree here like the CPU does
+    (by default k_paths uses the 4-wide view, where one visit covers up to three binary nodes)."""
+    import emul_binding
+    monkeypatch.setenv("RT_WIDE_BVH", "0")
+    scene, cam, depth, _ = build_case(name)
+    ctx = make_ctx(scene)
+    leaf = ctx.build_stats()["leaf_size"]
+    st = ctx.render(cam, depth, flags=api.FLAG_COUNT_WORK)[3]
+    ctx.close()
+    _, _, _, counts = emul_binding.Emulation().render(scene, cam, depth, leaf=leaf)
+    rays_gpu = st["rays_primary"] + st["rays_shadow"] + st["rays_secondary"]
+    rays_cpu = int(counts[0] + counts[1] + counts[2])
+    nodes_gpu = st["node_visits"] + st["shadow_node_visits"]
+    tris_gpu = st["tri_tests"] + st["shadow_tri_tests"]
+    assert nodes_gpu > 0 and tris_gpu > 0
+    assert abs(rays_gpu - rays_cpu) <= 0.001 * rays_cpu, (rays_gpu, rays_cpu)
+    assert abs(nodes_gpu - int(counts[3])) <= 0.01 * int(counts[3]), (nodes_gpu, int(counts[3]))
+    assert abs(tris_gpu - int(counts[4])) <= 0.01 * int(counts[4]), (tris_gpu, int(counts[4]))
+
+
 def test_bvh_equals_the_emulated_build():
     """Device radix sort + Karras + refit produce exactly the tree the serial emulation builds."""
     import emul_binding
