@@ -33,3 +33,54 @@ def build_case(name):
     if name == "bob_full_bboxfixed_d10":
         return scenes.obj_scene("bob_tri.obj"), scenes.stock_camera(w, h), 10, ob.MODE_BBOX_FIXED
     raise KeyError(name)
+
+
+# ---- edge cases (no golden fixtures: checked against the oracle on the spot) --------------------------------------
+EDGE_CASES = ["empty_world", "no_lights", "one_triangle", "two_triangles", "degenerate_and_duplicate_triangles",
+              "coincident_centroids", "tiny_frame_1x1", "tiny_frame_7x5", "tiny_frame_33x1"]
+
+
+def build_edge_case(name):
+    """-> (scene, camera, max_depth).  Inputs the domain offers at its borders: nothing to hit, nothing to light,
+    hierarchies of one and two leaves, zero-area and repeated triangles (|A| < 1e-7 rejection, duplicate Morton
+    keys), frames smaller than a tile and than a warp batch."""
+    import numpy as np
+    from realtrace_b200.scene import Scene, make_materials
+    w, h = 96, 64
+    cam = scenes.close_camera(w, h)
+    base = dict(materials=make_materials([scenes.OBJ_MATERIAL, dict(color=(0.7, 0.7, 0.2), kr=0.4)]),
+                lights=np.asarray([scenes.STOCK_LIGHT], np.float32), ambient=scenes.STOCK_AMBIENT,
+                background=scenes.STOCK_BACKGROUND)
+    tri = np.asarray([[-6, -4, 0, 6, -4, 0, 0, 6, 0]], np.float32)                     # faces the close camera
+    if name == "empty_world":
+        return Scene(name=name, **base).normalise(), cam, 3
+    if name == "no_lights":
+        s = scenes.obj_scene("bob_tri.obj", 2000, lights=())
+        s.lights = np.zeros((0, 6), np.float32)
+        return s.normalise(), scenes.stock_camera(w, h), 3
+    if name == "one_triangle":
+        return Scene(tri_v=tri, tri_material=np.zeros(1, np.uint32), name=name, **base).normalise(), cam, 3
+    if name == "two_triangles":
+        t2 = np.concatenate([tri, tri + np.asarray([3, 1, -5] * 3, np.float32)])
+        return Scene(tri_v=t2, tri_material=np.asarray([0, 1], np.uint32), name=name, **base).normalise(), cam, 3
+    if name == "degenerate_and_duplicate_triangles":
+        s = scenes.obj_scene("tetrahedron.obj")
+        v = np.asarray(s.tri_v, np.float32).reshape(-1, 9)
+        zero_area = np.repeat(v[:4, :3], 3, axis=1).reshape(4, 9)                   # three equal vertices
+        collinear = np.asarray([[0, 0, 0, 1, 1, 1, 2, 2, 2]], np.float32)
+        allv = np.concatenate([v, v[:5], zero_area, collinear, v[5:8]])                # repeats: equal t, equal keys
+        s.tri_v = allv
+        s.tri_material = np.zeros(len(allv), np.uint32)
+        return s.normalise(), scenes.stock_camera(w, h), 3
+    if name == "coincident_centroids":
+        # 40 triangles of growing size around ONE centroid: 40 identical Morton keys
+        k = np.arange(1, 41, dtype=np.float32)[:, None]
+        unit = np.asarray([[-1, -1, 0, 1, -1, 0, 0, 2, 0]], np.float32)
+        allv = unit * (0.2 * k) + np.asarray([0, 0, 1] * 3, np.float32) * (0.1 * k)   # (z offset keeps t distinct)
+        allv[:, 2::3] -= allv[:, 2::3].mean(axis=1, keepdims=True) - 0.0                # same centroid in z too
+        allv[:, 2::3] += 0.05 * k                                                       # ... up to a small stagger
+        return Scene(tri_v=allv, tri_material=(np.arange(40) % 2).astype(np.uint32), name=name, **base).normalise(), cam, 3
+    if name.startswith("tiny_frame_"):
+        fw, fh = (int(x) for x in name[len("tiny_frame_"):].split("x"))
+        return scenes.obj_scene("tetrahedron.obj"), scenes.stock_camera(fw, fh), 3
+    raise KeyError(name)
