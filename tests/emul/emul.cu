@@ -405,9 +405,11 @@ extern "C" int emul_bvh(const oracle_scene* in, int leaf_size, float* nodes, uin
     return (int)(S.nodes.size() / 4);
 }
 
-// Per-pixel traversal cost of the primary rays (node visits, triangle tests) — used to study load
-// balance (profiles/r1_tuning.md).
-extern "C" int emul_primary_cost(const oracle_scene* in, const rt_camera* cam, int leaf_size, uint32_t* nodes, uint32_t* tris) {
+// Per-pixel traversal cost of the primary rays (node visits, triangle tests) and, where shadow_steps is given,
+// of the shadow rays of the primary hit (node visits + triangle tests, summed over the lights) — used to study
+// load balance and the length of the per-lane dependency chains (profiles/r1_tuning.md).
+extern "C" int emul_primary_cost(const oracle_scene* in, const rt_camera* cam, int leaf_size, uint32_t* nodes, uint32_t* tris,
+                                 uint32_t* shadow_steps) {
     EmulScene S;
     build(in, leaf_size, S);
     const SceneDev& s = S.dev;
@@ -420,11 +422,27 @@ extern "C" int emul_primary_cost(const oracle_scene* in, const rt_camera* cam, i
             for (int k = 0; k < 3; k++) dd[k] = -(double)cam->w[k] * (double)cam->focal_distance + (double)cam->u[k] * (double)xw + (double)cam->v[k] * (double)yw;
             double l = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
             f3 d = mk3((float)(dd[0] / l), (float)(dd[1] / l), (float)(dd[2] / l));
+            f3 o = mk3(cam->pos[0], cam->pos[1], cam->pos[2]);
             HitRec h;
             WorkCount wc{0, 0};
-            trace_ray<false>(s, mk3(cam->pos[0], cam->pos[1], cam->pos[2]), d, false, h, &wc, &overflow);
-            nodes[(size_t)i + (size_t)j * W] = wc.nodes;
-            tris[(size_t)i + (size_t)j * W] = wc.tris;
+            bool found = trace_ray<false>(s, o, d, false, h, &wc, &overflow);
+            size_t at = (size_t)i + (size_t)j * W;
+            nodes[at] = wc.nodes;
+            tris[at] = wc.tris;
+            if (shadow_steps) {
+                uint32_t steps = 0;
+                if (found) {
+                    f3 P = fma3(d, h.t, o);
+                    for (int li = 0; li < s.n_lights; li++) {
+                        f3 toL = mk3(s.lights[2 * li]) - P;                  // world.cpp:45
+                        HitRec sh;
+                        WorkCount ws{0, 0};
+                        trace_ray<true>(s, fma3(toL, 0.01f, P), normalize(toL), false, sh, &ws, &overflow);
+                        steps += ws.nodes + ws.tris;
+                    }
+                }
+                shadow_steps[at] = steps;
+            }
         }
     return 0;
 }

@@ -55,17 +55,19 @@ class Emulation:
         assert rc == 0, rc
         return prim, t
 
-    def primary_cost(self, scene, cam, leaf=1):
-        """Per-pixel (node visits, triangle tests) of the primary rays."""
+    def primary_cost(self, scene, cam, leaf=1, shadows=False):
+        """Per-pixel (node visits, triangle tests) of the primary rays [and the steps of the hit's shadow rays]."""
         s, keep = ob._scene_struct(scene)
         W, H = cam.width, cam.height
         nodes = np.zeros((H, W), np.uint32)
         tris = np.zeros((H, W), np.uint32)
+        shadow = np.zeros((H, W), np.uint32) if shadows else None
         c = api.camera_struct(cam)
-        self.lib.emul_primary_cost.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2
-        rc = self.lib.emul_primary_cost(C.byref(s), C.byref(c), leaf, nodes.ctypes.data, tris.ctypes.data)
+        self.lib.emul_primary_cost.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 3
+        rc = self.lib.emul_primary_cost(C.byref(s), C.byref(c), leaf, nodes.ctypes.data, tris.ctypes.data,
+                                        shadow.ctypes.data if shadows else None)
         assert rc == 0, rc
-        return nodes, tris
+        return (nodes, tris, shadow) if shadows else (nodes, tris)
 
     def bvh(self, scene, leaf=4):
         s, keep = ob._scene_struct(scene)
