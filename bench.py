@@ -362,6 +362,29 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         rays_total = float(rays_local)
     value = rays_total / (ms * 1e-3) / 1e6
 
+    # ---- N > 1: is the frame the ranks assembled in rank 0's memory the frame one GPU renders?  One more frame
+    # through the timed path (untimed), then rank 0 renders the whole frame by itself and compares byte for byte.
+    # Every collective sits outside the rank-0 block, so a failure in the check cannot hang the other ranks.
+    frame_check = None
+    if world > 1 or os.environ.get("RT_BENCH_FRAME_CHECK"):
+        barrier()
+        step_device(False)
+        barrier()
+        if rank == 0:
+            try:
+                got = np.empty((H, W, 3), np.uint8)
+                ctx.download(frame_ptr, got)
+                alone = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
+                ctx.render_device(cam, depth, alone.data_ptr())
+                want = alone.cpu().numpy().reshape(H, W, 3)
+                bad = int((got != want).sum())
+                frame_check = {"equal_to_the_1_gpu_frame": bad == 0, "mismatching_bytes": bad, "bytes": int(got.size)}
+                if bad:
+                    print(f"[bench] WARNING: the assembled frame differs from rank 0's own render in {bad} bytes", file=sys.stderr)
+            except Exception as e:   # noqa: BLE001 — report, never hang or lose the measurement
+                frame_check = {"error": repr(e)}
+        barrier()
+
     # ---- N > 1 diagnostics (RT_BENCH_PHASES=1): where does a frame's time go on each rank?  Same asynchronous
     # frame loop as the timed one, with extra events between the phases (p2p path without stealing).
     if world > 1 and assemble == "p2p" and not cursor_ptr and os.environ.get("RT_BENCH_PHASES"):
@@ -417,7 +440,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     sampler.stop()
     out = {"value": value, "ms_per_step": ms / steps,
            "ms_per_step_p50": float(np.percentile(per_step, 50)), "ms_per_step_p99": float(np.percentile(per_step, 99)), "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
-           "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "tile": (tile[0] or 64, tile[1] or 32), "cam": cam_py, "depth": depth,
+           "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "tile": (tile[0] or 64, tile[1] or 32), "frame_check": frame_check, "cam": cam_py, "depth": depth,
            "scene": scene, "build": bstats, "commit_s": commit_s, "last": stats[-1], "rays_per_frame": rays_total / steps}
 
     # ---- roofline of the dominant kernel + work counts (single GPU, rank 0)
@@ -487,6 +510,7 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": 64 + 24, "d2h_bytes_per_step": cam.width * cam.height * 3,
                     "what": "rt_render: camera + params in, RGB8 frame into pinned host memory (scene resident)"},
             "gpu_launches": main["launches"], "clocks": main["clocks"],
+            **({"frame_check": main["frame_check"]} if main.get("frame_check") is not None else {}),
             "host_enqueue_ms_per_step": main["host_enqueue_ms_per_step"],
             "build": {"commit_s": main["commit_s"], **main["build"]}}
 
