@@ -10,11 +10,17 @@
 //             from the pixel index (tile-ordered, 8x4 pixels per 32 consecutive indices); later waves
 //             read 48-byte SoA ray records.  Hits are compacted into a hit queue with warp-aggregated
 //             atomics; misses add throughput*background at once (world.cpp:110).
+//             FUSE: the lane then walks its hit's shadow rays itself (one kernel, one tail per wave).
+//             SHADE (primary wave, used where the frame sits in another GPU's memory): the warp also
+//             shades its hits at the end of every 32-pixel batch and stores the finished 8x4 block
+//             with 8-byte stores — trace, shade and delivery over NVLink in ONE kernel per frame.
 //   k_traverse<SHADOW>  one any-hit query per (hit, light): world.cpp:44-51 (no tmax).  Same kernel
-//             body, early exit on the first accepted hit, one occlusion byte out.
+//             body, early exit on the first accepted hit, one occlusion byte out (> 8 lights, or
+//             RT_FUSE_SHADOW=0).
 //   k_shade   per hit: the local Phong-like term (world.cpp:126-137) from the occlusion bytes, then
 //             the mirror / dielectric children (:77-107) appended to the next wave's ray queue with
 //             one atomic per warp (shfl prefix sum).
+//   k_paths   every bounce generation in one launch: a lane follows the whole subtree of one bounce ray.
 //   k_resolve 32.32 fixed-point accumulators -> clamp -> (uint8)(255 c) (color.cpp:19-28,
 //             camera.cpp:49-51) into the frame or into this rank's packed tile buffer.
 // Pixel sums use integer atomics, so the frame is bit-identical for any tile split, queue order
