@@ -25,10 +25,9 @@ for tag, env in (("binary tree", {}), ("4-wide view", {"EMUL_WIDE": "1"})):
     nodes, tris, sh = emul_binding.Emulation().primary_cost(scene, cam, 1, shadows=True)
     p = blocks(nodes.astype(np.int64) + tris); s = blocks(sh.astype(np.int64))
     fused = (p + s).max(axis=2)                 # a lane walks its primary ray, then its shadow ray(s)
-    split = np.maximum(p.max(axis=2), s.max(axis=2))   # shadow rays handed to another warp: two shorter chains
     work = (p + s).sum(axis=2)
     print(f"{name} {W}x{H} {tag}: {p.size} lanes, mean steps/lane {float((p + s).mean()):.1f}  ({time.time() - t0:.0f}s)")
-    for label, c in (("fused chain (today)", fused), ("primary | shadow split", split)):
+    for label, c in (("primary + shadow chain", fused),):
         q = np.percentile(c, [50, 90, 99, 99.9, 99.99])
         print(f"   {label:24s} per-batch chain: p50 {q[0]:.0f} p90 {q[1]:.0f} p99 {q[2]:.0f} p99.9 {q[3]:.0f} p99.99 {q[4]:.0f} max {c.max()}")
     eff = work.sum() / (32.0 * fused.sum())
