@@ -84,3 +84,38 @@ def build_edge_case(name):
         fw, fh = (int(x) for x in name[len("tiny_frame_"):].split("x"))
         return scenes.obj_scene("tetrahedron.obj"), scenes.stock_camera(fw, fh), 3
     raise KeyError(name)
+
+
+def random_scene(seed, n_tri=300, w=96, h=64):
+    """Seeded random world for fuzzing: a triangle soup around the origin, a few spheres / quads / cylinders, mixed
+    diffuse / mirror / dielectric / vertex-coloured materials, one to three lights, a camera looking at the cloud."""
+    import numpy as np
+    from realtrace_b200.scene import Camera, Scene, make_materials
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-12, 12, (n_tri, 1, 3))
+    tri = (c + rng.uniform(-2.5, 2.5, (n_tri, 3, 3))).reshape(n_tri, 9).astype(np.float32)
+    mats = make_materials([
+        dict(color=tuple(rng.uniform(0.1, 0.9, 3)), ka=0.2, kd=0.9, ks=0.4),
+        dict(color=tuple(rng.uniform(0.1, 0.9, 3)), ka=0.1, kd=0.7, ks=0.3, kr=float(rng.uniform(0.2, 0.8))),
+        dict(color=(1.0, 1.0, 1.0), ka=0.3, kd=0.9, ks=0.4, kr=0.1, kt=0.8, eta=float(rng.uniform(1.2, 2.0))),
+        dict(color=(0.5, 0.5, 0.5), ka=0.2, kd=1.0, ks=0.4, barycentric=True),
+    ])
+    tri_mat = rng.integers(0, 4, n_tri).astype(np.uint32)
+    n_s, n_p, n_c = (int(x) for x in rng.integers(0, 4, 3))
+    sph = np.concatenate([rng.uniform(-10, 10, (n_s, 3)), rng.uniform(0.8, 3.0, (n_s, 1))], axis=1).astype(np.float32)
+    y0 = float(rng.uniform(-14, -9))
+    pln = np.asarray([[-25, y0 - k, -25, 25, y0 - k, -25, 25, y0 - k, 25, -25, y0 - k, 25] for k in range(n_p)], np.float32).reshape(n_p, 12)
+    cyl = np.concatenate([rng.uniform(-10, 10, (n_c, 3)), rng.uniform(0.4, 1.2, (n_c, 1)),
+                          rng.normal(size=(n_c, 3))], axis=1).astype(np.float32)      # axis not normalised (cylinder.h:17-21)
+    nl = int(rng.integers(1, 4))
+    lights = np.concatenate([rng.uniform(-30, 30, (nl, 3)) + np.asarray([0, 35, 0]), rng.uniform(0.3, 1.0, (nl, 3))], axis=1).astype(np.float32)
+    scene = Scene(tri_v=tri, tri_material=tri_mat, tri_rgb=rng.uniform(0, 1, (n_tri, 9)).astype(np.float32),
+                  sph=sph, sph_material=rng.integers(0, 3, n_s).astype(np.uint32),
+                  pln=pln, pln_material=rng.integers(0, 2, n_p).astype(np.uint32),
+                  cyl=cyl, cyl_material=rng.integers(0, 3, n_c).astype(np.uint32),
+                  materials=mats, lights=lights, ambient=(1.0, 1.0, 1.0), background=(0.1, 0.3, 0.6),
+                  name=f"random{seed}").normalise()
+    eye = rng.normal(size=3)
+    eye = eye / np.linalg.norm(eye) * float(rng.uniform(28, 45))
+    cam = Camera(pos=tuple(float(x) for x in eye), target=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), fovy=45.0, width=w, height=h)
+    return scene, cam, int(rng.integers(1, 6))
