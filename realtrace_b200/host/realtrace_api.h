@@ -79,8 +79,9 @@ public:
     double G() const { return g; }
     double B() const { return b; }
     void clamp() {
-        if (r > 1.0) r = 1.0; if (g > 1.0) g = 1.0; if (b > 1.0) b = 1.0;
-        if (r < 0.0) r = 0.0; if (g < 0.0) g = 0.0; if (b < 0.0) b = 0.0;
+        r = r > 1.0 ? 1.0 : (r < 0.0 ? 0.0 : r);           // color.cpp:19-28
+        g = g > 1.0 ? 1.0 : (g < 0.0 ? 0.0 : g);
+        b = b > 1.0 ? 1.0 : (b < 0.0 ? 0.0 : b);
     }
 };
 inline Color operator*(const Color& c, double f) { return Color(c.r * f, c.g * f, c.b * f); }

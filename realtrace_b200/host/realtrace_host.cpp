@@ -288,8 +288,8 @@ bool read_png(const std::string& path, Image& img) {
 // "normalised" fetch of realtrace_b200/objio.py: texel/255, u -> column, v -> row from the bottom.
 Color texel(const Image& im, double u, double v) {
     int col = (int)std::floor(u * im.w), row = (int)std::floor((1.0 - v) * im.h);
-    if (col < 0) col = 0; if (col >= im.w) col = im.w - 1;
-    if (row < 0) row = 0; if (row >= im.h) row = im.h - 1;
+    col = col < 0 ? 0 : (col >= im.w ? im.w - 1 : col);
+    row = row < 0 ? 0 : (row >= im.h ? im.h - 1 : row);
     const unsigned char* p = &im.px[((size_t)row * im.w + col) * im.ch];
     return Color((double)(float)(p[0] / 255.0f), (double)(float)(p[1] / 255.0f), (double)(float)(p[2] / 255.0f));
 }
