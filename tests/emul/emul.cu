@@ -394,6 +394,42 @@ extern "C" int emul_trace_rays(const oracle_scene* in, int leaf_size, int brute,
     return overflow ? -5 : 0;
 }
 
+// Experiment (round-2 preparation): a nearest-hit walk that takes `switch_after` steps on the binary tree and then
+// continues on the 4-wide view of the same tree with the SAME stack — both views index the same nodes, so a pushed
+// or current node code means the same subtree in either.  Returns per ray the hit and the number of dependent steps.
+extern "C" int emul_hybrid_walk(const oracle_scene* in, int switch_after, const float* rays, uint32_t n, int32_t* prim,
+                                float* t_hit, uint32_t* steps) {
+    EmulScene S;
+    setenv("EMUL_WIDE", "1", 1);
+    build(in, 1, S);
+    unsetenv("EMUL_WIDE");
+    const SceneDev& s = S.dev;
+    bool overflow = false;
+    for (uint32_t k = 0; k < n; k++) {
+        const float* p = rays + 6 * (size_t)k;
+        double x = p[3], y = p[4], z = p[5], l = std::sqrt(x * x + y * y + z * z);
+        RayPrep r = prep_ray(mk3(p[0], p[1], p[2]), mk3((float)(x / l), (float)(y / l), (float)(z / l)));
+        HitRec hit;
+        hit.t = RT_FLT_MAX; hit.prim = RT_MISS; hit.beta = hit.gamma = 0.0f;
+        int stack[RT_STACK_SIZE], sp = 0, node = s.n_bvh_tris > 0 ? 0 : RT_DONE;
+        uint32_t st = 0;
+        while (node != RT_DONE) {
+            if (rt_is_internal(node)) {
+                node = ((int)st >= switch_after) ? bvh4_node_step(s, r, hit.t, node, stack, sp, &overflow)
+                                                 : bvh_node_step(s, r, hit.t, node, stack, sp, &overflow);
+            } else {
+                leaf_test(s, node, r, hit, false, nullptr);
+                node = sp ? stack[--sp] : RT_DONE;
+            }
+            st++;
+        }
+        prim[k] = hit.prim;
+        t_hit[k] = hit.t;
+        steps[k] = st;
+    }
+    return overflow ? -5 : 0;
+}
+
 // BVH introspection for structure checks: returns node count; copies nodes (16 floats each) and order.
 extern "C" int emul_bvh(const oracle_scene* in, int leaf_size, float* nodes, uint32_t* order, uint64_t* keys, uint32_t* n_bvh) {
     EmulScene S;

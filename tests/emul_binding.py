@@ -69,6 +69,20 @@ class Emulation:
         assert rc == 0, rc
         return (nodes, tris, shadow) if shadows else (nodes, tris)
 
+    def hybrid_walk(self, scene, rays, switch_after):
+        """Nearest hits of a walk that switches from the binary tree to its 4-wide view after `switch_after` steps
+        (same stack).  -> (prim code, t, dependent steps) per ray."""
+        s, keep = ob._scene_struct(scene)
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        prim = np.zeros(len(rays), np.int32)
+        t = np.zeros(len(rays), np.float32)
+        steps = np.zeros(len(rays), np.uint32)
+        self.lib.emul_hybrid_walk.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32] + [C.c_void_p] * 3
+        rc = self.lib.emul_hybrid_walk(C.byref(s), switch_after, rays.ctypes.data, len(rays), prim.ctypes.data,
+                                       t.ctypes.data, steps.ctypes.data)
+        assert rc == 0, rc
+        return prim, t, steps
+
     def bvh(self, scene, leaf=4):
         s, keep = ob._scene_struct(scene)
         n = len(scene.tri_v)

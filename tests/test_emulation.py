@@ -66,6 +66,21 @@ def test_emulated_random_worlds_match_the_reference(emul, port_oracle, seed):
     parity.assert_parity(m, f"random world {seed}")
 
 
+@pytest.mark.parametrize("switch_after", [0, 7, 40])
+def test_binary_and_wide_views_are_interchangeable_mid_ray(emul, switch_after):
+    """The 4-wide view (k_collapse4) indexes the same nodes as the binary tree, so a ray may change views at any
+    step and keep its stack: hits are bit-identical, the number of dependent steps drops."""
+    scene, _, _, _ = build_case("blubmixed_d5")
+    rng = np.random.default_rng(11)
+    o = rng.uniform(-40, 40, (4000, 3))
+    rays = np.concatenate([o, rng.uniform(-8, 8, (4000, 3)) - o], axis=1).astype(np.float32)
+    p0, t0, s0 = emul.hybrid_walk(scene, rays, 1 << 30)          # binary all the way
+    p1, t1, s1 = emul.hybrid_walk(scene, rays, switch_after)
+    assert np.array_equal(p0, p1) and np.array_equal(t0, t1)
+    assert (p0 >= 0).sum() > 300
+    assert s1.sum() < s0.sum() and s1.max() <= s0.max()
+
+
 def test_emulated_bvh_equals_brute_force(emul):
     scene, cam, depth, _ = build_case("bobtex_d3")
     a = emul.render(scene, cam, depth)
