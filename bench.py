@@ -508,7 +508,9 @@ def run_gpu_arm(args):
                        "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"},
             "e2e": {"value": main["e2e_value"], "unit": "Mrays/s", "ms_per_step": main["e2e_ms_per_step"],
                     "h2d_bytes_per_step": 64 + 24, "d2h_bytes_per_step": cam.width * cam.height * 3,
-                    "what": "rt_render: camera + params in, RGB8 frame into pinned host memory (scene resident)"},
+                    "what": ("rt_render: camera + params in, RGB8 frame into pinned host memory (scene resident)" if world == 1 else
+                             "per frame and rank: render its tiles + push into rank 0's frame + handshake, synchronised; "
+                             "rank 0 then copies the assembled RGB8 frame into pinned host memory (wall clock, max over ranks)")},
             "gpu_launches": main["launches"], "clocks": main["clocks"],
             **({"frame_check": main["frame_check"]} if main.get("frame_check") is not None else {}),
             "host_enqueue_ms_per_step": main["host_enqueue_ms_per_step"],
