@@ -73,7 +73,8 @@ int rt_create(rt_ctx** out, int device) {
         env_int("RT_REFILL_QUEUE", 1, 32, c->refill_queue);
         env_int("RT_REFILL_SHADOW", 1, 32, c->refill_shadow);
         env_int("RT_BLOCKS_PER_SM", 1, 32, c->blocks_per_sm);
-        env_int("RT_WIDE_BVH", 0, 2, c->wide_bvh);
+        env_int("RT_WIDE_BVH", 0, 3, c->wide_bvh);
+        env_int("RT_HYBRID_AFTER", 0, 100000, c->hybrid_after);
         env_int("RT_FUSE_SHADOW", 0, 1, c->fuse_shadow);
         env_int("RT_FUSE_SHADE", 0, 2, c->fuse_shade);
         env_int("RT_TILE_BUCKET_BITS", 0, 8, c->tile_bucket_bits);

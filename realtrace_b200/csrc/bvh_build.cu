@@ -300,7 +300,7 @@ static void upload_static_scene(rt_ctx* c) {
 static void publish_scene(rt_ctx* c) {
     SceneDev& s = c->scene;
     s.nodes = c->d_nodes.p;
-    s.nodes4 = (((c->wide_bvh == 1 && c->has_reflective) || c->wide_bvh == 2) && c->n_bvh >= 1) ? c->d_nodes4.p : nullptr;
+    s.nodes4 = (((c->wide_bvh == 1 && c->has_reflective) || c->wide_bvh >= 2) && c->n_bvh >= 1) ? c->d_nodes4.p : nullptr;
     s.tris = c->d_tris.p;
     s.tri_rgb = c->h_tri_rgb.empty() ? nullptr : c->d_tri_rgb.p;
     s.analytic = c->d_analytic.p;
@@ -342,7 +342,7 @@ static void run_refit(rt_ctx* c) {
     }
     // the 4-wide view serves k_paths (latency-bound bounce paths; mode 1, only built when something reflects)
     // or every fused walk (mode 2)
-    if (((c->wide_bvh == 1 && c->has_reflective) || c->wide_bvh == 2) && nb >= 1) {
+    if (((c->wide_bvh == 1 && c->has_reflective) || c->wide_bvh >= 2) && nb >= 1) {
         int nn = nb >= 2 ? (int)nb - 1 : 1;
         c->d_nodes4.reserve(RT_NODE4_FLOAT4S * (size_t)nn);
         k_collapse4<<<blocks_for((uint32_t)nn), TPB, 0, st>>>(c->d_nodes.p, nn, c->d_nodes4.p);

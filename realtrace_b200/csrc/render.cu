@@ -187,6 +187,7 @@ struct TravArgs {
     WaveCounters* next;       // SHADE: their counter
     int max_depth;            // SHADE
     int remote_out;           // SHADE: direct_rgb is another GPU's frame (informational: same code path)
+    int hybrid_after;         // WIDE == 2: steps a ray takes on the binary tree before it continues on the 4-wide view
 };
 
 // Appends the bounce rays of this warp's shaded hits to the next wave's queue: exclusive prefix over the
@@ -271,8 +272,12 @@ __device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uin
 // the shadow ray(s) of that hit (one per light, same walk with early exit) and only then emits the
 // hit together with its occlusion bits.  One kernel and one tail per wave instead of two, no second
 // derivation of the hit point, and lanes whose rays missed keep pulling new rays meanwhile.
-// WIDE: walk the 4-wide view of the tree (SceneDev::nodes4); a template parameter so that the binary walk
-// keeps its register budget (72 vs 96 registers with both compiled in).
+// WIDE = 1: walk the 4-wide view of the tree (SceneDev::nodes4); a template parameter so that the binary walk
+// keeps its register budget.  WIDE = 2 (EXPERIMENTAL, RT_WIDE_BVH=3): hybrid — a ray starts on the binary tree
+// and continues on the 4-wide view, with the same stack, once it has taken more than hybrid_after steps: both
+// views index the same nodes, so hits are bit-identical (tests/test_emulation.py), the bulk of the rays never
+// leaves the cheaper binary step, and the longest dependency chains lose a third of their steps
+// (profiles/r1_tuning.md section 15).  80 registers.
 // SHADE (fused primary rays, whole-batch refill): the hit is not queued for k_shade either.  A lane keeps its
 // hit and occlusion bits until the warp's 32-pixel batch is done, then the warp shades all its hits together
 // (World::shade_ray, world.cpp:32-111, same shade_hit as k_shade), writes the pixels and queues the bounce
@@ -280,11 +285,12 @@ __device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uin
 #ifndef RT_SHADE_FUSED_MIN_BLOCKS
 #define RT_SHADE_FUSED_MIN_BLOCKS 7     // SHADE: hold the kernel to the traversal loop's 72 registers (the once-per-batch shading spills)
 #endif
-template <int MODE, bool COUNT, bool FUSE, bool WIDE = false, bool SHADE = false>
-__global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 0) k_traverse(const __grid_constant__ TravArgs a) {
+template <int MODE, bool COUNT, bool FUSE, int WIDE = 0, bool SHADE = false>
+__global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : (WIDE == 2 ? 6 : 0)) k_traverse(const __grid_constant__ TravArgs a) {
     constexpr bool ANY = MODE == MODE_SHADOW;
     static_assert(!(FUSE && ANY), "FUSE applies to the nearest-hit modes");
     static_assert(!WIDE || FUSE, "the wide walk is instantiated for the fused kernels only");
+    static_assert(WIDE >= 0 && WIDE <= 2, "WIDE: 0 binary walk, 1 4-wide view, 2 hybrid");
     static_assert(!SHADE || (FUSE && MODE == MODE_PRIMARY), "in-kernel shading is for the fused primary wave");
     __shared__ float s_pdir[SHADE ? 3 * TRAV_TPB : 1];   // SHADE: primary direction of the lane's pending hit
     const unsigned FULL = 0xffffffffu;
@@ -322,6 +328,7 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
     nh.t = RT_FLT_MAX; nh.prim = RT_MISS; nh.beta = nh.gamma = 0.0f;
     f3 P = mk3(0, 0, 0);
     uint32_t occl_mask = 0;
+    int ray_steps = 0;                     // WIDE == 2: steps of the current ray (primary or shadow)
     bool pending = false, qfull = false;   // SHADE: this lane's hit waits for the end of the batch
     uint32_t px_rgb = 0;                   // SHADE, RGB8 output: the lane's finished pixel, stored with its 8x4 block
     bool px_have = false;
@@ -333,6 +340,7 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
         found = false;
         sp = 0;
         node = (use_bvh && sd.x == sd.x && sd.y == sd.y && sd.z == sd.z) ? 0 : RT_DONE;
+        ray_steps = 0;
         traced_shadow++;
     };
 
@@ -453,6 +461,7 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
                     active = true;
                     phase = -1;
                     sp = 0;
+                    ray_steps = 0;
                     // a NaN direction (ignored refract() failure, world.cpp:83) misses everything
                     bool finite = d.x == d.x && d.y == d.y && d.z == d.z;
                     r = prep_ray(o, d);
@@ -475,10 +484,13 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
             if (a.loop_style == 0) {
                 while (rt_is_internal(node)) {
                     if (COUNT) wcp->nodes++;
-                    node = WIDE ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
-                                 : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
+                    if (WIDE == 2) ray_steps++;
+                    node = (WIDE == 1 || (WIDE == 2 && ray_steps > a.hybrid_after))
+                               ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
+                               : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                 }
                 while (node < 0) {
+                    if (WIDE == 2) ray_steps++;
                     if (leaf_test(a.s, node, r, hit, any, wcp)) {
                         found = true;
                         if (any) { node = RT_DONE; break; }
@@ -489,10 +501,12 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
                 // "if-if": every lane advances one step of whatever kind per iteration, for a bounded
                 // number of iterations before the warp looks at its refill state again
                 for (int it = 0; it < a.loop_style && node != RT_DONE; it++) {
+                    if (WIDE == 2) ray_steps++;
                     if (rt_is_internal(node)) {
                         if (COUNT) wcp->nodes++;
-                        node = WIDE ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
-                                 : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
+                        node = (WIDE == 1 || (WIDE == 2 && ray_steps > a.hybrid_after))
+                                   ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
+                                   : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                     } else {
                         if (leaf_test(a.s, node, r, hit, any, wcp)) {
                             found = true;
@@ -1231,13 +1245,18 @@ template <int MODE, bool FUSE, bool SHADE = false>
 void launch_traverse(rt_ctx* c, const TravArgs& a, bool count) {
     int blocks = MODE == MODE_SHADOW ? c->shadow_blocks : (FUSE ? (SHADE ? c->fused_shade_blocks : c->fused_blocks) : c->trace_blocks);
     if (FUSE && a.s.nodes4 != nullptr && c->wide_bvh == 2) {
-        constexpr bool W = FUSE;   // only the fused kernels have a wide instantiation
+        constexpr int W = FUSE ? 1 : 0;   // only the fused kernels have a wide instantiation
         blocks = SHADE ? c->wide_shade_blocks : c->wide_blocks;
         if (count) k_traverse<MODE, true, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
         else k_traverse<MODE, false, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+    } else if (FUSE && a.s.nodes4 != nullptr && c->wide_bvh == 3) {
+        constexpr int W = FUSE ? 2 : 0;   // experimental hybrid walk
+        blocks = SHADE ? c->hybrid_shade_blocks : c->hybrid_blocks;
+        if (count) k_traverse<MODE, true, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+        else k_traverse<MODE, false, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
     } else {
-        if (count) k_traverse<MODE, true, FUSE, false, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
-        else k_traverse<MODE, false, FUSE, false, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+        if (count) k_traverse<MODE, true, FUSE, 0, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
+        else k_traverse<MODE, false, FUSE, 0, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
     }
     RT_CUDA(cudaGetLastError());
 }
@@ -1401,10 +1420,13 @@ void rt_render_init(rt_ctx* c) {
     c->shadow_blocks = persistent_blocks(k_traverse<MODE_SHADOW, false, false>, TRAV_TPB, c->sm_count);
     c->path_blocks = persistent_blocks(k_paths<false>, TRAV_TPB, c->sm_count);
     c->path_wide_blocks = persistent_blocks(k_paths<false, true>, TRAV_TPB, c->sm_count);
-    c->wide_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false, true, true>, TRAV_TPB, c->sm_count),
-                        persistent_blocks(k_traverse<MODE_QUEUE, false, true, true>, TRAV_TPB, c->sm_count));
-    c->fused_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, false, true>, TRAV_TPB, c->sm_count);
-    c->wide_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, true, true>, TRAV_TPB, c->sm_count);
+    c->wide_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false, true, 1>, TRAV_TPB, c->sm_count),
+                        persistent_blocks(k_traverse<MODE_QUEUE, false, true, 1>, TRAV_TPB, c->sm_count));
+    c->fused_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, 0, true>, TRAV_TPB, c->sm_count);
+    c->wide_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, 1, true>, TRAV_TPB, c->sm_count);
+    c->hybrid_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false, true, 2>, TRAV_TPB, c->sm_count),
+                          persistent_blocks(k_traverse<MODE_QUEUE, false, true, 2>, TRAV_TPB, c->sm_count));
+    c->hybrid_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, 2, true>, TRAV_TPB, c->sm_count);
     c->shade_blocks = lo(persistent_blocks(k_shade<true>, SHADE_TPB, c->sm_count),
                          persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
     if (c->blocks_per_sm > 0) {   // RT_BLOCKS_PER_SM: cap the persistent grids (tuning)
@@ -1447,6 +1469,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     ta.aux_t = aux_dev ? aux_dev->t : nullptr;
     ta.brute = (p->flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
     ta.cap = (uint32_t)c->queue_cap;
+    ta.hybrid_after = c->hybrid_after;
     ShadeArgs sa;
     memset(&sa, 0, sizeof sa);
     sa.s = c->scene; sa.cam = ta.cam; sa.f = f;
@@ -1456,7 +1479,8 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
 
     if (p->flags & RT_FLAG_WARP_TIMES) {
         int mb = c->trace_blocks;
-        for (int b : {c->fused_blocks, c->fused_shade_blocks, c->wide_blocks, c->wide_shade_blocks}) mb = b > mb ? b : mb;
+        for (int b : {c->fused_blocks, c->fused_shade_blocks, c->wide_blocks, c->wide_shade_blocks, c->hybrid_blocks, c->hybrid_shade_blocks})
+            mb = b > mb ? b : mb;
         c->d_warp_times.reserve(2 * (size_t)mb * (TRAV_TPB / 32));
         ta.warp_times = c->d_warp_times.p;
     }
@@ -1590,6 +1614,7 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
     ta.aux_prim = c->d_aux_prim.p; ta.aux_t = c->d_aux_t.p;
     ta.brute = (flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
     ta.cap = (uint32_t)cap;
+    ta.hybrid_after = c->hybrid_after;
     ShadeArgs sa;
     memset(&sa, 0, sizeof sa);
     sa.s = c->scene; sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.accum = c->d_accum.p;

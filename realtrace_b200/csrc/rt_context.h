@@ -116,7 +116,7 @@ struct rt_ctx {
     DevBuf<float> d_tri_v;
     DevBuf<uint32_t> d_tri_mat, d_tri_obj;
     DevBuf<float4> d_tri_rgb, d_tris, d_nodes, d_nodes4, d_box_lo, d_box_hi, d_materials, d_lights;
-    int wide_bvh = 1;                      // 4-wide collapse of the tree: 0 off, 1 for k_paths (bounce paths), 2 everywhere (RT_WIDE_BVH)
+    int wide_bvh = 1;                      // 4-wide collapse of the tree: 0 off, 1 for k_paths (bounce paths), 2 everywhere, 3 k_paths + hybrid walk in k_traverse (experimental) (RT_WIDE_BVH)
     DevBuf<AnalyticPrim> d_analytic;
     DevBuf<uint64_t> d_keys[2];
     DevBuf<uint32_t> d_vals[2];
@@ -162,6 +162,8 @@ struct rt_ctx {
     bool refit_pending = false;
     int trace_blocks = 0, fused_blocks = 0, shadow_blocks = 0, shade_blocks = 0, path_blocks = 0;
     int wide_blocks = 0, path_wide_blocks = 0, fused_shade_blocks = 0, wide_shade_blocks = 0;
+    int hybrid_blocks = 0, hybrid_shade_blocks = 0;
+    int hybrid_after = 32;                 // RT_WIDE_BVH=3 (experimental): binary steps before a ray moves to the 4-wide view (RT_HYBRID_AFTER)
     int tile_bucket_bits = 5;              // heavy-tiles-first: mantissa bits of the cost kept in the sort key (RT_TILE_BUCKET_BITS)
     int fuse_shade = 1;                    // primary hits shaded inside the fused traversal kernel (RT_FUSE_SHADE): 0 never,
                                            // 1 when that kernel also pushes finished tiles to a remote frame, 2 always

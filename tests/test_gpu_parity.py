@@ -71,6 +71,25 @@ def test_edge_cases_through_the_abi(oracle, name):
         assert (prim == -1).all() and st["rays_shadow"] == 0
 
 
+@pytest.mark.skipif(not os.environ.get("RT_TEST_EXPERIMENTAL"), reason="experimental knobs: set RT_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("after", ["0", "8", "32"])
+@pytest.mark.parametrize("name", ["synth_small_d1", "blubmixed_d5", "bobtex_d3"])
+def test_experimental_hybrid_walk(oracle, name, after, monkeypatch):
+    """RT_WIDE_BVH=3 (not a default, prepared for the next round): rays move from the binary tree to its 4-wide
+    view after RT_HYBRID_AFTER steps.  The emulation shows bit-identical hits (test_emulation.py); here the frames
+    must equal the default walk's."""
+    scene, cam, depth, _ = build_case(name)
+    ctx = make_ctx(scene)
+    want = ctx.render(cam, depth, aux=True)
+    ctx.close()
+    monkeypatch.setenv("RT_WIDE_BVH", "3")
+    monkeypatch.setenv("RT_HYBRID_AFTER", after)
+    ctx = make_ctx(scene)
+    got = ctx.render(cam, depth, aux=True)
+    ctx.close()
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0])
+
+
 def test_kat_rays_through_the_abi():
     g = np.load(os.path.join(GOLDEN, "kat_rays.npz"))
     names, rays = kat.kat_rays()
