@@ -430,6 +430,110 @@ extern "C" int emul_hybrid_walk(const oracle_scene* in, int switch_after, const 
     return overflow ? -5 : 0;
 }
 
+// Analysis (round-2 preparation): SIMD efficiency of one warp = one 8x4 pixel block under different loop
+// structures, from the exact step sequences (N = node step, L = leaf test) of its 32 primary rays and their shadow
+// rays (walked one after the other by the same lane, like the fused kernel).  out[policy][0..3] = executions of the
+// node branch, of the leaf branch, lane-steps spent in node steps, lane-steps spent in leaf tests.
+//   policy 0: if-if — per iteration every live lane takes its next step; the warp issues the node branch if any lane
+//             is at a node and the leaf branch if any lane is at a leaf (the shipped loop)
+//   policy 1: while-while — all lanes run node steps until each has reached a leaf (or finished), then all run leaf
+//             tests until each is back at a node
+//   policy 2: if-if with the leaf branch postponed until at least `quorum` lanes wait at a leaf (or nobody can take a
+//             node step)
+static void step_sequence(const SceneDev& s, f3 o, f3 d, bool any_hit, std::vector<uint8_t>& seq, HitRec& hit, bool& found) {
+    RayPrep r = prep_ray(o, d);
+    hit.t = RT_FLT_MAX; hit.prim = RT_MISS; hit.beta = hit.gamma = 0.0f;
+    found = false;
+    bool overflow = false;
+    int stack[RT_STACK_SIZE], sp = 0, node = s.n_bvh_tris > 0 ? 0 : RT_DONE;
+    while (node != RT_DONE) {
+        if (rt_is_internal(node)) { seq.push_back(0); node = bvh_node_step(s, r, hit.t, node, stack, sp, &overflow); }
+        else {
+            seq.push_back(1);
+            if (leaf_test(s, node, r, hit, any_hit, nullptr)) { found = true; if (any_hit) break; }
+            node = sp ? stack[--sp] : RT_DONE;
+        }
+    }
+    for (int k = 0; k < s.n_analytic && !(any_hit && found); k++) {
+        const AnalyticPrim p = s.analytic[k];
+        if (analytic_test(p, o, d, hit.t, hit.beta, hit.gamma)) { hit.prim = rt_analytic_code(k); found = true; }
+    }
+}
+extern "C" int emul_simd_model(const oracle_scene* in, const rt_camera* cam, int quorum, double* out /*3 x 4*/) {
+    EmulScene S;
+    build(in, 1, S);
+    const SceneDev& s = S.dev;
+    const int W = cam->width, H = cam->height;
+    for (int k = 0; k < 12; k++) out[k] = 0.0;
+    std::vector<uint8_t> seq[32];
+    f3 o = mk3(cam->pos[0], cam->pos[1], cam->pos[2]);
+    for (int by = 0; by + 4 <= H; by += 4)
+        for (int bx = 0; bx + 8 <= W; bx += 8) {
+            for (int l = 0; l < 32; l++) {
+                int i = bx + (l & 7), j = by + (l >> 3);
+                seq[l].clear();
+                float xw = (float)((double)cam->aspect * (i - W / 2.0 + 0.5) / W), yw = (float)((j - H / 2.0 + 0.5) / H);
+                double dd[3];
+                for (int k = 0; k < 3; k++) dd[k] = -(double)cam->w[k] * (double)cam->focal_distance + (double)cam->u[k] * (double)xw + (double)cam->v[k] * (double)yw;
+                double len = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+                f3 d = mk3((float)(dd[0] / len), (float)(dd[1] / len), (float)(dd[2] / len));
+                HitRec h; bool found;
+                step_sequence(s, o, d, false, seq[l], h, found);
+                if (found)
+                    for (int li = 0; li < s.n_lights; li++) {
+                        f3 P = fma3(d, h.t, o), toL = mk3(s.lights[2 * li]) - P;
+                        HitRec sh; bool sf;
+                        step_sequence(s, fma3(toL, 0.01f, P), normalize(toL), true, seq[l], sh, sf);
+                    }
+            }
+            size_t pos[32];
+            // policy 0: if-if
+            for (int l = 0; l < 32; l++) pos[l] = 0;
+            for (;;) {
+                int nn = 0, nl = 0;
+                for (int l = 0; l < 32; l++) if (pos[l] < seq[l].size()) { if (seq[l][pos[l]]) nl++; else nn++; }
+                if (!nn && !nl) break;
+                if (nn) { out[0] += 1; out[2] += nn; }
+                if (nl) { out[1] += 1; out[3] += nl; }
+                for (int l = 0; l < 32; l++) if (pos[l] < seq[l].size()) pos[l]++;
+            }
+            // policy 1: while-while
+            for (int l = 0; l < 32; l++) pos[l] = 0;
+            for (;;) {
+                bool any = false;
+                for (;;) {   // node phase
+                    int nn = 0;
+                    for (int l = 0; l < 32; l++) if (pos[l] < seq[l].size() && seq[l][pos[l]] == 0) { nn++; pos[l]++; }
+                    if (!nn) break;
+                    out[4] += 1; out[6] += nn; any = true;
+                }
+                for (;;) {   // leaf phase
+                    int nl = 0;
+                    for (int l = 0; l < 32; l++) if (pos[l] < seq[l].size() && seq[l][pos[l]] == 1) { nl++; pos[l]++; }
+                    if (!nl) break;
+                    out[5] += 1; out[7] += nl; any = true;
+                }
+                if (!any) break;
+            }
+            // policy 2: if-if, leaf branch waits for a quorum
+            for (int l = 0; l < 32; l++) pos[l] = 0;
+            for (;;) {
+                int nn = 0, nl = 0;
+                for (int l = 0; l < 32; l++) if (pos[l] < seq[l].size()) { if (seq[l][pos[l]]) nl++; else nn++; }
+                if (!nn && !nl) break;
+                if (nn) {
+                    out[8] += 1; out[10] += nn;
+                    for (int l = 0; l < 32; l++) if (pos[l] < seq[l].size() && seq[l][pos[l]] == 0) pos[l]++;
+                }
+                if (nl && (nl >= quorum || !nn)) {
+                    out[9] += 1; out[11] += nl;
+                    for (int l = 0; l < 32; l++) if (pos[l] < seq[l].size() && seq[l][pos[l]] == 1) pos[l]++;
+                }
+            }
+        }
+    return 0;
+}
+
 // BVH introspection for structure checks: returns node count; copies nodes (16 floats each) and order.
 extern "C" int emul_bvh(const oracle_scene* in, int leaf_size, float* nodes, uint32_t* order, uint64_t* keys, uint32_t* n_bvh) {
     EmulScene S;
