@@ -459,6 +459,100 @@ static void step_sequence(const SceneDev& s, f3 o, f3 d, bool any_hit, std::vect
         if (analytic_test(p, o, d, hit.t, hit.beta, hit.gamma)) { hit.prim = rt_analytic_code(k); found = true; }
     }
 }
+// Variant walk for the model: leaf children are tested inside the node step that finds their box hit ("eager
+// leaves"; only internal nodes are ever pushed).  seq gets one entry per iteration: the number of triangle tests
+// made in it (0, 1 or 2).  Nearest hits must equal the shipped walk's.
+static void eager_sequence(const SceneDev& s, f3 o, f3 d, bool any_hit, std::vector<uint8_t>& seq, HitRec& hit, bool& found) {
+    RayPrep r = prep_ray(o, d);
+    hit.t = RT_FLT_MAX; hit.prim = RT_MISS; hit.beta = hit.gamma = 0.0f;
+    found = false;
+    int stack[RT_STACK_SIZE], sp = 0, node = s.n_bvh_tris > 1 ? 0 : RT_DONE;
+    if (s.n_bvh_tris == 1) {   // single-leaf tree: the root record holds the leaf
+        seq.push_back(1);
+        if (leaf_test(s, (int)as_uint(s.nodes[3].x), r, hit, any_hit, nullptr)) found = true;
+    }
+    while (node != RT_DONE) {
+        const float4* n = s.nodes + RT_NODE_FLOAT4S * (size_t)node;
+        float4 n0 = n[0], n1 = n[1], n2 = n[2], n3 = n[3];
+        float t0, t1;
+        bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, r, hit.t, t0);
+        bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, r, hit.t, t1);
+        int c0 = (int)as_uint(n3.x), c1 = (int)as_uint(n3.y);
+        if (h0 && h1 && t1 < t0) { int tc = c0; c0 = c1; c1 = tc; float tt = t0; t0 = t1; t1 = tt; }
+        else if (!h0 && h1) { c0 = c1; t0 = t1; h0 = true; h1 = false; }
+        uint8_t tests = 0;
+        int next_a = RT_DONE, next_b = RT_DONE;     // internal children still to visit, near first
+        bool stop = false;
+        if (h0) {
+            if (c0 < 0) { tests++; if (leaf_test(s, c0, r, hit, any_hit, nullptr)) { found = true; stop = any_hit; } }
+            else next_a = c0;
+        }
+        if (h1 && !stop && t1 <= hit.t) {
+            if (c1 < 0) { tests++; if (leaf_test(s, c1, r, hit, any_hit, nullptr)) { found = true; stop = any_hit; } }
+            else { if (next_a == RT_DONE) next_a = c1; else next_b = c1; }
+        }
+        seq.push_back(tests);
+        if (stop) break;
+        if (next_a != RT_DONE) { if (next_b != RT_DONE && sp < RT_STACK_SIZE) stack[sp++] = next_b; node = next_a; }
+        else node = sp ? stack[--sp] : RT_DONE;
+    }
+    for (int k = 0; k < s.n_analytic && !(any_hit && found); k++) {
+        const AnalyticPrim p = s.analytic[k];
+        if (analytic_test(p, o, d, hit.t, hit.beta, hit.gamma)) { hit.prim = rt_analytic_code(k); found = true; }
+    }
+}
+// out: [0] iterations (warp), [1] leaf sub-branch executions, [2] lane-iterations, [3] lane-tests, [4] rays whose
+// nearest hit differs from the shipped walk's, [5] rays, [6] longest lane chain (iterations), [7] triangle tests of the
+// shipped walk for comparison
+extern "C" int emul_simd_model_eager(const oracle_scene* in, const rt_camera* cam, double* out /*8*/) {
+    EmulScene S;
+    build(in, 1, S);
+    const SceneDev& s = S.dev;
+    const int W = cam->width, H = cam->height;
+    for (int k = 0; k < 8; k++) out[k] = 0.0;
+    std::vector<uint8_t> seq[32], ref;
+    f3 o = mk3(cam->pos[0], cam->pos[1], cam->pos[2]);
+    for (int by = 0; by + 4 <= H; by += 4)
+        for (int bx = 0; bx + 8 <= W; bx += 8) {
+            for (int l = 0; l < 32; l++) {
+                int i = bx + (l & 7), j = by + (l >> 3);
+                seq[l].clear();
+                float xw = (float)((double)cam->aspect * (i - W / 2.0 + 0.5) / W), yw = (float)((j - H / 2.0 + 0.5) / H);
+                double dd[3];
+                for (int k = 0; k < 3; k++) dd[k] = -(double)cam->w[k] * (double)cam->focal_distance + (double)cam->u[k] * (double)xw + (double)cam->v[k] * (double)yw;
+                double len = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+                f3 d = mk3((float)(dd[0] / len), (float)(dd[1] / len), (float)(dd[2] / len));
+                HitRec h, h2; bool found, f2;
+                eager_sequence(s, o, d, false, seq[l], h, found);
+                ref.clear();
+                step_sequence(s, o, d, false, ref, h2, f2);
+                for (uint8_t v : ref) out[7] += v;
+                out[5] += 1;
+                if (found != f2 || (found && (h.prim != h2.prim || h.t != h2.t))) out[4] += 1;
+                if (found)
+                    for (int li = 0; li < s.n_lights; li++) {
+                        f3 P = fma3(d, h.t, o), toL = mk3(s.lights[2 * li]) - P;
+                        HitRec sh; bool sf;
+                        eager_sequence(s, fma3(toL, 0.01f, P), normalize(toL), true, seq[l], sh, sf);
+                        ref.clear();
+                        step_sequence(s, fma3(toL, 0.01f, P), normalize(toL), true, ref, h2, f2);
+                        for (uint8_t v : ref) out[7] += v;
+                        if (sf != f2) out[4] += 1;
+                    }
+            }
+            size_t maxlen = 0;
+            for (int l = 0; l < 32; l++) { maxlen = std::max(maxlen, seq[l].size()); out[2] += (double)seq[l].size(); for (uint8_t v : seq[l]) out[3] += v; }
+            out[6] = std::max(out[6], (double)maxlen);
+            for (size_t it = 0; it < maxlen; it++) {
+                int mt = 0;
+                for (int l = 0; l < 32; l++) if (it < seq[l].size()) mt = std::max(mt, (int)seq[l][it]);
+                out[0] += 1;
+                out[1] += mt;
+            }
+        }
+    return 0;
+}
+
 extern "C" int emul_simd_model(const oracle_scene* in, const rt_camera* cam, int quorum, double* out /*3 x 4*/) {
     EmulScene S;
     build(in, 1, S);
