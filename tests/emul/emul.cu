@@ -561,10 +561,11 @@ extern "C" int emul_simd_model(const oracle_scene* in, const rt_camera* cam, int
     for (int k = 0; k < 12; k++) out[k] = 0.0;
     std::vector<uint8_t> seq[32];
     f3 o = mk3(cam->pos[0], cam->pos[1], cam->pos[2]);
-    for (int by = 0; by + 4 <= H; by += 4)
-        for (int bx = 0; bx + 8 <= W; bx += 8) {
+    const int bw = getenv("EMUL_BLOCK_W") ? atoi(getenv("EMUL_BLOCK_W")) : 8, bh = 32 / bw;   // pixel block of a warp
+    for (int by = 0; by + bh <= H; by += bh)
+        for (int bx = 0; bx + bw <= W; bx += bw) {
             for (int l = 0; l < 32; l++) {
-                int i = bx + (l & 7), j = by + (l >> 3);
+                int i = bx + (l % bw), j = by + (l / bw);
                 seq[l].clear();
                 float xw = (float)((double)cam->aspect * (i - W / 2.0 + 0.5) / W), yw = (float)((j - H / 2.0 + 0.5) / H);
                 double dd[3];
