@@ -553,6 +553,61 @@ extern "C" int emul_simd_model_eager(const oracle_scene* in, const rt_camera* ca
     return 0;
 }
 
+// Refill policy model: ONE warp works through the whole frame (8x4 blocks in raster order, fused primary + shadow
+// sequences per ray, if-if loop); idle lanes take the next rays of the stream as soon as at least `threshold` lanes
+// are idle (32 = whole batches, the shipped setting for primary rays).  out: [0] node-branch executions, [1]
+// leaf-branch executions, [2] refill events, [3] lane-steps.
+extern "C" int emul_simd_refill_model(const oracle_scene* in, const rt_camera* cam, int threshold, double* out /*4*/) {
+    EmulScene S;
+    build(in, 1, S);
+    const SceneDev& s = S.dev;
+    const int W = cam->width, H = cam->height;
+    for (int k = 0; k < 4; k++) out[k] = 0.0;
+    f3 o = mk3(cam->pos[0], cam->pos[1], cam->pos[2]);
+    std::vector<uint8_t> seq[32];
+    size_t pos[32];
+    for (int l = 0; l < 32; l++) pos[l] = 0;
+    // the stream: pixel k of the frame in 8x4-block raster order
+    const int bxn = W / 8, byn = H / 4;
+    const long total = (long)bxn * byn * 32;
+    long next = 0;
+    auto fetch = [&](int l) {
+        long k = next++;
+        long b = k / 32; int q = (int)(k % 32);
+        int i = (int)(b % bxn) * 8 + (q & 7), j = (int)(b / bxn) * 4 + (q >> 3);
+        seq[l].clear(); pos[l] = 0;
+        float xw = (float)((double)cam->aspect * (i - W / 2.0 + 0.5) / W), yw = (float)((j - H / 2.0 + 0.5) / H);
+        double dd[3];
+        for (int c = 0; c < 3; c++) dd[c] = -(double)cam->w[c] * (double)cam->focal_distance + (double)cam->u[c] * (double)xw + (double)cam->v[c] * (double)yw;
+        double len = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+        f3 d = mk3((float)(dd[0] / len), (float)(dd[1] / len), (float)(dd[2] / len));
+        HitRec h; bool found;
+        step_sequence(s, o, d, false, seq[l], h, found);
+        if (found)
+            for (int li = 0; li < s.n_lights; li++) {
+                f3 P = fma3(d, h.t, o), toL = mk3(s.lights[2 * li]) - P;
+                HitRec sh; bool sf;
+                step_sequence(s, fma3(toL, 0.01f, P), normalize(toL), true, seq[l], sh, sf);
+            }
+    };
+    for (;;) {
+        int idle = 0;
+        for (int l = 0; l < 32; l++) if (pos[l] >= seq[l].size()) idle++;
+        if (next < total && (idle >= threshold || idle == 32)) {
+            out[2] += 1;
+            for (int l = 0; l < 32 && next < total; l++) if (pos[l] >= seq[l].size()) fetch(l);
+        }
+        int nn = 0, nl = 0;
+        for (int l = 0; l < 32; l++) if (pos[l] < seq[l].size()) { if (seq[l][pos[l]]) nl++; else nn++; }
+        if (!nn && !nl) { if (next >= total) break; continue; }
+        if (nn) out[0] += 1;
+        if (nl) out[1] += 1;
+        out[3] += nn + nl;
+        for (int l = 0; l < 32; l++) if (pos[l] < seq[l].size()) pos[l]++;
+    }
+    return 0;
+}
+
 extern "C" int emul_simd_model(const oracle_scene* in, const rt_camera* cam, int quorum, double* out /*3 x 4*/) {
     EmulScene S;
     build(in, 1, S);
