@@ -126,7 +126,22 @@ typedef struct rt_build_stats {
 /* ---- life cycle -------------------------------------------------------------------------- */
 /* device: CUDA ordinal.  Replaces nothing in the reference (single-threaded CPU code).        */
 int rt_create(rt_ctx** out, int device);
+/* One context that drives n_devices GPUs from the calling thread (one rt_ctx per process drives N
+ * GPUs): the scene is replicated on every device, each frame is cut into interleaved screen tiles (tile t belongs
+ * to device t % n), every device stores its finished pixels into the frame that lives on device_ids[0] over
+ * NVLink peer access (cudaDeviceEnablePeerAccess), and a flag handshake in peer memory completes the frame.
+ * device_ids == NULL means 0 .. n_devices-1; n_devices == 0 means every visible device.  Every rt_* call works
+ * on such a context: scene calls are mirrored to all devices, rt_scene_commit builds the LBVH on all of them
+ * concurrently, rt_render / rt_render_device / rt_render_enqueue split the frame; per-ray queries and
+ * introspection run on device_ids[0].  With one device it is exactly rt_create.                              */
+int rt_create_multi(rt_ctx** out, const int* device_ids, int n_devices);
+int rt_device_count(rt_ctx* ctx, int32_t* n_devices);
 int rt_destroy(rt_ctx* ctx);
+/* Page-locked host memory for frames (Camera::bitmap, camera.cpp:19): the device-to-host copy of a frame into
+ * such a buffer is an asynchronous DMA at full PCIe rate; a pageable buffer (the reference's new[]) is staged
+ * by the driver.  rt_render page-locks a pageable rgb_out on first use (cudaHostRegister) where it can.     */
+int rt_host_alloc(void** out, uint64_t bytes);
+int rt_host_free(void* p);
 const char* rt_last_error(rt_ctx* ctx);      /* ctx may be NULL: last error of rt_create        */
 /* Run all further work of this context on an existing CUDA stream (a cudaStream_t passed as a
  * pointer, e.g. torch.cuda.current_stream().cuda_stream); NULL restores the context's own stream.
@@ -181,6 +196,13 @@ int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* 
 /* rt_render_device with stats == NULL only enqueues the frame on the context's stream and returns;
  * rt_synchronize waits for it and reports errors raised by the kernels meanwhile.              */
 int rt_synchronize(rt_ctx* ctx);
+/* Pipelined host-buffer frames: rt_render_enqueue enqueues the frame AND its copy into rgb_out (page-locked:
+ * rt_host_alloc, else it is page-locked here) and returns; rt_render_wait(slot) blocks until that frame has
+ * arrived.  Two slots (0, 1) with their own device frames: enqueue frame k+1 into the other slot before waiting
+ * for frame k and the copy of frame k overlaps the rendering of frame k+1 (the display path of
+ * Parellel/main.cu:62-70,122-133 without GL: the host buffer stands in for the PBO).                        */
+int rt_render_enqueue(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint8_t* rgb_out, int32_t slot);
+int rt_render_wait(rt_ctx* ctx, int32_t slot);
 
 /* ---- multi-GPU (one process per GPU)                                                         */
 /* A device buffer other processes on the node can map (CUDA IPC over NVLink peer access): the
@@ -228,6 +250,20 @@ int rt_shade_rays(rt_ctx* ctx, const float* rays, uint32_t n, int32_t max_depth,
  * index into the triangle array given to rt_scene_set_triangles; keys: sorted Morton keys.     */
 int rt_bvh_download(rt_ctx* ctx, float* nodes, uint32_t* tri_order, uint64_t* keys, uint32_t* n_nodes,
                     uint32_t* n_bvh_triangles);
+
+/* Roofline denominators measured on this context's device, a few hundred ms:
+ *   l2_read_gbs             float4 __ldg sweeps over a 64 MiB buffer, all SMs (L2-resident after the first sweep)
+ *   l2_random_node_gbs      random 64-byte records (the BVH node format) out of the same buffer, one dependent
+ *                           chain per thread at full occupancy; l2_dependent_fetch_ns = time of one chain step
+ *   hbm_read_gbs            one sweep over 2 GiB
+ *   fma_lane_instr_per_s    8 independent FFMA chains per thread at full occupancy = 128 lanes x SMs x real clock;
+ *                           issue_warp_instr_per_s = that / 32 (one warp instruction per scheduler and clock)   */
+typedef struct rt_microbench_result {
+    double l2_read_gbs, l2_random_node_gbs, l2_dependent_fetch_ns, hbm_read_gbs;
+    double fma_lane_instr_per_s, issue_warp_instr_per_s, implied_sm_mhz;
+    int32_t sm_count, l2_buffer_mib;
+} rt_microbench_result;
+int rt_microbench(rt_ctx* ctx, rt_microbench_result* out);
 
 /* Kernels enqueued so far by rt_render / rt_render_device / rt_render_push / rt_peer_sync / rt_assemble_tiles
  * and the refit kernels of rt_scene_commit (a host-side running count, no synchronisation; rt_peer_barrier, the

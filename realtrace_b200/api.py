@@ -58,7 +58,17 @@ class RtBuildStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class RtMicrobench(C.Structure):
+    _fields_ = [("l2_read_gbs", C.c_double), ("l2_random_node_gbs", C.c_double), ("l2_dependent_fetch_ns", C.c_double),
+                ("hbm_read_gbs", C.c_double), ("fma_lane_instr_per_s", C.c_double), ("issue_warp_instr_per_s", C.c_double),
+                ("implied_sm_mhz", C.c_double), ("sm_count", C.c_int32), ("l2_buffer_mib", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 ABI_SYMBOLS = [
+    "rt_create_multi", "rt_device_count", "rt_host_alloc", "rt_host_free", "rt_render_enqueue", "rt_render_wait", "rt_microbench",
     "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_scene_set_triangles", "rt_scene_set_spheres",
     "rt_scene_set_planes", "rt_scene_set_cylinders", "rt_scene_set_materials", "rt_scene_set_lights",
     "rt_scene_set_environment", "rt_scene_commit", "rt_scene_update_vertices", "rt_scene_update_vertices_device", "rt_scene_build_stats", "rt_render",
@@ -79,6 +89,13 @@ def load_library():
     lib = C.CDLL(LIB_PATH)
     vp, u32p, fp = C.c_void_p, C.c_void_p, C.c_void_p
     lib.rt_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.rt_create_multi.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
+    lib.rt_device_count.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.rt_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+    lib.rt_host_free.argtypes = [vp]
+    lib.rt_render_enqueue.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp, C.c_int32]
+    lib.rt_render_wait.argtypes = [vp, C.c_int32]
+    lib.rt_microbench.argtypes = [vp, C.POINTER(RtMicrobench)]
     lib.rt_destroy.argtypes = [vp]
     lib.rt_last_error.argtypes = [vp]
     lib.rt_last_error.restype = C.c_char_p
@@ -154,17 +171,57 @@ def tile_layout(width, height, tile_w=0, tile_h=0, rank=0, world=1):
     return a.value, b.value, c.value
 
 
-class Context:
-    """One GPU context (rt_ctx)."""
+def host_alloc(nbytes):
+    """Page-locked host buffer (rt_host_alloc) as a numpy uint8 array; free with host_free(array)."""
+    lib = load_library()
+    p = C.c_void_p()
+    rc = lib.rt_host_alloc(C.byref(p), nbytes)
+    if rc != 0:
+        raise RtError(rc, "rt_host_alloc failed")
+    arr = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value))
+    return arr
 
-    def __init__(self, device=0):
+
+def host_free(arr):
+    load_library().rt_host_free(arr.ctypes.data)
+
+
+class Context:
+    """One context (rt_ctx): one GPU (device = ordinal) or several (devices = list of ordinals, or "all")."""
+
+    def __init__(self, device=0, devices=None):
         self.lib = load_library()
         h = C.c_void_p()
-        rc = self.lib.rt_create(C.byref(h), device)
+        if devices is None:
+            rc = self.lib.rt_create(C.byref(h), device)
+        elif devices == "all":
+            rc = self.lib.rt_create_multi(C.byref(h), None, 0)
+        else:
+            ids = (C.c_int * len(devices))(*devices)
+            rc = self.lib.rt_create_multi(C.byref(h), ids, len(devices))
         if rc != 0:
             raise RtError(rc, self.lib.rt_last_error(None).decode())
         self.h = h
         self._keep = []
+
+    def device_count(self):
+        n = C.c_int32()
+        self._check(self.lib.rt_device_count(self.h, C.byref(n)))
+        return n.value
+
+    def microbench(self):
+        r = RtMicrobench()
+        self._check(self.lib.rt_microbench(self.h, C.byref(r)))
+        return r.as_dict()
+
+    def render_enqueue(self, cam, max_depth, out, slot):
+        """Pipelined host frame: enqueue render + copy into `out` (page-locked numpy array), do not wait."""
+        c = camera_struct(cam)
+        p = self._params(max_depth)
+        self._check(self.lib.rt_render_enqueue(self.h, C.byref(c), C.byref(p), out.ctypes.data, slot))
+
+    def render_wait(self, slot):
+        self._check(self.lib.rt_render_wait(self.h, slot))
 
     def close(self):
         if getattr(self, "h", None):

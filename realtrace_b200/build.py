@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librealtrace_b200.so")
-SOURCES = ["api.cu", "render.cu", "bvh_build.cu", "radix_sort.cu"]
+SOURCES = ["api.cu", "render.cu", "bvh_build.cu", "radix_sort.cu", "multi_device.cu", "microbench.cu"]
 HEADERS = ["rt_hd.h", "rt_scene.h", "rt_intersect.h", "rt_traverse.h", "rt_shade.h", "rt_bvh.h", "rt_context.h",
            os.path.join("..", "..", "include", "realtrace_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

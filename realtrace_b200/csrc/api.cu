@@ -32,34 +32,27 @@ static void need(bool ok, const char* what) {
     if (!ok) throw RtError{RT_ERR_INVALID_ARGUMENT, what};
 }
 
-extern "C" {
+// rank 0 (the context the caller holds) and the contexts of the other devices (rt_create_multi)
+static std::vector<rt_ctx*> all_ranks(rt_ctx* c) {
+    std::vector<rt_ctx*> v{c};
+    v.insert(v.end(), c->kids.begin(), c->kids.end());
+    return v;
+}
 
-int rt_create(rt_ctx** out, int device) {
-    if (!out) return RT_ERR_INVALID_ARGUMENT;
-    *out = nullptr;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        g_create_error = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
-                         "); realtrace_b200 has no CPU fallback";
-        cudaGetLastError();
-        return RT_ERR_NO_DEVICE;
-    }
-    if (device < 0 || device >= count) {
-        g_create_error = "device ordinal out of range";
-        return RT_ERR_INVALID_ARGUMENT;
-    }
-    rt_ctx* c = nullptr;
+// A context for one device (throws RtError).
+static rt_ctx* make_ctx(int device) {
+    rt_ctx* c = new rt_ctx;
     try {
-        c = new rt_ctx;
         c->device = device;
         RT_CUDA(cudaSetDevice(device));
         cudaDeviceProp prop;
         RT_CUDA(cudaGetDeviceProperties(&prop, device));
         c->sm_count = prop.multiProcessorCount;
         RT_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        RT_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         c->stream = c->own_stream;
         for (auto& ev : c->ev) RT_CUDA(cudaEventCreate(&ev));
+        for (auto& ev : c->mg_ev) RT_CUDA(cudaEventCreate(&ev));
         const char* ls = getenv("RT_LEAF_SIZE");
         if (ls) {
             int v = atoi(ls);
@@ -73,10 +66,10 @@ int rt_create(rt_ctx** out, int device) {
         env_int("RT_REFILL_QUEUE", 1, 32, c->refill_queue);
         env_int("RT_REFILL_SHADOW", 1, 32, c->refill_shadow);
         env_int("RT_BLOCKS_PER_SM", 1, 32, c->blocks_per_sm);
-        env_int("RT_WIDE_BVH", 0, 3, c->wide_bvh);
-        env_int("RT_HYBRID_AFTER", 0, 100000, c->hybrid_after);
+        env_int("RT_WIDE_BVH", 0, 2, c->wide_bvh);
         env_int("RT_FUSE_SHADOW", 0, 1, c->fuse_shadow);
         env_int("RT_FUSE_SHADE", 0, 2, c->fuse_shade);
+        env_int("RT_FRAME_KERNEL", 0, 2, c->frame_kernel);
         env_int("RT_TILE_BUCKET_BITS", 0, 8, c->tile_bucket_bits);
         env_int("RT_PATH_KERNEL", 0, 1, c->path_kernel);
         env_int("RT_TILE_FEEDBACK", 0, 1, c->tile_feedback);
@@ -85,9 +78,120 @@ int rt_create(rt_ctx** out, int device) {
         env_int("RT_LOOP_QUEUE", 0, 1024, c->loop_queue);
         env_int("RT_LOOP_SHADOW", 0, 1024, c->loop_shadow);
         rt_render_init(c);
+    } catch (...) {
+        delete c;
+        throw;
+    }
+    return c;
+}
+
+static void destroy_one(rt_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& s : ctx->slots) {
+        rt_frame_release(ctx, s.frame);
+        if (s.ready) cudaEventDestroy(s.ready);
+        for (auto& e : s.done)
+            if (e) cudaEventDestroy(e);
+        if (s.h_sticky) cudaFreeHost(s.h_sticky);
+    }
+    for (void* p : ctx->host_registered) cudaHostUnregister(p);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->mg_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->h_waves) cudaFreeHost(ctx->h_waves);
+    if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
+    if (ctx->h_sticky) cudaFreeHost(ctx->h_sticky);
+    for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
+    for (void* p : ctx->ipc_created) cudaFree(p);
+    if (ctx->mg_sync) cudaFree(ctx->mg_sync);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+// One rank's part of a multi-GPU frame, only enqueued (see rt_render_push in the header).
+void rt_push_frame(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, void* packed_dev, void* frame_dev,
+                   void* sync_buf, uint32_t frame_index, const rt_aux_out* aux_dev) {
+    int world = p->world_size > 1 ? p->world_size : 1, rank = world > 1 ? p->rank : 0;
+    if (rt_frame_kernel_ok(ctx, p, true)) {
+        // bounce-free scene: ONE launch traces, shades, copies this rank's tiles into the shared frame with 16-byte
+        // stores (over NVLink where they live on another GPU) and does its part of the handshake (k_frame)
+        ctx->push.frame = frame_dev; ctx->push.sync = sync_buf; ctx->push.frame_index = frame_index;
+        ctx->push.rank = rank; ctx->push.world = world; ctx->push.done = false;
+        try { rt_render_frame(ctx, cam, p, packed_dev, aux_dev, nullptr); }
+        catch (...) { ctx->push = rt_ctx::PushTarget{}; throw; }
+        bool done = ctx->push.done;
+        ctx->push = rt_ctx::PushTarget{};
+        if (done) return;
+        // (the frame took the multi-kernel path after all: finish like a scene with bounces)
+        rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 0);
+        rt_assemble(ctx, packed_dev, rank, world, cam->width, cam->height, p->tile_w > 0 ? p->tile_w : 64,
+                    p->tile_h > 0 ? p->tile_h : 32, frame_dev);
+        rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 1);
+        return;
+    }
+    if (rt_frame_pushes_inline(ctx, p)) {
+        // bounce-free scene: ONE kernel traces, shades and stores every finished 8x4 block straight into the
+        // shared frame (over NVLink where that block lives on another GPU); the packed buffer is not used
+        rt_render_params q = *p;
+        q.flags &= ~(uint32_t)RT_FLAG_PACKED_TILES;
+        rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 0);
+        ctx->remote_output = true;
+        try { rt_render_frame(ctx, cam, &q, frame_dev, aux_dev, nullptr); }
+        catch (...) { ctx->remote_output = false; throw; }
+        ctx->remote_output = false;
+        rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 1);
+        return;
+    }
+    rt_render_frame(ctx, cam, p, packed_dev, aux_dev, nullptr);
+    rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 0);
+    rt_assemble(ctx, packed_dev, rank, world, cam->width, cam->height, p->tile_w > 0 ? p->tile_w : 64,
+                p->tile_h > 0 ? p->tile_h : 32, frame_dev);
+    rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 1);
+}
+
+extern "C" {
+
+int rt_create_multi(rt_ctx** out, const int* device_ids, int n_devices) {
+    if (!out) return RT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                         "); realtrace_b200 has no CPU fallback";
+        cudaGetLastError();
+        return RT_ERR_NO_DEVICE;
+    }
+    if (n_devices == 0) n_devices = count < RT_MAX_DEVICES ? count : RT_MAX_DEVICES;
+    if (n_devices < 0 || n_devices > RT_MAX_DEVICES) {
+        g_create_error = "rt_create_multi: between 1 and 16 devices";
+        return RT_ERR_INVALID_ARGUMENT;
+    }
+    std::vector<int> devs((size_t)n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        devs[i] = device_ids ? device_ids[i] : i;
+        bool dup = false;
+        for (int j = 0; j < i; j++) dup |= devs[j] == devs[i];
+        if (devs[i] < 0 || devs[i] >= count || dup) {
+            g_create_error = "device ordinal out of range (or listed twice)";
+            return RT_ERR_INVALID_ARGUMENT;
+        }
+    }
+    rt_ctx* c = nullptr;
+    try {
+        c = make_ctx(devs[0]);
+        if (n_devices > 1) rt_multi_attach(c, devs, make_ctx);
+        RT_CUDA(cudaSetDevice(devs[0]));
     } catch (const RtError& err) {
         g_create_error = err.msg;
-        delete c;
+        if (c) {
+            for (rt_ctx* k : c->kids) destroy_one(k);
+            destroy_one(c);
+        }
         cudaGetLastError();
         return err.code;
     }
@@ -95,20 +199,48 @@ int rt_create(rt_ctx** out, int device) {
     return RT_OK;
 }
 
+int rt_create(rt_ctx** out, int device) { return rt_create_multi(out, &device, 1); }
+
+int rt_device_count(rt_ctx* ctx, int32_t* n) {
+    if (!ctx || !n) return RT_ERR_INVALID_ARGUMENT;
+    *n = 1 + (int32_t)ctx->kids.size();
+    return RT_OK;
+}
+
 int rt_destroy(rt_ctx* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    for (rt_ctx* k : ctx->kids) {
+        cudaSetDevice(k->device);
+        cudaDeviceSynchronize();
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (auto& ev : ctx->ev)
-        if (ev) cudaEventDestroy(ev);
-    if (ctx->h_waves) cudaFreeHost(ctx->h_waves);
-    if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
-    if (ctx->h_sticky) cudaFreeHost(ctx->h_sticky);
-    for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
-    for (void* p : ctx->ipc_created) cudaFree(p);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-    delete ctx;
+    // shared frames first: they are mapped on every device
+    for (auto& s : ctx->slots) rt_frame_release(ctx, s.frame);
+    for (rt_ctx* k : ctx->kids) destroy_one(k);
+    destroy_one(ctx);
     return RT_OK;
+}
+
+int rt_host_alloc(void** out, uint64_t bytes) {
+    if (!out || bytes == 0) return RT_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("rt_host_alloc: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_NO_DEVICE;
+    }
+    *out = p;
+    return RT_OK;
+}
+
+int rt_host_free(void* p) {
+    if (!p) return RT_OK;
+    cudaError_t e = cudaFreeHost(p);
+    cudaGetLastError();
+    return e == cudaSuccess ? RT_OK : RT_ERR_CUDA;
 }
 
 const char* rt_last_error(rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -122,14 +254,16 @@ int rt_scene_set_triangles(rt_ctx* ctx, const float* v, const uint32_t* material
     return guarded(ctx, [&] {
         need(n == 0 || (v && material_id), "rt_scene_set_triangles: v and material_id are required");
         need(n < (1u << 28), "rt_scene_set_triangles: at most 2^28 - 1 triangles");
-        ctx->h_tri_v.assign(v, v + 9 * (size_t)n);
-        ctx->host_vertices_stale = false;
-        ctx->h_tri_mat.assign(material_id, material_id + n);
-        ctx->h_tri_obj.resize(n);
-        for (uint32_t i = 0; i < n; i++) ctx->h_tri_obj[i] = object_id ? object_id[i] : i;
-        if (vertex_rgb) ctx->h_tri_rgb.assign(vertex_rgb, vertex_rgb + 9 * (size_t)n);
-        else ctx->h_tri_rgb.clear();
-        ctx->committed = false;
+        for (rt_ctx* c : all_ranks(ctx)) {
+            c->h_tri_v.assign(v, v + 9 * (size_t)n);
+            c->host_vertices_stale = false;
+            c->h_tri_mat.assign(material_id, material_id + n);
+            c->h_tri_obj.resize(n);
+            for (uint32_t i = 0; i < n; i++) c->h_tri_obj[i] = object_id ? object_id[i] : i;
+            if (vertex_rgb) c->h_tri_rgb.assign(vertex_rgb, vertex_rgb + 9 * (size_t)n);
+            else c->h_tri_rgb.clear();
+            c->committed = false;
+        }
     });
 }
 
@@ -153,6 +287,7 @@ int rt_scene_set_spheres(rt_ctx* ctx, const float* p, const uint32_t* material_i
             ctx->h_spheres[i].a = make_float4(q[0], q[1], q[2], q[3]);
         }
         ctx->committed = false;
+        for (rt_ctx* k : ctx->kids) { k->h_spheres = ctx->h_spheres; k->committed = false; }
     });
 }
 
@@ -169,6 +304,7 @@ int rt_scene_set_planes(rt_ctx* ctx, const float* p, const uint32_t* material_id
             ctx->h_planes[i].d = make_float4(q[9], q[10], q[11], 0);
         }
         ctx->committed = false;
+        for (rt_ctx* k : ctx->kids) { k->h_planes = ctx->h_planes; k->committed = false; }
     });
 }
 
@@ -183,30 +319,37 @@ int rt_scene_set_cylinders(rt_ctx* ctx, const float* p, const uint32_t* material
             ctx->h_cylinders[i].b = make_float4(q[4], q[5], q[6], 0);
         }
         ctx->committed = false;
+        for (rt_ctx* k : ctx->kids) { k->h_cylinders = ctx->h_cylinders; k->committed = false; }
     });
 }
 
 int rt_scene_set_materials(rt_ctx* ctx, const rt_material* m, uint32_t n) {
     return guarded(ctx, [&] {
         need(n > 0 && m, "rt_scene_set_materials: at least one material is required");
-        ctx->h_materials.assign(m, m + n);
-        ctx->committed = false;
+        for (rt_ctx* c : all_ranks(ctx)) {
+            c->h_materials.assign(m, m + n);
+            c->committed = false;
+        }
     });
 }
 
 int rt_scene_set_lights(rt_ctx* ctx, const float* pos_rgb, uint32_t n) {
     return guarded(ctx, [&] {
         need(n == 0 || pos_rgb, "rt_scene_set_lights: pos_rgb is required");
-        ctx->h_lights.assign(pos_rgb, pos_rgb + 6 * (size_t)n);
-        ctx->committed = false;
+        for (rt_ctx* c : all_ranks(ctx)) {
+            c->h_lights.assign(pos_rgb, pos_rgb + 6 * (size_t)n);
+            c->committed = false;
+        }
     });
 }
 
 int rt_scene_set_environment(rt_ctx* ctx, const float ambient[3], const float background[3]) {
     return guarded(ctx, [&] {
         need(ambient && background, "rt_scene_set_environment: both colours are required");
-        for (int k = 0; k < 3; k++) { ctx->ambient[k] = ambient[k]; ctx->background[k] = background[k]; }
-        if (ctx->committed) for (int k = 0; k < 3; k++) { ctx->scene.ambient[k] = ambient[k]; ctx->scene.background[k] = background[k]; }
+        for (rt_ctx* c : all_ranks(ctx)) {
+            for (int k = 0; k < 3; k++) { c->ambient[k] = ambient[k]; c->background[k] = background[k]; }
+            if (c->committed) for (int k = 0; k < 3; k++) { c->scene.ambient[k] = ambient[k]; c->scene.background[k] = background[k]; }
+        }
     });
 }
 
@@ -215,11 +358,16 @@ int rt_scene_commit(rt_ctx* ctx, int mode) {
         need(mode == RT_COMMIT_BUILD || mode == RT_COMMIT_REFIT, "rt_scene_commit: unknown mode");
         if (mode == RT_COMMIT_REFIT) {
             if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "rt_scene_commit(REFIT) before a BUILD commit"};
-            rt_build_bvh(ctx, true);
+            for (rt_ctx* c : all_ranks(ctx)) {      // only enqueues kernels: no helper threads needed
+                RT_CUDA(cudaSetDevice(c->device));
+                rt_build_bvh(c, true);
+            }
+            RT_CUDA(cudaSetDevice(ctx->device));
             return;
         }
         need(!ctx->h_materials.empty(), "rt_scene_commit: no materials set");
-        if (ctx->host_vertices_stale && ctx->committed && ctx->n_tri && ctx->h_tri_v.size() == 9 * (size_t)ctx->n_tri) {
+        if (ctx->host_vertices_stale && ctx->n_tri && ctx->h_tri_v.size() == 9 * (size_t)ctx->n_tri &&
+            ctx->d_tri_v.cap >= 9 * (size_t)ctx->n_tri) {
             // vertices were last written on the device (rt_scene_update_vertices_device): a rebuild starts from them
             RT_CUDA(cudaMemcpyAsync(ctx->h_tri_v.data(), ctx->d_tri_v.p, ctx->h_tri_v.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
             RT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -243,7 +391,13 @@ int rt_scene_commit(rt_ctx* ctx, int mode) {
                 if (p.object_id == 0xffffffffu) p.object_id = next;
                 next++;
             }
-        rt_build_bvh(ctx, false);
+        for (rt_ctx* k : ctx->kids) {               // same staging on every rank (ids resolved, vertices current)
+            k->h_tri_v = ctx->h_tri_v;
+            k->host_vertices_stale = false;
+            k->h_spheres = ctx->h_spheres; k->h_planes = ctx->h_planes; k->h_cylinders = ctx->h_cylinders;
+        }
+        if (ctx->kids.empty()) rt_build_bvh(ctx, false);
+        else rt_multi_build(ctx, false);
         ctx->committed = true;
     });
 }
@@ -252,10 +406,14 @@ int rt_scene_update_vertices(rt_ctx* ctx, const float* v, uint32_t n) {
     return guarded(ctx, [&] {
         if (!ctx->committed) throw RtError{RT_ERR_NOT_COMMITTED, "rt_scene_update_vertices before commit"};
         need(v && n == ctx->n_tri, "rt_scene_update_vertices: vertex count must equal the committed triangle count");
-        ctx->h_tri_v.assign(v, v + 9 * (size_t)n);
-        ctx->host_vertices_stale = false;
-        RT_CUDA(cudaMemcpyAsync(ctx->d_tri_v.p, ctx->h_tri_v.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (rt_ctx* c : all_ranks(ctx)) {
+            RT_CUDA(cudaSetDevice(c->device));
+            c->h_tri_v.assign(v, v + 9 * (size_t)n);
+            c->host_vertices_stale = false;
+            RT_CUDA(cudaMemcpyAsync(c->d_tri_v.p, c->h_tri_v.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        }
+        for (rt_ctx* c : all_ranks(ctx)) RT_CUDA(cudaStreamSynchronize(c->stream));
+        RT_CUDA(cudaSetDevice(ctx->device));
     });
 }
 
@@ -267,6 +425,17 @@ int rt_scene_update_vertices_device(rt_ctx* ctx, const float* v_dev, uint32_t n)
         // enqueued on the same stream (rt_set_stream) or be complete
         RT_CUDA(cudaMemcpyAsync(ctx->d_tri_v.p, v_dev, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
         ctx->host_vertices_stale = true;
+        if (!ctx->kids.empty()) {
+            // the other devices take their copy from rank 0's over NVLink, after rank 0's copy has landed
+            RT_CUDA(cudaEventRecord(ctx->mg_ev[0], ctx->stream));
+            for (rt_ctx* k : ctx->kids) {
+                RT_CUDA(cudaSetDevice(k->device));
+                RT_CUDA(cudaStreamWaitEvent(k->stream, ctx->mg_ev[0], 0));
+                RT_CUDA(cudaMemcpyPeerAsync(k->d_tri_v.p, k->device, ctx->d_tri_v.p, ctx->device, 9 * (size_t)n * sizeof(float), k->stream));
+                k->host_vertices_stale = true;
+            }
+            RT_CUDA(cudaSetDevice(ctx->device));
+        }
     });
 }
 
@@ -292,8 +461,88 @@ int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* 
                      const rt_aux_out* aux_dev, rt_frame_stats* stats) {
     return guarded(ctx, [&] {
         check_render_args(ctx, cam, p);
-        rt_render_frame(ctx, cam, p, rgb_out_dev, aux_dev, stats);
+        if (ctx->kids.empty()) {
+            rt_render_frame(ctx, cam, p, rgb_out_dev, aux_dev, stats);
+            return;
+        }
+        // several devices: rgb_out_dev / aux_dev live on rank 0's device; every rank stores its tiles there
+        need(rgb_out_dev != nullptr, "rt_render_device on a multi-device context needs an output buffer");
+        rt_multi_enqueue_frame(ctx, cam, p, rgb_out_dev, aux_dev);
+        if (stats) rt_multi_collect(ctx, stats);
     });
+}
+
+// Device-side aux buffers of rt_render (rank 0), cleared to "miss".
+static rt_aux_out prepare_aux(rt_ctx* ctx, const rt_aux_out* aux, size_t npix) {
+    rt_aux_out aux_dev{nullptr, nullptr};
+    if (aux && (aux->prim_id || aux->t)) {
+        ctx->d_aux_prim.reserve(npix);
+        ctx->d_aux_t.reserve(npix);
+        aux_dev.prim_id = ctx->d_aux_prim.p;
+        aux_dev.t = ctx->d_aux_t.p;
+        // pixels of tiles this rank does not own stay "miss"
+        RT_CUDA(cudaMemsetAsync(ctx->d_aux_prim.p, 0xff, npix * sizeof(int32_t), ctx->stream));
+        RT_CUDA(cudaMemsetAsync(ctx->d_aux_t.p, 0, npix * sizeof(float), ctx->stream));
+    }
+    return aux_dev;
+}
+
+static void ensure_slot(rt_ctx* ctx, int slot, size_t bytes) {
+    rt_ctx::FrameSlot& s = ctx->slots[slot];
+    rt_frame_reserve(ctx, s.frame, bytes);
+    if (!s.ready) {
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+        std::vector<rt_ctx*> ranks = all_ranks(ctx);
+        for (size_t r = 0; r < ranks.size(); r++) {
+            RT_CUDA(cudaSetDevice(ranks[r]->device));
+            RT_CUDA(cudaEventCreateWithFlags(&s.done[r], cudaEventDisableTiming));
+        }
+        RT_CUDA(cudaSetDevice(ctx->device));
+        RT_CUDA(cudaMallocHost((void**)&s.h_sticky, RT_MAX_DEVICES * sizeof(uint32_t)));
+        memset(s.h_sticky, 0, RT_MAX_DEVICES * sizeof(uint32_t));
+    }
+}
+
+// Waits for the host copy of `slot` and raises what the kernels of that frame reported.
+static void wait_slot(rt_ctx* ctx, int slot) {
+    rt_ctx::FrameSlot& s = ctx->slots[slot];
+    if (!s.in_flight) return;
+    s.in_flight = false;
+    std::vector<rt_ctx*> ranks = all_ranks(ctx);
+    RtError first{RT_OK, ""};
+    for (size_t r = 0; r < ranks.size(); r++) {
+        RT_CUDA(cudaEventSynchronize(s.done[r]));
+        uint32_t fl = s.h_sticky[r];
+        if (fl) {
+            s.h_sticky[r] = 0;
+            RT_CUDA(cudaSetDevice(ranks[r]->device));
+            RT_CUDA(cudaMemsetAsync(ranks[r]->d_sticky.p, 0, sizeof(uint32_t), ranks[r]->stream));
+            if (first.code == RT_OK) first = rt_sticky_error(fl);
+        }
+    }
+    RT_CUDA(cudaSetDevice(ctx->device));
+    if (first.code != RT_OK) throw first;
+}
+
+// Frame `slot`: render into the slot's device frame, then copy it to the host on the copy streams.
+static void enqueue_slot(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint8_t* rgb_out, int slot,
+                         const rt_aux_out* aux_dev) {
+    size_t bytes = (size_t)cam->width * cam->height * 3;
+    ensure_slot(ctx, slot, bytes);
+    rt_ctx::FrameSlot& s = ctx->slots[slot];
+    if (s.in_flight) wait_slot(ctx, slot);           // the slot's previous frame must have left its device frame
+    if (ctx->kids.empty()) {
+        rt_render_params q = *p;
+        q.flags &= ~(uint32_t)RT_FLAG_PACKED_TILES;
+        q.world_size = 1; q.rank = 0;
+        rt_render_frame(ctx, cam, &q, s.frame.va, aux_dev, nullptr);
+    } else {
+        rt_multi_enqueue_frame(ctx, cam, p, s.frame.va, aux_dev);
+    }
+    RT_CUDA(cudaEventRecord(s.ready, ctx->stream));
+    rt_frame_download_async(ctx, s.frame, rgb_out, bytes, s.ready, s.done, s.h_sticky);
+    s.in_flight = true;
 }
 
 int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint8_t* rgb_out, const rt_aux_out* aux,
@@ -302,6 +551,30 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint
         check_render_args(ctx, cam, p);
         need(rgb_out != nullptr, "rt_render: rgb_out is NULL");
         size_t npix = (size_t)cam->width * cam->height;
+        if (!ctx->kids.empty()) {
+            // several devices: whole frames only (the tile split is the library's business here)
+            need(!(p->flags & RT_FLAG_PACKED_TILES) && p->world_size <= 1, "rt_render on a multi-device context renders whole frames");
+            rt_aux_out aux_dev = prepare_aux(ctx, aux, npix);
+            if (aux_dev.prim_id) {
+                // the other ranks write their pixels' aux values into rank 0's buffers: after the clear above
+                RT_CUDA(cudaEventRecord(ctx->mg_ev[0], ctx->stream));
+                for (rt_ctx* k : ctx->kids) {
+                    RT_CUDA(cudaSetDevice(k->device));
+                    RT_CUDA(cudaStreamWaitEvent(k->stream, ctx->mg_ev[0], 0));
+                }
+                RT_CUDA(cudaSetDevice(ctx->device));
+            }
+            enqueue_slot(ctx, cam, p, rgb_out, 0, aux_dev.prim_id ? &aux_dev : nullptr);
+            if (aux && aux->prim_id)
+                RT_CUDA(cudaMemcpyAsync(aux->prim_id, ctx->d_aux_prim.p, npix * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            if (aux && aux->t)
+                RT_CUDA(cudaMemcpyAsync(aux->t, ctx->d_aux_t.p, npix * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            RtError deferred{RT_OK, ""};
+            try { rt_multi_collect(ctx, stats); } catch (const RtError& e) { deferred = e; }
+            try { wait_slot(ctx, 0); } catch (const RtError& e) { if (deferred.code == RT_OK) deferred = e; }
+            if (deferred.code != RT_OK) throw deferred;
+            return;
+        }
         bool packed = (p->flags & RT_FLAG_PACKED_TILES) != 0;
         size_t bytes = npix * 3;
         if (packed) {
@@ -311,16 +584,7 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint
             bytes = (size_t)owned * tb;
         }
         ctx->d_rgb.reserve(bytes ? bytes : 1);
-        rt_aux_out aux_dev{nullptr, nullptr};
-        if (aux && (aux->prim_id || aux->t)) {
-            ctx->d_aux_prim.reserve(npix);
-            ctx->d_aux_t.reserve(npix);
-            aux_dev.prim_id = ctx->d_aux_prim.p;
-            aux_dev.t = ctx->d_aux_t.p;
-            // pixels of tiles this rank does not own stay "miss"
-            RT_CUDA(cudaMemsetAsync(ctx->d_aux_prim.p, 0xff, npix * sizeof(int32_t), ctx->stream));
-            RT_CUDA(cudaMemsetAsync(ctx->d_aux_t.p, 0, npix * sizeof(float), ctx->stream));
-        }
+        rt_aux_out aux_dev = prepare_aux(ctx, aux, npix);
         if (!packed && p->world_size > 1) RT_CUDA(cudaMemsetAsync(ctx->d_rgb.p, 0, bytes, ctx->stream));
         RtError deferred{RT_OK, ""};
         try {
@@ -334,13 +598,59 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint
             RT_CUDA(cudaMemcpyAsync(aux->prim_id, ctx->d_aux_prim.p, npix * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (aux && aux->t)
             RT_CUDA(cudaMemcpyAsync(aux->t, ctx->d_aux_t.p, npix * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        // the copies are in flight: wait for them and surface errors the kernels raised meanwhile (with stats == NULL
+        // rt_render_frame did not synchronise, so the sticky error word has not been looked at yet)
+        try {
+            rt_sync_and_check(ctx);
+        } catch (const RtError& e) {
+            if (deferred.code == RT_OK) deferred = e;
+        }
         if (deferred.code != RT_OK) throw deferred;
     });
 }
 
+int rt_render_enqueue(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint8_t* rgb_out, int32_t slot) {
+    return guarded(ctx, [&] {
+        check_render_args(ctx, cam, p);
+        need(rgb_out != nullptr && (slot == 0 || slot == 1), "rt_render_enqueue: rgb_out is NULL or slot is not 0/1");
+        need(!(p->flags & RT_FLAG_PACKED_TILES) && p->world_size <= 1, "rt_render_enqueue renders whole frames");
+        // an asynchronous copy needs a page-locked destination: lock the caller's buffer the first time it is seen
+        cudaPointerAttributes at;
+        cudaError_t e = cudaPointerGetAttributes(&at, rgb_out);
+        if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered) {
+            cudaGetLastError();
+            size_t bytes = (size_t)cam->width * cam->height * 3;
+            if (cudaHostRegister(rgb_out, bytes, cudaHostRegisterPortable) == cudaSuccess) ctx->host_registered.push_back(rgb_out);
+            else cudaGetLastError();                  // stays pageable: the copy is then staged by the driver
+        }
+        enqueue_slot(ctx, cam, p, rgb_out, slot, nullptr);
+    });
+}
+
+int rt_render_wait(rt_ctx* ctx, int32_t slot) {
+    return guarded(ctx, [&] {
+        need(slot == 0 || slot == 1, "rt_render_wait: slot is not 0/1");
+        wait_slot(ctx, slot);
+    });
+}
+
 int rt_synchronize(rt_ctx* ctx) {
-    return guarded(ctx, [&] { rt_sync_and_check(ctx); });
+    return guarded(ctx, [&] {
+        RtError first{RT_OK, ""};
+        for (rt_ctx* c : all_ranks(ctx)) {
+            try {
+                RT_CUDA(cudaSetDevice(c->device));
+                rt_sync_and_check(c);
+            } catch (const RtError& e) {
+                if (first.code == RT_OK) first = e;
+            }
+        }
+        for (int s = 0; s < 2; s++) {
+            try { wait_slot(ctx, s); } catch (const RtError& e) { if (first.code == RT_OK) first = e; }
+        }
+        RT_CUDA(cudaSetDevice(ctx->device));
+        if (first.code != RT_OK) throw first;
+    });
 }
 
 int rt_shared_buffer_create(rt_ctx* ctx, uint64_t bytes, void** dev_ptr, unsigned char handle[64]) {
@@ -391,25 +701,7 @@ int rt_render_push(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p,
         check_render_args(ctx, cam, p);
         need(packed_dev && frame_dev && sync_buf, "rt_render_push: NULL buffer");
         need((p->flags & RT_FLAG_PACKED_TILES) != 0 && p->world_size >= 1, "rt_render_push: needs RT_FLAG_PACKED_TILES and a world size");
-        int world = p->world_size > 1 ? p->world_size : 1, rank = world > 1 ? p->rank : 0;
-        if (rt_frame_pushes_inline(ctx, p)) {
-            // bounce-free scene: ONE kernel traces, shades and stores every finished 8x4 block straight into the
-            // shared frame (over NVLink on ranks > 0); the packed buffer is not used
-            rt_render_params q = *p;
-            q.flags &= ~(uint32_t)RT_FLAG_PACKED_TILES;
-            rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 0);
-            ctx->remote_output = true;
-            try { rt_render_frame(ctx, cam, &q, frame_dev, nullptr, nullptr); }
-            catch (...) { ctx->remote_output = false; throw; }
-            ctx->remote_output = false;
-            rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 1);
-            return;
-        }
-        rt_render_frame(ctx, cam, p, packed_dev, nullptr, nullptr);
-        rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 0);
-        rt_assemble(ctx, packed_dev, rank, world, cam->width, cam->height, p->tile_w > 0 ? p->tile_w : 64,
-                    p->tile_h > 0 ? p->tile_h : 32, frame_dev);
-        rt_peer_sync_enqueue(ctx, sync_buf, rank, world, frame_index, 1);
+        rt_push_frame(ctx, cam, p, packed_dev, frame_dev, sync_buf, frame_index, nullptr);
     });
 }
 
@@ -473,6 +765,13 @@ int rt_bvh_download(rt_ctx* ctx, float* nodes, uint32_t* tri_order, uint64_t* ke
         if (tri_order && nb) RT_CUDA(cudaMemcpyAsync(tri_order, ctx->d_vals[ctx->sorted_buf].p, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (keys && nb) RT_CUDA(cudaMemcpyAsync(keys, ctx->d_keys[ctx->sorted_buf].p, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         RT_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int rt_microbench(rt_ctx* ctx, rt_microbench_result* out) {
+    return guarded(ctx, [&] {
+        need(out != nullptr, "rt_microbench: out is NULL");
+        rt_run_microbench(ctx, out);
     });
 }
 

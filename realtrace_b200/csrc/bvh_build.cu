@@ -77,6 +77,20 @@ __global__ void __launch_bounds__(TPB) k_scene_bounds(const float* __restrict__ 
     }
 }
 
+__global__ void k_bounds_init(uint32_t* __restrict__ bounds) {
+    int k = threadIdx.x;
+    if (k < 12) bounds[k] = (k % 6) < 3 ? 0xffffffffu : 0u;
+}
+
+// Absolute pad of the node boxes: 4e-6 of the largest scene coordinate, derived on the device from the scene
+// box of the CURRENT vertices (a refit of a mesh that moved or grew must not keep the pad of the old extent).
+__device__ __forceinline__ float pad_from_bounds(const uint32_t* __restrict__ bounds) {
+    float amax = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) amax = fmaxf(amax, fabsf(ord_decode(bounds[k])));
+    return amax * 4.0e-6f;
+}
+
 __global__ void __launch_bounds__(TPB) k_morton(const float* __restrict__ v, uint32_t n,
                                                const uint32_t* __restrict__ bounds, float large_frac,
                                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
@@ -174,9 +188,10 @@ __global__ void __launch_bounds__(TPB) k_refit(const float* __restrict__ v, cons
                                               const KarrasNode* __restrict__ kn, const int* __restrict__ leaf_parent,
                                               const int* __restrict__ node_parent, uint32_t* __restrict__ visit,
                                               float4* __restrict__ box_lo, float4* __restrict__ box_hi,
-                                              float4* __restrict__ nodes, int leaf_size, float pad_abs) {
+                                              float4* __restrict__ nodes, int leaf_size, const uint32_t* __restrict__ bounds) {
     int k = blockIdx.x * TPB + threadIdx.x;
     if (k >= n) return;
+    const float pad_abs = pad_from_bounds(bounds);
     f3 a, b, c;
     load_tri(v, order[k], a, b, c);
     Aabb bx = tri_aabb(a, b, c);
@@ -220,7 +235,8 @@ __global__ void __launch_bounds__(TPB) k_collapse4(const float4* __restrict__ no
 
 // A BVH of one triangle: root with one leaf child and one empty child.
 __global__ void k_single_leaf(const float* __restrict__ v, const uint32_t* __restrict__ order,
-                              float4* __restrict__ nodes, float pad_abs) {
+                              float4* __restrict__ nodes, const uint32_t* __restrict__ bounds) {
+    const float pad_abs = pad_from_bounds(bounds);
     f3 a, b, c;
     load_tri(v, order[0], a, b, c);
     Aabb p = pad_box(tri_aabb(a, b, c), pad_abs);
@@ -313,10 +329,24 @@ static void publish_scene(rt_ctx* c) {
     for (int k = 0; k < 3; k++) { s.ambient[k] = c->ambient[k]; s.background[k] = c->background[k]; }
 }
 
-static void run_refit(rt_ctx* c) {
+static void launch_scene_bounds(rt_ctx* c) {
+    cudaStream_t st = c->stream;
+    uint32_t n = c->n_tri;
+    k_bounds_init<<<1, 32, 0, st>>>(c->d_bounds.p);
+    int bb = blocks_for(n);
+    if (bb > c->sm_count * 8) bb = c->sm_count * 8;
+    k_scene_bounds<<<bb, TPB, 0, st>>>(c->d_tri_v.p, n, c->d_bounds.p);
+    RT_CUDA(cudaGetLastError());
+}
+
+static void run_refit(rt_ctx* c, bool new_vertices) {
     cudaStream_t st = c->stream;
     uint32_t n = c->n_tri, nb = c->n_bvh;
     const uint32_t* order = c->d_vals[c->sorted_buf].p;
+    if (new_vertices && n) {       // REFIT commit: the pad of the node boxes follows the current extent
+        launch_scene_bounds(c);
+        c->launch_total += 2;
+    }
     if (n) {
         k_tri_records<<<blocks_for(n), TPB, 0, st>>>(c->d_tri_v.p, c->d_tri_mat.p, c->d_tri_obj.p, order, n, c->d_tris.p);
         RT_CUDA(cudaGetLastError());
@@ -327,16 +357,15 @@ static void run_refit(rt_ctx* c) {
         RT_CUDA(cudaGetLastError());
         c->launch_total++;
     }
-    float pad_abs = c->scene_abs_max * 4.0e-6f;
     if (nb >= 2) {
         RT_CUDA(cudaMemsetAsync(c->d_visit.p, 0, (nb - 1) * sizeof(uint32_t), st));
         k_refit<<<blocks_for(nb), TPB, 0, st>>>(c->d_tri_v.p, order, (int)nb, c->d_karras.p, c->d_leaf_parent.p,
                                                 c->d_node_parent.p, c->d_visit.p, c->d_box_lo.p, c->d_box_hi.p,
-                                                c->d_nodes.p, c->leaf_size, pad_abs);
+                                                c->d_nodes.p, c->leaf_size, c->d_bounds.p);
         RT_CUDA(cudaGetLastError());
         c->launch_total++;
     } else if (nb == 1) {
-        k_single_leaf<<<1, 1, 0, st>>>(c->d_tri_v.p, order, c->d_nodes.p, pad_abs);
+        k_single_leaf<<<1, 1, 0, st>>>(c->d_tri_v.p, order, c->d_nodes.p, c->d_bounds.p);
         RT_CUDA(cudaGetLastError());
         c->launch_total++;
     }
@@ -356,7 +385,7 @@ void rt_build_bvh(rt_ctx* c, bool refit_only) {
     if (refit_only) {
         // asynchronous: only enqueues; rt_scene_build_stats reads the event pair later
         RT_CUDA(cudaEventRecord(c->ev[8], st));
-        run_refit(c);
+        run_refit(c, true);
         RT_CUDA(cudaEventRecord(c->ev[9], st));
         c->refit_pending = true;
         publish_scene(c);
@@ -382,13 +411,7 @@ void rt_build_bvh(rt_ctx* c, bool refit_only) {
         c->d_node_parent.reserve(n);
         c->d_visit.reserve(n);
 
-        uint32_t init[12];
-        for (int k = 0; k < 3; k++) { init[k] = 0xffffffffu; init[3 + k] = 0u; init[6 + k] = 0xffffffffu; init[9 + k] = 0u; }
-        RT_CUDA(cudaMemcpyAsync(c->d_bounds.p, init, sizeof init, cudaMemcpyHostToDevice, st));
-        int bb = blocks_for(n);
-        if (bb > c->sm_count * 8) bb = c->sm_count * 8;
-        k_scene_bounds<<<bb, TPB, 0, st>>>(c->d_tri_v.p, n, c->d_bounds.p);
-        RT_CUDA(cudaGetLastError());
+        launch_scene_bounds(c);
 
         float large_frac = n >= 64 ? 0.25f : FLT_MAX;
         uint32_t h_large = 0;
@@ -402,18 +425,6 @@ void rt_build_bvh(rt_ctx* c, bool refit_only) {
             if (h_large <= RT_MAX_LARGE) break;
             large_frac = FLT_MAX;   // too many outliers to test linearly: keep them all in the hierarchy
         }
-        uint32_t hb[12];
-        RT_CUDA(cudaMemcpyAsync(hb, c->d_bounds.p, sizeof hb, cudaMemcpyDeviceToHost, st));
-        RT_CUDA(cudaStreamSynchronize(st));
-        float amax = 0.0f;
-        for (int k = 0; k < 6; k++) {
-            uint32_t u = hb[k];
-            uint32_t bits = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-            float f;
-            memcpy(&f, &bits, 4);
-            amax = fmaxf(amax, fabsf(f));
-        }
-        c->scene_abs_max = amax;
         c->n_large = h_large;
         c->n_bvh = n - h_large;
 
@@ -426,7 +437,7 @@ void rt_build_bvh(rt_ctx* c, bool refit_only) {
             RT_CUDA(cudaGetLastError());
         }
     }
-    run_refit(c);
+    run_refit(c, false);
     RT_CUDA(cudaEventRecord(c->ev[5], st));
     RT_CUDA(cudaEventSynchronize(c->ev[5]));
     RT_CUDA(cudaEventElapsedTime(&c->build_stats.ms_build, c->ev[4], c->ev[5]));

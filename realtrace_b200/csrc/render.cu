@@ -187,7 +187,6 @@ struct TravArgs {
     WaveCounters* next;       // SHADE: their counter
     int max_depth;            // SHADE
     int remote_out;           // SHADE: direct_rgb is another GPU's frame (informational: same code path)
-    int hybrid_after;         // WIDE == 2: steps a ray takes on the binary tree before it continues on the 4-wide view
 };
 
 // Appends the bounce rays of this warp's shaded hits to the next wave's queue: exclusive prefix over the
@@ -273,11 +272,8 @@ __device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uin
 // hit together with its occlusion bits.  One kernel and one tail per wave instead of two, no second
 // derivation of the hit point, and lanes whose rays missed keep pulling new rays meanwhile.
 // WIDE = 1: walk the 4-wide view of the tree (SceneDev::nodes4); a template parameter so that the binary walk
-// keeps its register budget.  WIDE = 2 (EXPERIMENTAL, RT_WIDE_BVH=3): hybrid — a ray starts on the binary tree
-// and continues on the 4-wide view, with the same stack, once it has taken more than hybrid_after steps: both
-// views index the same nodes, so hits are bit-identical (tests/test_emulation.py), the bulk of the rays never
-// leaves the cheaper binary step, and the longest dependency chains lose a third of their steps
-// (profiles/r1_tuning.md section 15).  80 registers.
+// keeps its register budget.  (A hybrid that moved a ray to the wide view after 32 steps was measured in round 2:
+// it removes the kernel's tail but costs the bulk 20 % at 80 registers — profiles/r2_tuning.md — and was deleted.)
 // SHADE (fused primary rays, whole-batch refill): the hit is not queued for k_shade either.  A lane keeps its
 // hit and occlusion bits until the warp's 32-pixel batch is done, then the warp shades all its hits together
 // (World::shade_ray, world.cpp:32-111, same shade_hit as k_shade), writes the pixels and queues the bounce
@@ -285,15 +281,17 @@ __device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uin
 #ifndef RT_SHADE_FUSED_MIN_BLOCKS
 #define RT_SHADE_FUSED_MIN_BLOCKS 7     // SHADE: hold the kernel to the traversal loop's 72 registers (the once-per-batch shading spills)
 #endif
-template <int MODE, bool COUNT, bool FUSE, int WIDE = 0, bool SHADE = false>
-__global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : (WIDE == 2 ? 6 : 0)) k_traverse(const __grid_constant__ TravArgs a) {
+// The body of the traversal kernels (k_traverse, and phase 1 of k_frame).  Returns the number of work items this
+// warp claimed from the cursor (warp-uniform): k_frame's "everything is traced" barrier counts them.
+template <int MODE, bool COUNT, bool FUSE, int WIDE, bool SHADE>
+__device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pdir) {
     constexpr bool ANY = MODE == MODE_SHADOW;
     static_assert(!(FUSE && ANY), "FUSE applies to the nearest-hit modes");
     static_assert(!WIDE || FUSE, "the wide walk is instantiated for the fused kernels only");
-    static_assert(WIDE >= 0 && WIDE <= 2, "WIDE: 0 binary walk, 1 4-wide view, 2 hybrid");
+    static_assert(WIDE >= 0 && WIDE <= 1, "WIDE: 0 binary walk, 1 4-wide view");
     static_assert(!SHADE || (FUSE && MODE == MODE_PRIMARY), "in-kernel shading is for the fused primary wave");
-    __shared__ float s_pdir[SHADE ? 3 * TRAV_TPB : 1];   // SHADE: primary direction of the lane's pending hit
     const unsigned FULL = 0xffffffffu;
+    uint32_t claimed = 0;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t n, n_hits_in = 0;
@@ -328,7 +326,6 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
     nh.t = RT_FLT_MAX; nh.prim = RT_MISS; nh.beta = nh.gamma = 0.0f;
     f3 P = mk3(0, 0, 0);
     uint32_t occl_mask = 0;
-    int ray_steps = 0;                     // WIDE == 2: steps of the current ray (primary or shadow)
     bool pending = false, qfull = false;   // SHADE: this lane's hit waits for the end of the batch
     uint32_t px_rgb = 0;                   // SHADE, RGB8 output: the lane's finished pixel, stored with its 8x4 block
     bool px_have = false;
@@ -340,7 +337,6 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
         found = false;
         sp = 0;
         node = (use_bvh && sd.x == sd.x && sd.y == sd.y && sd.z == sd.z) ? 0 : RT_DONE;
-        ray_steps = 0;
         traced_shadow++;
     };
 
@@ -385,6 +381,7 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
                 batch_t0 = clock64();
             }
             if (base + (uint32_t)cnt >= n) exhausted = true;
+            if (base < n) claimed += min((uint32_t)cnt, n - base);
             my = base + __popc(need & lt);
             have = !active && my < n;
         } else if (MODE == MODE_PRIMARY && exhausted && !steal_done && need == FULL) {
@@ -461,8 +458,7 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
                     active = true;
                     phase = -1;
                     sp = 0;
-                    ray_steps = 0;
-                    // a NaN direction (ignored refract() failure, world.cpp:83) misses everything
+                                // a NaN direction (ignored refract() failure, world.cpp:83) misses everything
                     bool finite = d.x == d.x && d.y == d.y && d.z == d.z;
                     r = prep_ray(o, d);
                     node = (use_bvh && finite) ? 0 : RT_DONE;
@@ -484,13 +480,11 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
             if (a.loop_style == 0) {
                 while (rt_is_internal(node)) {
                     if (COUNT) wcp->nodes++;
-                    if (WIDE == 2) ray_steps++;
-                    node = (WIDE == 1 || (WIDE == 2 && ray_steps > a.hybrid_after))
+                    node = WIDE == 1
                                ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
                                : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                 }
                 while (node < 0) {
-                    if (WIDE == 2) ray_steps++;
                     if (leaf_test(a.s, node, r, hit, any, wcp)) {
                         found = true;
                         if (any) { node = RT_DONE; break; }
@@ -501,10 +495,9 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
                 // "if-if": every lane advances one step of whatever kind per iteration, for a bounded
                 // number of iterations before the warp looks at its refill state again
                 for (int it = 0; it < a.loop_style && node != RT_DONE; it++) {
-                    if (WIDE == 2) ray_steps++;
                     if (rt_is_internal(node)) {
                         if (COUNT) wcp->nodes++;
-                        node = (WIDE == 1 || (WIDE == 2 && ray_steps > a.hybrid_after))
+                        node = WIDE == 1
                                    ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
                                    : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
                     } else {
@@ -631,6 +624,13 @@ __global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 
         a.warp_times[2 * wid] = t_start;
         a.warp_times[2 * wid + 1] = t_end;
     }
+    return claimed;
+}
+
+template <int MODE, bool COUNT, bool FUSE, int WIDE = 0, bool SHADE = false>
+__global__ void __launch_bounds__(TRAV_TPB, SHADE ? RT_SHADE_FUSED_MIN_BLOCKS : 0) k_traverse(const __grid_constant__ TravArgs a) {
+    __shared__ float s_pdir[SHADE ? 3 * TRAV_TPB : 1];   // SHADE: primary direction of the lane's pending hit
+    traverse_body<MODE, COUNT, FUSE, WIDE, SHADE>(a, s_pdir);
 }
 
 struct ShadeArgs {
@@ -705,6 +705,175 @@ __global__ void __launch_bounds__(SHADE_TPB, RT_SHADE_MIN_BLOCKS) k_shade(const 
     if (__any_sync(0xffffffffu, qfull) && lane == 0) atomicOr(a.sticky, 1u);
 }
 
+
+// ---- k_frame: a whole bounce-free frame in ONE launch --------------------------------------------------------------
+// The north-star workload (config 4: primary + shadow rays, no bounces) used to take a traversal kernel, a shading
+// kernel and — when the frame lives on another GPU — a push kernel between two single-thread handshake kernels: five
+// launches whose gaps and tails are a third of an 8-GPU frame.  Here the persistent warps run all of it:
+//   phase 1  traverse_body<PRIMARY, FUSE>: nearest hits + their shadow rays; misses write their pixel, hits go to
+//            the compacted hit queue (same code as k_traverse)
+//   barrier  a warp that finds the ray cursor empty adds the work items it claimed to done[0] and waits until the
+//            sum is the whole share — a barrier on WORK, not on CTAs, so it cannot deadlock on CTAs that are not
+//            resident yet (they find nothing to claim and pass straight through)
+//   phase 2  the hit queue is shaded with full warps (k_shade's code), pixels written as RGB8
+//   barrier  the same on done[1] == number of hits
+//   phase 3  (frame elsewhere) this rank's packed tiles -> the shared frame with 16-byte stores over NVLink, after
+//            rank 0's "previous frame consumed" flag
+//   exit     the last CTA to finish (done[2]) signals rank 0's arrival slot with a system-scope atomic; on rank 0 it
+//            waits for the other ranks' arrivals instead, so the completion of rank 0's kernel IS the completion of
+//            the frame.  No handshake kernels, no collective.
+struct FrameSyncDev {
+    uint32_t* done;                 // [0] work items traced, [1] hits shaded, [2] CTAs finished; zero between frames
+    uint32_t* sync;                 // rt_peer_sync layout in rank 0's memory (peer mapped), or nullptr: no other ranks
+    uint32_t frame, rank, world;
+};
+struct PushDev {                    // phase 3; packed == nullptr: pixels were written in place, nothing to push
+    const uint8_t* packed;
+    uint8_t* frame;
+    uint32_t tiles_total;
+    int wide16;                     // rows of tile and frame are 16-byte multiples, both buffers 16-byte aligned
+};
+struct FrameArgs {
+    TravArgs t;
+    FrameSyncDev y;
+    PushDev push;
+    int max_depth;
+};
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+
+// Spin until *p >= want; gives up after ~2 s (sticky bit 4) like the handshake kernels.
+__device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t want, uint32_t* sticky, unsigned ns) {
+    long long t0 = clock64();
+    while (ld_volatile_u32(p) < want) {
+        if (clock64() - t0 > 4000000000ll) { atomicOr(sticky, 4u); break; }
+        __nanosleep(ns);
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(const __grid_constant__ FrameArgs a) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool pushing = a.push.packed != nullptr;
+    // rank 0 opens the frame for the other ranks: everything enqueued on its stream for the previous frame (a copy to
+    // the host, say) has finished before this kernel started
+    if (a.y.sync && a.y.rank == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        volatile uint32_t* consumed = a.y.sync + 64;
+        if (*consumed < a.y.frame) *consumed = a.y.frame;
+        __threadfence_system();
+    }
+    // ---- phase 1
+    uint32_t claimed = traverse_body<MODE_PRIMARY, COUNT, true, 0, false>(a.t, nullptr);
+    const uint32_t n_items = a.t.f.n_local_pix;
+    if (lane == 0) {
+        __threadfence();
+        if (claimed) atomicAdd(a.y.done + 0, claimed);
+        spin_until_ge(a.y.done + 0, n_items, a.t.sticky, 100);
+        __threadfence();
+    }
+    __syncwarp();
+    // ---- phase 2: shade the hit queue (World::shade_ray's local term, world.cpp:40-63, :126-137)
+    const uint32_t n_hits = __ldcg(&a.t.wave->n_hits);
+    const f3 bg = mk3(a.t.s.background[0], a.t.s.background[1], a.t.s.background[2]);
+    uint32_t shaded = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&a.t.wave->fetch_shade, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n_hits) break;
+        uint32_t pos = base + lane;
+        if (pos < n_hits) {
+            uint32_t idx = __ldcg(a.t.hitq + pos);
+            float4 hr = __ldcg(a.t.hits + pos);
+            uint32_t om = (uint32_t)__ldcg(a.t.occl + pos);
+            HitRec h;
+            h.t = hr.x; h.prim = __float_as_int(hr.y); h.beta = hr.z; h.gamma = hr.w;
+            int pi = 0, pj = 0;
+            f3 o, d;
+            local_to_pixel(a.t.f, idx, pi, pj);
+            primary_ray(a.t.cam, pi, pj, o, d);
+            ShadeOut out;
+            uint32_t li = 0;
+            auto any_hit = [&](f3, f3) -> bool { bool o2 = ((om >> li) & 1u) != 0; li++; return o2; };
+            shade_hit(a.t.s, o, d, 0, h, a.max_depth, any_hit, out);
+            f3 contrib = out.local + out.bg_weight * bg;
+            write_pixel_direct(a.t.direct_rgb, pixel_byte_offset(a.t.f, pi, pj, a.t.direct_packed), contrib);
+        }
+        shaded += min(32u, n_hits - base);
+    }
+    if (pushing && lane == 0) {
+        __threadfence();
+        if (shaded) atomicAdd(a.y.done + 1, shaded);
+        spin_until_ge(a.y.done + 1, n_hits, a.t.sticky, 100);
+        if (a.y.sync && a.y.rank != 0) spin_until_ge(a.y.sync + 64, a.y.frame, a.t.sticky, 200);   // frame open?
+        __threadfence();
+    }
+    __syncwarp();
+    // ---- phase 3: packed tiles -> the shared frame
+    if (pushing) {
+        const FrameDev& f = a.t.f;
+        const uint32_t world = (uint32_t)f.world, src = a.y.rank;
+        const uint32_t n_owned = a.push.tiles_total > src ? (a.push.tiles_total - src + world - 1) / world : 0u;
+        const uint32_t stride = gridDim.x * blockDim.x;
+        if (a.push.wide16) {
+            const uint32_t chunks_per_row = (uint32_t)(f.tile_w * 3) >> 4, chunks_per_tile = chunks_per_row * (uint32_t)f.tile_h;
+            const uint32_t total = n_owned * chunks_per_tile;
+            for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+                uint32_t tl = q / chunks_per_tile, r = q % chunks_per_tile;
+                uint32_t tile = src + tl * world;
+                int y = (int)(r / chunks_per_row), cb = (int)(r % chunks_per_row) * 16;
+                int tx = (int)(tile % (uint32_t)f.tiles_x), ty = (int)(tile / (uint32_t)f.tiles_x);
+                int j = ty * f.tile_h + y;
+                if (j >= f.H) continue;
+                int row_bytes = min(f.tile_w, f.W - tx * f.tile_w) * 3;
+                if (cb >= row_bytes) continue;
+                size_t src0 = ((size_t)tl * f.tile_pix + (size_t)y * f.tile_w) * 3 + cb;
+                size_t dst0 = ((size_t)tx * f.tile_w + (size_t)j * f.W) * 3 + cb;
+                if (cb + 16 <= row_bytes) {
+                    *reinterpret_cast<uint4*>(a.push.frame + dst0) = __ldcg(reinterpret_cast<const uint4*>(a.push.packed + src0));
+                } else {
+                    for (int k = 0; k < row_bytes - cb; k++) a.push.frame[dst0 + k] = __ldcg(a.push.packed + src0 + k);
+                }
+            }
+        } else {
+            const uint32_t quads_per_row = (uint32_t)f.tile_w >> 2, quads_per_tile = quads_per_row * (uint32_t)f.tile_h;
+            const uint32_t total = n_owned * quads_per_tile;
+            for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+                uint32_t tl = q / quads_per_tile, r = q % quads_per_tile;
+                uint32_t tile = src + tl * world;
+                int y = (int)(r / quads_per_row), x0 = (int)(r % quads_per_row) * 4;
+                int tx = (int)(tile % (uint32_t)f.tiles_x), ty = (int)(tile / (uint32_t)f.tiles_x);
+                int j = ty * f.tile_h + y, i0 = tx * f.tile_w + x0;
+                if (j >= f.H || i0 >= f.W) continue;
+                int npx = min(4, f.W - i0);
+                size_t src0 = ((size_t)tl * f.tile_pix + (size_t)y * f.tile_w + x0) * 3;
+                size_t dst0 = ((size_t)i0 + (size_t)j * f.W) * 3;
+                for (int k = 0; k < 3 * npx; k++) a.push.frame[dst0 + k] = __ldcg(a.push.packed + src0 + k);
+            }
+        }
+    }
+    // ---- exit: the last CTA completes the frame
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                            // this CTA's stores (peer memory included) are out
+        uint32_t prev = atomicAdd(a.y.done + 2, 1u);
+        if (prev == gridDim.x - 1) {
+            if (a.y.sync && a.y.world > 1) {
+                uint32_t* slot = a.y.sync + (a.y.frame % 64u);
+                if (a.y.rank != 0) {
+                    atomicAdd_system(slot, 1u);
+                } else {
+                    spin_until_ge(slot, a.y.world - 1, a.t.sticky, 100);
+                    __threadfence_system();
+                    *(volatile uint32_t*)(a.y.sync + ((a.y.frame + 32u) % 64u)) = 0u;   // the slot that comes into use 32 frames on
+                }
+            }
+            a.y.done[0] = 0; a.y.done[1] = 0; a.y.done[2] = 0;                         // ready for the next frame
+            __threadfence();
+        }
+    }
+}
 
 // ---- k_paths: every bounce generation in ONE launch --------------------------------------------------
 // The wave loop pays two kernel launches (and, with dielectrics, a host round trip) per generation,
@@ -1249,11 +1418,6 @@ void launch_traverse(rt_ctx* c, const TravArgs& a, bool count) {
         blocks = SHADE ? c->wide_shade_blocks : c->wide_blocks;
         if (count) k_traverse<MODE, true, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
         else k_traverse<MODE, false, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
-    } else if (FUSE && a.s.nodes4 != nullptr && c->wide_bvh == 3) {
-        constexpr int W = FUSE ? 2 : 0;   // experimental hybrid walk
-        blocks = SHADE ? c->hybrid_shade_blocks : c->hybrid_blocks;
-        if (count) k_traverse<MODE, true, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
-        else k_traverse<MODE, false, FUSE, W, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
     } else {
         if (count) k_traverse<MODE, true, FUSE, 0, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
         else k_traverse<MODE, false, FUSE, 0, SHADE><<<blocks, TRAV_TPB, 0, c->stream>>>(a);
@@ -1387,14 +1551,29 @@ WaveResult run_bounce_waves(rt_ctx* c, const TravArgs& ta, const ShadeArgs& sa, 
 
 }  // namespace
 
+// Can any hit spawn a live child ray?  A mirror child has level + 1 (world.cpp:105), alive from max_depth 1 on; the
+// refracted child of a dielectric has level * 2 (world.cpp:98), which stays 0 below a primary ray and is therefore
+// alive even at max_depth 0 (the reference's guard is `level > RECURSION_DEPTH`, world.cpp:33).
+bool rt_scene_bounces(const rt_ctx* c, int max_depth) {
+    return c->has_reflective && (max_depth >= 1 || (c->has_dielectric && max_depth >= 0));
+}
+
 // rt_render_push: can the frame's only kernel push its tiles itself?  Bounce-free scenes only: their pixels are
 // final the moment the batch is shaded.
 bool rt_frame_pushes_inline(const rt_ctx* c, const rt_render_params* p) {
-    const bool bounce = c->has_reflective && p->max_depth >= 1;
+    const bool bounce = rt_scene_bounces(c, p->max_depth);
     return !bounce && (p->flags & RT_FLAG_PACKED_TILES) && !(p->world_size > 1 && p->steal_pool_div > 0) &&
            wave0_shades_inline(c, true);
 }
 
+
+// Can the whole frame run as one k_frame launch?  Bounce-free scenes whose shadow rays ride in the primary lanes.
+// RT_FRAME_KERNEL: 0 never, 1 where the frame is pushed to a shared (multi-GPU) frame, 2 always.
+bool rt_frame_kernel_ok(const rt_ctx* c, const rt_render_params* p, bool pushing) {
+    const bool stealing = p->world_size > 1 && p->steal_pool_div > 0;
+    return (c->frame_kernel == 2 || (c->frame_kernel == 1 && pushing)) && !rt_scene_bounces(c, p->max_depth) && c->fuse_shadow &&
+           c->scene.n_lights > 0 && c->scene.n_lights <= 8 && !stealing && !(p->flags & RT_FLAG_WARP_TIMES);
+}
 
 // Waits for the context's stream and turns the sticky device error word into an exception.
 void rt_sync_and_check(rt_ctx* c) {
@@ -1404,11 +1583,16 @@ void rt_sync_and_check(rt_ctx* c) {
     uint32_t fl = *c->h_sticky;
     if (fl) {
         RT_CUDA(cudaMemsetAsync(c->d_sticky.p, 0, sizeof(uint32_t), st));
-        if (fl & 4u) throw RtError{RT_ERR_CUDA, "peer frame handshake timed out (a rank did not arrive within ~2 s)"};
-        if (fl & 1u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow: a wave spawned more rays than the queue holds"};
-        if (fl & 8u) throw RtError{RT_ERR_QUEUE_OVERFLOW, "pending-ray stack overflow in k_paths (dielectric chain deeper than RT_PATH_STACK); set RT_PATH_KERNEL=0"};
-        throw RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow (BVH deeper than RT_STACK_SIZE)"};
+        throw rt_sticky_error(fl);
     }
+}
+
+RtError rt_sticky_error(uint32_t fl) {
+    if (!fl) return RtError{RT_OK, ""};
+    if (fl & 4u) return RtError{RT_ERR_CUDA, "peer frame handshake timed out (a rank did not arrive within ~2 s)"};
+    if (fl & 1u) return RtError{RT_ERR_QUEUE_OVERFLOW, "ray queue overflow: a wave spawned more rays than the queue holds"};
+    if (fl & 8u) return RtError{RT_ERR_QUEUE_OVERFLOW, "pending-ray stack overflow in k_paths (dielectric chain deeper than RT_PATH_STACK); set RT_PATH_KERNEL=0"};
+    return RtError{RT_ERR_QUEUE_OVERFLOW, "traversal stack overflow (BVH deeper than RT_STACK_SIZE)"};
 }
 
 void rt_render_init(rt_ctx* c) {
@@ -1424,16 +1608,17 @@ void rt_render_init(rt_ctx* c) {
                         persistent_blocks(k_traverse<MODE_QUEUE, false, true, 1>, TRAV_TPB, c->sm_count));
     c->fused_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, 0, true>, TRAV_TPB, c->sm_count);
     c->wide_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, 1, true>, TRAV_TPB, c->sm_count);
-    c->hybrid_blocks = lo(persistent_blocks(k_traverse<MODE_PRIMARY, false, true, 2>, TRAV_TPB, c->sm_count),
-                          persistent_blocks(k_traverse<MODE_QUEUE, false, true, 2>, TRAV_TPB, c->sm_count));
-    c->hybrid_shade_blocks = persistent_blocks(k_traverse<MODE_PRIMARY, false, true, 2, true>, TRAV_TPB, c->sm_count);
     c->shade_blocks = lo(persistent_blocks(k_shade<true>, SHADE_TPB, c->sm_count),
                          persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
+    c->frame_blocks = persistent_blocks(k_frame<false>, TRAV_TPB, c->sm_count);
+    c->d_fsync.reserve(4);
+    RT_CUDA(cudaMemset(c->d_fsync.p, 0, 4 * sizeof(uint32_t)));
     if (c->blocks_per_sm > 0) {   // RT_BLOCKS_PER_SM: cap the persistent grids (tuning)
         int cap = c->blocks_per_sm * c->sm_count;
         c->trace_blocks = lo(c->trace_blocks, cap);
         c->fused_blocks = lo(c->fused_blocks, cap);
         c->fused_shade_blocks = lo(c->fused_shade_blocks, cap);
+        c->frame_blocks = lo(c->frame_blocks, cap);
         c->shadow_blocks = lo(c->shadow_blocks, cap);
         c->path_blocks = lo(c->path_blocks, cap);
     }
@@ -1452,7 +1637,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     setup_layout(c, cam, p);
     FrameDev f = frame_dev(c, p);
     const bool count = (p->flags & RT_FLAG_COUNT_WORK) != 0;
-    const bool bounce = c->has_reflective && p->max_depth >= 1;
+    const bool bounce = rt_scene_bounces(c, p->max_depth);
     const size_t pix_cap = (size_t)f.n_local_pix + (size_t)f.n_pool_blocks * 32u;   // own tiles + everything stealable
     ensure_queues(c, pix_cap, bounce);
     c->d_accum.reserve(3 * (pix_cap ? pix_cap : 1));
@@ -1469,7 +1654,6 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     ta.aux_t = aux_dev ? aux_dev->t : nullptr;
     ta.brute = (p->flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
     ta.cap = (uint32_t)c->queue_cap;
-    ta.hybrid_after = c->hybrid_after;
     ShadeArgs sa;
     memset(&sa, 0, sizeof sa);
     sa.s = c->scene; sa.cam = ta.cam; sa.f = f;
@@ -1479,7 +1663,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
 
     if (p->flags & RT_FLAG_WARP_TIMES) {
         int mb = c->trace_blocks;
-        for (int b : {c->fused_blocks, c->fused_shade_blocks, c->wide_blocks, c->wide_shade_blocks, c->hybrid_blocks, c->hybrid_shade_blocks})
+        for (int b : {c->fused_blocks, c->fused_shade_blocks, c->wide_blocks, c->wide_shade_blocks})
             mb = b > mb ? b : mb;
         c->d_warp_times.reserve(2 * (size_t)mb * (TRAV_TPB / 32));
         ta.warp_times = c->d_warp_times.p;
@@ -1494,8 +1678,41 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     ta.remote_out = (c->remote_output && direct) ? 1 : 0;
     uint32_t launches = 0;
     const bool has_work = f.n_local_pix > 0 || f.steal_cursor != nullptr;
-    if (has_work) launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, c->ev[1], c->ev[2]);
-    else { RT_CUDA(cudaEventRecord(c->ev[1], st)); RT_CUDA(cudaEventRecord(c->ev[2], st)); }
+    const bool pushing = c->push.frame != nullptr;
+    if (direct && rt_frame_kernel_ok(c, p, pushing) && (has_work || pushing)) {
+        // the whole frame in one launch: trace + shadow rays, shade, (push + handshake)
+        FrameArgs fa;
+        memset(&fa, 0, sizeof fa);
+        ta.q = queue_of(c, 0);
+        ta.wave = c->d_waves.p;
+        ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p; ta.occl = c->d_occl.p;
+        ta.refill_min = c->refill_primary_fused;
+        ta.loop_style = c->loop_primary;
+        fa.t = ta;
+        fa.max_depth = p->max_depth;
+        fa.y.done = c->d_fsync.p;
+        if (pushing) {
+            fa.y.sync = c->push.world > 1 ? (uint32_t*)c->push.sync : nullptr;
+            fa.y.frame = c->push.frame_index; fa.y.rank = (uint32_t)c->push.rank; fa.y.world = (uint32_t)c->push.world;
+            fa.push.packed = (const uint8_t*)rgb_dev;
+            fa.push.frame = (uint8_t*)c->push.frame;
+            fa.push.tiles_total = (uint32_t)c->layout.tiles_x * (uint32_t)c->layout.tiles_y;
+            fa.push.wide16 = (f.W * 3) % 16 == 0 && (f.tile_w * 3) % 16 == 0 && ((uintptr_t)rgb_dev & 15) == 0 &&
+                             ((uintptr_t)c->push.frame & 15) == 0;
+        }
+        if (count) k_frame<true><<<c->frame_blocks, TRAV_TPB, 0, st>>>(fa);
+        else k_frame<false><<<c->frame_blocks, TRAV_TPB, 0, st>>>(fa);
+        RT_CUDA(cudaGetLastError());
+        launches++;
+        c->push.done = true;
+        RT_CUDA(cudaEventRecord(c->ev[1], st));
+        RT_CUDA(cudaEventRecord(c->ev[2], st));
+    } else if (has_work) {
+        launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, c->ev[1], c->ev[2]);
+    } else {
+        RT_CUDA(cudaEventRecord(c->ev[1], st));
+        RT_CUDA(cudaEventRecord(c->ev[2], st));
+    }
     RT_CUDA(cudaEventRecord(c->ev[3], st));
 
     WaveResult wr;
@@ -1577,7 +1794,7 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
     cudaStream_t st = c->stream;
     if (n == 0) return;
     const bool count = false;
-    const bool bounce = shade && c->has_reflective && max_depth >= 1;
+    const bool bounce = shade && rt_scene_bounces(c, max_depth);
     ensure_queues(c, n, true);
     size_t cap = c->queue_cap;
     c->d_accum.reserve(3 * (size_t)n);
@@ -1614,7 +1831,6 @@ void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth,
     ta.aux_prim = c->d_aux_prim.p; ta.aux_t = c->d_aux_t.p;
     ta.brute = (flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
     ta.cap = (uint32_t)cap;
-    ta.hybrid_after = c->hybrid_after;
     ShadeArgs sa;
     memset(&sa, 0, sizeof sa);
     sa.s = c->scene; sa.hits = c->d_hits.p; sa.hitq = c->d_hitq.p; sa.accum = c->d_accum.p;

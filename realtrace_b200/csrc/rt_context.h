@@ -93,8 +93,37 @@ struct TileLayout {
     }
 };
 
+#define RT_MAX_DEVICES 16
+
 struct rt_ctx {
     int device = 0;
+    // ---- one context driving several GPUs (rt_create_multi): the context the caller holds is rank 0, `kids` are
+    // ranks 1..n-1 on the other devices (scene replicated, frame split into interleaved tiles); kids have parent set
+    std::vector<rt_ctx*> kids;
+    rt_ctx* parent = nullptr;
+    void* mg_sync = nullptr;               // handshake words in rank 0's memory (rt_peer_sync layout), mapped by every rank
+    uint32_t mg_frame = 0;                 // frames rendered through the multi-device path (handshake slot counter)
+    cudaEvent_t mg_ev[2] = {};
+    std::vector<void*> host_registered;    // caller buffers page-locked on first use by rt_render_enqueue (unregistered at destroy)
+    cudaStream_t copy_stream = nullptr;    // frame -> host copies of this rank (its own PCIe link), overlapping the next frame
+    DevBuf<uint8_t> d_packed;              // this rank's tiles back to back (scenes with bounces: resolve target before the push)
+    // A frame every rank can store into: for n > 1 a virtual address range whose granules are physically spread
+    // round robin over the ranks' GPUs (multi_device.cu), else a plain allocation on this device.
+    struct SharedFrame {
+        void* va = nullptr;
+        size_t bytes = 0, gran = 0, granules = 0;
+        bool vmm = false;
+        std::vector<unsigned long long> handles;   // CUmemGenericAllocationHandle per granule
+        std::vector<int> owner;                    // rank whose GPU backs the granule
+    };
+    struct FrameSlot {                     // rt_render_enqueue / rt_render_wait: two frames in flight
+        SharedFrame frame;
+        cudaEvent_t ready = nullptr;       // frame complete in device memory (rank 0's render stream)
+        cudaEvent_t done[RT_MAX_DEVICES] = {};     // rank r's share of the host copy has landed
+        uint32_t* h_sticky = nullptr;      // pinned, RT_MAX_DEVICES words: each rank's error word after the frame
+        bool in_flight = false;
+    };
+    FrameSlot slots[2];
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
     int sm_count = 148;
@@ -116,7 +145,7 @@ struct rt_ctx {
     DevBuf<float> d_tri_v;
     DevBuf<uint32_t> d_tri_mat, d_tri_obj;
     DevBuf<float4> d_tri_rgb, d_tris, d_nodes, d_nodes4, d_box_lo, d_box_hi, d_materials, d_lights;
-    int wide_bvh = 1;                      // 4-wide collapse of the tree: 0 off, 1 for k_paths (bounce paths), 2 everywhere, 3 k_paths + hybrid walk in k_traverse (experimental) (RT_WIDE_BVH)
+    int wide_bvh = 1;                      // 4-wide collapse of the tree: 0 off, 1 for k_paths (bounce paths), 2 everywhere (RT_WIDE_BVH)
     DevBuf<AnalyticPrim> d_analytic;
     DevBuf<uint64_t> d_keys[2];
     DevBuf<uint32_t> d_vals[2];
@@ -128,7 +157,6 @@ struct rt_ctx {
     SceneDev scene{};
     rt_build_stats build_stats{};
     int leaf_size = 1;                     // measured best on B200 with the if-if walk (profiles/r1_tuning.md)
-    float scene_abs_max = 1.0f;
 
     // ---- render state
     TileLayout layout;
@@ -162,12 +190,20 @@ struct rt_ctx {
     bool refit_pending = false;
     int trace_blocks = 0, fused_blocks = 0, shadow_blocks = 0, shade_blocks = 0, path_blocks = 0;
     int wide_blocks = 0, path_wide_blocks = 0, fused_shade_blocks = 0, wide_shade_blocks = 0;
-    int hybrid_blocks = 0, hybrid_shade_blocks = 0;
-    int hybrid_after = 32;                 // RT_WIDE_BVH=3 (experimental): binary steps before a ray moves to the 4-wide view (RT_HYBRID_AFTER)
     int tile_bucket_bits = 5;              // heavy-tiles-first: mantissa bits of the cost kept in the sort key (RT_TILE_BUCKET_BITS)
     int fuse_shade = 1;                    // primary hits shaded inside the fused traversal kernel (RT_FUSE_SHADE): 0 never,
                                            // 1 when that kernel also pushes finished tiles to a remote frame, 2 always
     bool remote_output = false;            // rt_render_push: the frame being rendered into sits in another GPU's memory
+    int frame_kernel = 2;                  // whole bounce-free frames in one k_frame launch (RT_FRAME_KERNEL): 0 never, 1 when pushed to a shared frame, 2 always
+    int frame_blocks = 0;
+    DevBuf<uint32_t> d_fsync;              // k_frame's phase counters (zero between frames)
+    struct PushTarget {                    // set by rt_push_frame around rt_render_frame: where this rank's tiles go
+        void* frame = nullptr;             // the shared frame (nullptr: not pushing)
+        void* sync = nullptr;
+        uint32_t frame_index = 0;
+        int rank = 0, world = 1;
+        bool done = false;                 // rt_render_frame pushed (and signalled) inside its one kernel
+    } push;
     uint64_t launch_total = 0;             // kernels enqueued by frame-level calls since rt_create (rt_debug_frame_launches)
     int path_kernel = 1;                   // bounce generations in one k_paths launch (RT_PATH_KERNEL=0: wave loop)
     int fuse_shadow = 1;                   // shadow rays ride in the lane that found the hit (RT_FUSE_SHADOW)
@@ -190,6 +226,22 @@ void rt_render_init(rt_ctx* c);                                     // render.cu
 void rt_sync_and_check(rt_ctx* c);                                  // render.cu
 void rt_peer_barrier_enqueue(rt_ctx* c, void* sync_buf, int world, uint32_t epoch);   // render.cu
 void rt_peer_sync_enqueue(rt_ctx* c, void* sync_buf, int rank, int world, uint32_t frame_index, int phase);   // render.cu
+bool rt_scene_bounces(const rt_ctx* c, int max_depth);                     // render.cu
+bool rt_frame_kernel_ok(const rt_ctx* c, const rt_render_params* p, bool pushing);   // render.cu
 bool rt_frame_pushes_inline(const rt_ctx* c, const rt_render_params* p);   // render.cu
 void rt_assemble(rt_ctx* c, const void* packed, int src_rank, int world, int width, int height, int tile_w,
                  int tile_h, void* frame);                          // render.cu
+RtError rt_sticky_error(uint32_t flags);                             // render.cu: device error word -> error (code RT_OK if 0)
+void rt_push_frame(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, void* packed_dev, void* frame_dev,
+                   void* sync_buf, uint32_t frame_index, const rt_aux_out* aux_dev);   // api.cu: body of rt_render_push
+void rt_run_microbench(rt_ctx* c, rt_microbench_result* out);         // microbench.cu
+// multi_device.cu
+void rt_frame_reserve(rt_ctx* c, rt_ctx::SharedFrame& f, size_t bytes);
+void rt_frame_release(rt_ctx* c, rt_ctx::SharedFrame& f);
+void rt_multi_attach(rt_ctx* c, const std::vector<int>& devices, rt_ctx* (*make_ctx)(int device));
+void rt_multi_build(rt_ctx* c, bool refit_only);
+void rt_multi_enqueue_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p, void* frame_dev,
+                            const rt_aux_out* aux_dev);
+void rt_multi_collect(rt_ctx* c, rt_frame_stats* stats);
+void rt_frame_download_async(rt_ctx* c, const rt_ctx::SharedFrame& f, uint8_t* host, size_t bytes, cudaEvent_t ready,
+                             cudaEvent_t* done, uint32_t* h_sticky);

@@ -168,8 +168,10 @@ public:
     enum Kind { SPHERE, PLANE, CYLINDER, TRIANGLE };
     Object(Material* mat) : material(mat), isSolid(true) {}
     virtual ~Object() {}
-    virtual bool intersect(Ray& ray) const;                 // one-ray GPU query against this object alone is
-                                                            // not offered: use World::firstIntersection
+    // object.h:15: one ray against THIS object alone, with the reference's acceptance rules
+    // (Ray::setParameter).  A host-side convenience of the class mirror (plain FP64 like the
+    // reference); rendering and World::firstIntersection never call it — they run on the GPU.
+    virtual bool intersect(Ray& ray) const = 0;
     virtual Color shade(const Ray& ray) const { return material->shade(ray, isSolid); }
     Material* getMaterial() const { return material; }
     virtual Vector3D getNormalAtPosition(const Vector3D& position) const = 0;
@@ -181,6 +183,7 @@ class Sphere : public Object {                              // sphere.h:10-25
     double radius;
 public:
     Sphere(const Vector3D& _pos, double _rad, Material* mat) : Object(mat), position(_pos), radius(_rad) {}
+    bool intersect(Ray& ray) const override;               // sphere.cpp:5-39
     Vector3D getNormalAtPosition(const Vector3D& p) const override { return p - position; }
     Kind kind() const override { return SPHERE; }
     const Vector3D& getPosition() const { return position; }
@@ -192,6 +195,7 @@ class Plane : public Object {                               // plane.h:10-30
 public:
     Plane(const Vector3D& p1, const Vector3D& p2, const Vector3D& p3, const Vector3D& p4, Material* mat)
         : Object(mat), position1(p1), position2(p2), position3(p3), position4(p4) { Normal = crossProduct(p3 - p1, p2 - p1); }
+    bool intersect(Ray& ray) const override;               // plane.cpp:12-27
     Vector3D getNormalAtPosition(const Vector3D&) const override { return Normal; }
     Kind kind() const override { return PLANE; }
     const Vector3D& getCorner(int i) const { return i == 0 ? position1 : i == 1 ? position2 : i == 2 ? position3 : position4; }
@@ -203,6 +207,7 @@ class Cylinder : public Object {                            // cylinder.h:10-25
     Vector3D up;
 public:
     Cylinder(const Vector3D& _pos, double _rad, const Vector3D& u, Material* mat) : Object(mat), position(_pos), radius(_rad), up(u) {}
+    bool intersect(Ray& ray) const override;               // cylinder.cpp:14-32
     Vector3D getNormalAtPosition(const Vector3D& p) const override {
         double t = dotProduct(p - position, up) / dotProduct(up, up);
         return p - position - t * up;
@@ -217,6 +222,7 @@ class Triangle : public Object {                            // triangle.h:14-37
     Vector3D vertexA, vertexB, vertexC;
 public:
     Triangle(const Vector3D& a, const Vector3D& b, const Vector3D& c, Material* mat) : Object(mat), vertexA(a), vertexB(b), vertexC(c) {}
+    bool intersect(Ray& ray) const override;               // triangle.cpp:10-24
     Vector3D getNormalAtPosition(const Vector3D&) const override { return crossProduct(vertexA - vertexB, vertexA - vertexC); }
     Kind kind() const override { return TRIANGLE; }
     BBox getWorldBound();
@@ -286,7 +292,8 @@ private:
 // ---- camera.h:7-34 -------------------------------------------------------------------------------
 class Camera {
     Vector3D position, target, up, line_of_sight, u, v, w;
-    unsigned char* bitmap;
+    unsigned char* bitmap;                                  // page-locked (rt_host_alloc) where a CUDA device exists,
+    bool bitmap_pinned;                                     // so the frame arrives by asynchronous DMA
     int width, height;
     float fovy, focalDistance, focalWidth, focalHeight, aspect;
     friend class RenderEngine;
@@ -313,15 +320,25 @@ public:
     // (renderengine.cpp:10-26).  Here one call renders the whole frame on the GPU into
     // Camera::getBitmap() and returns true, so `while(!engine->renderLoop()){}` still terminates.
     bool renderLoop() { render(); return true; }
-    void render();                                          // the name BASELINE.json's north star uses
+    void render();                                          // the name BASELINE.json's north star uses; the frame
+                                                            // is split over every visible GPU (setDevices narrows it)
+    // Which CUDA devices World's GPU core uses (default: all visible; call before the first render).
+    static void setDevices(const std::vector<int>& device_ids);
     void setMaxDepth(int d) { world->setMaxDepth(d); }
     // rays / timings of the last frame (include/realtrace_b200.h: rt_frame_stats)
     void frameStats(unsigned long long& primary, unsigned long long& shadow, unsigned long long& secondary, float& ms_device) const;
 };
 
-// ---- lumina.cpp:195-290: OBJ loader (SCALING_FACTOR 15; the 2000-face cap is a parameter) ----------
+// ---- lumina.cpp:195-290: OBJ loader (SCALING_FACTOR 15).  The same call loads the same scene as the
+// reference: at most 2000 faces (lumina.cpp:266) unless max_faces says otherwise (< 0: no cap).
+// texel_mode selects how a texture is fetched (lumina.cpp:175-187 goes through the un-vendored DevIL, see
+// DESIGN.md section 2): LITERAL restates those lines on an RGBA8 top-left-origin image (swapped row/column,
+// no /255, the un-decremented vt index of :249); NORMALISED is texel/255 with the usual OBJ conventions.
+enum { RT_TEXEL_NORMALISED = 0, RT_TEXEL_LITERAL = 1 };
+const int LUMINA_MAX_FACES = 2000;
 void load_image_from_obj(World* world, std::string file_name, std::string texture_file_name = "",
-                         std::string occlusion_map_file_name = "", int max_faces = -1);
+                         std::string occlusion_map_file_name = "", int max_faces = LUMINA_MAX_FACES,
+                         int texel_mode = RT_TEXEL_NORMALISED);
 void init_material_from_obj(Material* m);                   // lumina.cpp:163-172
 
 // ---- lumina.cpp:424-439 SaveImage: the frame as an image file.  The reference goes through DevIL

@@ -16,6 +16,9 @@
 
 namespace rtb200 {
 
+// RenderEngine::setDevices: empty = every visible GPU
+static std::vector<int> g_devices;
+
 struct Device {
     rt_ctx* ctx = nullptr;
     unsigned long committed_revision = 0;
@@ -24,7 +27,13 @@ struct Device {
 
     Device() {
         memset(&stats, 0, sizeof stats);
-        int rc = rt_create(&ctx, 0);
+        // one context over all the GPUs of the node; RT_DEVICES=k limits it to the first k
+        int rc;
+        if (!g_devices.empty()) rc = rt_create_multi(&ctx, g_devices.data(), (int)g_devices.size());
+        else {
+            const char* e = getenv("RT_DEVICES");
+            rc = rt_create_multi(&ctx, nullptr, e ? atoi(e) : 0);
+        }
         if (rc != RT_OK) throw std::runtime_error(std::string("realtrace_b200: ") + rt_last_error(nullptr));
     }
     ~Device() { if (ctx) rt_destroy(ctx); }
@@ -136,8 +145,56 @@ Color BarycentricMaterial::shade(const Ray& in, const bool) const {             
     return alpha * colors[0] + beta * colors[1] + gamma * colors[2];
 }
 
-bool Object::intersect(Ray&) const {
-    throw std::logic_error("realtrace_b200: per-object CPU intersection is not part of the GPU core; use World::firstIntersection");
+// ---- Object::intersect (object.h:15): one ray against one object, on the host in FP64 with the reference's
+// acceptance rules.  Part of the class mirror only — no frame, firstIntersection or shade_ray goes through these.
+namespace {
+// inside test + t of the ray against triangle (a, b, c): 0 outside / degenerate, 1 inside (t set)
+int ray_triangle(const Ray& r, const Vector3D& a, const Vector3D& b, const Vector3D& c, double& t) {
+    const Vector3D e1 = a - b, e2 = a - c, s = a - r.getOrigin(), d = r.getDirection();
+    const double A = det3(e1, e2, d);
+    if (std::fabs(A) < 1e-7) return 0;                                                      // triangle.h:12, plane.cpp:9
+    const double beta = det3(s, e2, d) / A, gamma = det3(e1, s, d) / A;
+    if (!(beta > 0.0 && gamma > 0.0 && beta + gamma < 1.0)) return 0;
+    t = det3(e1, e2, s) / A;
+    return 1;
+}
+}  // namespace
+
+bool Triangle::intersect(Ray& r) const {                                                    // triangle.cpp:10-24
+    double t;
+    return ray_triangle(r, vertexA, vertexB, vertexC, t) && r.setParameter((float)t, this);
+}
+
+bool Plane::intersect(Ray& r) const {                                                       // plane.cpp:12-27
+    // two triangles; the first one that CONTAINS the ray ends the test, whether or not its t was accepted
+    double t;
+    if (ray_triangle(r, position1, position2, position3, t)) { r.setParameter((float)t, this); return true; }
+    if (ray_triangle(r, position1, position3, position4, t)) { r.setParameter((float)t, this); return true; }
+    return false;
+}
+
+bool Sphere::intersect(Ray& r) const {                                                      // sphere.cpp:5-39
+    const Vector3D oc = r.getOrigin() - position;
+    const double b = 2.0 * dotProduct(r.getDirection(), oc), c = dotProduct(oc, oc) - radius * radius;
+    const double disc = b * b - 4.0 * c;
+    if (!(disc >= 0.0)) return false;
+    if (disc == 0.0) { r.setParameter((float)(-b / 2.0), this); return true; }
+    const double D = std::sqrt(disc);
+    const bool far_root = r.setParameter((float)((-b + D) / 2.0), this);                    // far root first, then near
+    const bool near_root = r.setParameter((float)((-b - D) / 2.0), this);
+    return far_root || near_root;
+}
+
+bool Cylinder::intersect(Ray& r) const {                                                    // cylinder.cpp:4-32
+    const Vector3D d = r.getDirection(), oc = r.getOrigin() - position;
+    const Vector3D dp = d - dotProduct(d, up) * up, op = oc - dotProduct(oc, up) * up;
+    const double A = dotProduct(dp, dp), B = 2.0 * dotProduct(dp, op), C = dotProduct(op, op) - radius * radius;
+    const double disc = B * B - 4.0 * A * C;
+    if (disc < 0.0) return false;
+    double lo = (-B + std::sqrt(disc)) / (2.0 * A), hi = (-B - std::sqrt(disc)) / (2.0 * A);
+    if (lo > hi) std::swap(lo, hi);
+    r.setParameter((float)(lo > 0.0 ? lo : hi), this);      // the larger root is never tried when 0 < lo <= SMALLEST_DIST
+    return true;
 }
 
 BBox Triangle::getWorldBound() {                                                            // triangle.cpp:31-40
@@ -183,14 +240,21 @@ Camera::Camera(const Vector3D& _pos, const Vector3D& _target, const Vector3D& _u
     w = -line_of_sight; w.normalize();
     u = crossProduct(up, w); u.normalize();
     v = crossProduct(w, u); v.normalize();
-    bitmap = new unsigned char[(size_t)width * height * 3];
+    // page-locked where a CUDA device exists (the frame then arrives by DMA), plain memory otherwise (a Camera can
+    // be built and queried on a machine without a GPU; rendering there throws)
+    void* pinned = nullptr;
+    bitmap_pinned = rt_host_alloc(&pinned, (uint64_t)width * height * 3) == RT_OK;
+    bitmap = bitmap_pinned ? (unsigned char*)pinned : new unsigned char[(size_t)width * height * 3];
     memset(bitmap, 0, (size_t)width * height * 3);
     focalHeight = 1.0f;
     aspect = float(width) / float(height);
     focalWidth = focalHeight * aspect;
     focalDistance = focalHeight / (2.0 * tan(fovy * M_PI / (180.0 * 2.0)));
 }
-Camera::~Camera() { delete[] bitmap; }
+Camera::~Camera() {
+    if (bitmap_pinned) rt_host_free(bitmap);
+    else delete[] bitmap;
+}
 const Vector3D Camera::get_ray_direction(const int i, const int j) const {
     Vector3D dir(0.0, 0.0, 0.0);
     dir += -w * (double)focalDistance;
@@ -226,6 +290,8 @@ void RenderEngine::render() {
     d.check(rt_render(d.ctx, &c, &p, camera->bitmap, nullptr, &d.stats), "render");
 }
 
+void RenderEngine::setDevices(const std::vector<int>& device_ids) { rtb200::g_devices = device_ids; }
+
 void RenderEngine::frameStats(unsigned long long& primary, unsigned long long& shadow, unsigned long long& secondary, float& ms_device) const {
     primary = shadow = secondary = 0; ms_device = 0;
     if (!world->dev) return;
@@ -251,12 +317,17 @@ bool read_png(const std::string& path, Image& img) {
         uint32_t len = be32(o);
         std::string type((const char*)&buf[o + 4], 4);
         if (o + 12 + len > buf.size()) return false;
-        if (type == "IHDR") { img.w = (int)be32(o + 8); img.h = (int)be32(o + 12); bit_depth = buf[o + 16]; colour = buf[o + 17]; interlace = buf[o + 20]; }
+        if (type == "IHDR") {
+            if (len != 13) return false;                                  // a truncated header must not be read past its end
+            uint32_t w32 = be32(o + 8), h32 = be32(o + 12);
+            if (w32 == 0 || h32 == 0 || w32 > 32768u || h32 > 32768u) return false;
+            img.w = (int)w32; img.h = (int)h32; bit_depth = buf[o + 16]; colour = buf[o + 17]; interlace = buf[o + 20];
+        }
         else if (type == "IDAT") idat.insert(idat.end(), buf.begin() + o + 8, buf.begin() + o + 8 + len);
         else if (type == "IEND") break;
         o += 12 + len;
     }
-    if (bit_depth != 8 || interlace != 0 || (colour != 2 && colour != 6)) return false;
+    if (img.w <= 0 || img.h <= 0 || bit_depth != 8 || interlace != 0 || (colour != 2 && colour != 6)) return false;
     img.ch = colour == 2 ? 3 : 4;
     size_t stride = (size_t)img.w * img.ch;
     std::vector<unsigned char> raw((stride + 1) * img.h);
@@ -269,6 +340,7 @@ bool read_png(const std::string& path, Image& img) {
         unsigned char* cur = &img.px[stride * y];
         const unsigned char* prev = y ? &img.px[stride * (y - 1)] : nullptr;
         int filter = in[0];
+        if (filter > 4) return false;
         for (size_t x = 0; x < stride; x++) {
             int a = x >= (size_t)bpp ? cur[x - bpp] : 0, b = prev ? prev[x] : 0, c = (prev && x >= (size_t)bpp) ? prev[x - bpp] : 0;
             int v = in[1 + x];
@@ -283,6 +355,23 @@ bool read_png(const std::string& path, Image& img) {
         }
     }
     return true;
+}
+
+// "literal" fetch: lumina.cpp:175-187 on an RGBA8, top-left-origin image (what DevIL hands out for this PNG is
+// not pinned by the reference): u scales with the width but indexes ROWS, v the columns, the
+// range test compares the row with the height and the column with the width, values are not divided by 255.
+Color texel_literal(const Image& im, double u, double v) {
+    int i = (int)std::floor(u * im.w), j = (int)std::floor(v * im.h);
+    if (i >= 0 && i < im.h && j >= 0 && j < im.w) {
+        size_t o = ((size_t)i * im.w + j) * 4;                            // 4 bytes per texel (:184)
+        auto byte_at = [&](size_t k) -> double {                          // RGBA8 view of an RGB8 / RGBA8 image
+            size_t px = k / 4, ch = k % 4;
+            if (px >= (size_t)im.w * im.h) return 0.0;
+            return ch < (size_t)im.ch ? (double)im.px[px * im.ch + ch] : 255.0;
+        };
+        return Color(byte_at(o), byte_at(o + 1), byte_at(o + 2));
+    }
+    return Color(0.8, 0.1, 0.0);                                          // :186
 }
 
 // "normalised" fetch of realtrace_b200/objio.py: texel/255, u -> column, v -> row from the bottom.
@@ -300,7 +389,8 @@ void init_material_from_obj(Material* m) {                                      
     m->ka = 0.2; m->kd = 0.9; m->ks = 0.4; m->kr = 0.4; m->kt = 0.0; m->eta = 3.0; m->n = 128;
 }
 
-void load_image_from_obj(World* world, std::string file_name, std::string texture_file_name, std::string, int max_faces) {
+void load_image_from_obj(World* world, std::string file_name, std::string texture_file_name, std::string, int max_faces,
+                         int texel_mode) {
     std::ifstream is(file_name);
     if (!is.is_open()) throw std::runtime_error("load_image_from_obj: could not open " + file_name);   // lumina.cpp:197-200 exits
     Image tex;
@@ -324,11 +414,30 @@ void load_image_from_obj(World* world, std::string file_name, std::string textur
                 std::stringstream ss(data);
                 while (getline(ss, token, '/')) idx[i].push_back(token.empty() ? 0 : stoi(token));
             }
-            if (max_faces >= 0 && (int)all_triangles.size() >= max_faces) continue;
+            if (max_faces >= 0 && (int)all_triangles.size() >= max_faces) continue;          // lumina.cpp:266
+            for (int i = 0; i < 3; i++)
+                if (idx[i].empty() || idx[i][0] < 1 || (size_t)idx[i][0] > vertices.size())
+                    throw std::runtime_error("load_image_from_obj: face refers to vertex " + std::to_string(idx[i].empty() ? 0 : idx[i][0]) +
+                                             " of " + std::to_string(vertices.size()) + " (negative/relative indices are not supported)");
             const Vector3D &a = vertices[idx[0][0] - 1], &b = vertices[idx[1][0] - 1], &cc = vertices[idx[2][0] - 1];
             Material* m;
-            if (has_texture && idx[0].size() >= 2 && idx[1].size() >= 2 && idx[2].size() >= 2) {
-                auto tv = [&](int k) { const auto& p = texture_vertices[idx[k][1] - 1]; return texel(tex, p.first, p.second); };
+            bool textured = has_texture && idx[0].size() >= 2 && idx[1].size() >= 2 && idx[2].size() >= 2 &&
+                            idx[0][1] != 0 && idx[1][1] != 0 && idx[2][1] != 0;       // `f v//vn` carries no vt
+            if (textured) {
+                for (int i = 0; i < 3; i++)
+                    if (idx[i][1] < 1 || (size_t)idx[i][1] > texture_vertices.size())
+                        throw std::runtime_error("load_image_from_obj: face refers to texture vertex " + std::to_string(idx[i][1]) +
+                                                 " of " + std::to_string(texture_vertices.size()));
+                auto tv = [&](int k) {
+                    if (texel_mode == RT_TEXEL_LITERAL) {
+                        // texture_vertices[idx] without the -1 (lumina.cpp:249); one past the end is UB there, the error colour here
+                        size_t ti = (size_t)idx[k][1];
+                        if (ti >= texture_vertices.size()) return Color(0.8, 0.1, 0.0);
+                        return texel_literal(tex, texture_vertices[ti].first, texture_vertices[ti].second);
+                    }
+                    const auto& p = texture_vertices[idx[k][1] - 1];
+                    return texel(tex, p.first, p.second);
+                };
                 m = new BarycentricMaterial(world, a, b, cc, tv(0), tv(1), tv(2));
                 // the textured workloads keep the loader's coefficients so that depth > 0 has mirror bounces
                 m->ka = 0.2; m->kd = 0.9; m->ks = 0.4; m->kr = 0.4; m->kt = 0.0; m->eta = 3.0;
@@ -423,11 +532,12 @@ Camera* InteractiveCamera::makeCamera() const {
 }
 
 // ---- CPU-testable entry points: what the loader, the image writer and the orbit camera produce --------
-extern "C" int rt_host_load_obj(const char* obj, const char* texture, int max_faces, float* tri_v, float* tri_rgb,
-                                int capacity, char* err, int err_len) {
+extern "C" int rt_host_load_obj2(const char* obj, const char* texture, int max_faces, int texel_mode, int use_default_cap,
+                                 float* tri_v, float* tri_rgb, int capacity, char* err, int err_len) {
     try {
         World world;
-        load_image_from_obj(&world, obj, texture ? texture : "", "", max_faces);
+        if (use_default_cap) load_image_from_obj(&world, obj, texture ? texture : "");      // the reference's call: 2000 faces
+        else load_image_from_obj(&world, obj, texture ? texture : "", "", max_faces, texel_mode);
         int n = 0;
         for (Object* o : world.getObjectList()) {
             Triangle* t = static_cast<Triangle*>(o);
@@ -446,6 +556,26 @@ extern "C" int rt_host_load_obj(const char* obj, const char* texture, int max_fa
         if (err && err_len > 0) { strncpy(err, e.what(), err_len - 1); err[err_len - 1] = 0; }
         return -1;
     }
+}
+extern "C" int rt_host_load_obj(const char* obj, const char* texture, int max_faces, float* tri_v, float* tri_rgb,
+                                int capacity, char* err, int err_len) {
+    return rt_host_load_obj2(obj, texture, max_faces, RT_TEXEL_NORMALISED, 0, tri_v, tri_rgb, capacity, err, err_len);
+}
+// Object::intersect of one analytic object / triangle against one ray: kind 0 sphere (cx cy cz r), 1 plane (4 corners),
+// 2 cylinder (px py pz r ux uy uz), 3 triangle (3 vertices).  Returns the bool of intersect(); *t_out = the ray's t after.
+extern "C" int rt_host_object_intersect(int kind, const double* g, const double ray[6], float* t_out) {
+    World w;
+    Material m(&w);
+    Object* o = nullptr;
+    if (kind == 0) o = new Sphere(Vector3D(g[0], g[1], g[2]), g[3], &m);
+    else if (kind == 1) o = new Plane(Vector3D(g[0], g[1], g[2]), Vector3D(g[3], g[4], g[5]), Vector3D(g[6], g[7], g[8]), Vector3D(g[9], g[10], g[11]), &m);
+    else if (kind == 2) o = new Cylinder(Vector3D(g[0], g[1], g[2]), g[3], Vector3D(g[4], g[5], g[6]), &m);
+    else o = new Triangle(Vector3D(g[0], g[1], g[2]), Vector3D(g[3], g[4], g[5]), Vector3D(g[6], g[7], g[8]), &m);
+    Ray r(Vector3D(ray[0], ray[1], ray[2]), Vector3D(ray[3], ray[4], ray[5]));
+    bool hit = o->intersect(r);
+    if (t_out) *t_out = r.getParameter();
+    delete o;
+    return hit ? 1 : 0;
 }
 extern "C" int rt_host_save_png(const char* file, const unsigned char* rgb, int w, int h) { return save_png(file, rgb, w, h) ? 0 : -1; }
 extern "C" void rt_host_orbit_eye(float yaw, float pitch, float radius, float out[3]) {
@@ -489,9 +619,9 @@ extern "C" int rt_host_demo(const char* which, const char* assets_dir, int width
             load_image_from_obj(world, assets + "/tetrahedron.obj");
         } else if (name == "bob_textured") {
             world->addLight(new PointLightSource(world, Vector3D(0, 10, 0), Color(1, 1, 1)));  // light2, :361
-            load_image_from_obj(world, assets + "/bob_tri.obj", assets + "/bob_diffuse.png");
+            load_image_from_obj(world, assets + "/bob_tri.obj", assets + "/bob_diffuse.png", "", -1);
         } else if (name == "lumina_default") {
-            load_image_from_obj(world, assets + "/bob_tri.obj", "", "", 2000);                 // :366 with the :266 cap
+            load_image_from_obj(world, assets + "/bob_tri.obj");                               // :366; the :266 cap is the default
         } else {
             throw std::runtime_error("unknown demo scene " + name);
         }

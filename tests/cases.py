@@ -6,7 +6,7 @@ SMALL = (160, 120)
 
 GOLDEN_CASES = [
     "tetra_d10", "bob2000_d10", "analytic_close_d5", "analytic_notetra_d5", "analytic_stock_d1",
-    "bobtex_d3", "blubmixed_d5", "synth_small_d1", "bob_full_bboxfixed_d10",
+    "bobtex_d3", "blubmixed_d5", "synth_small_d1", "bob_full_bboxfixed_d10", "analytic_close_d0",
 ]
 
 
@@ -30,6 +30,8 @@ def build_case(name):
     if name == "synth_small_d1":
         return (scenes.synthetic_sphere_grid(grid=3, level=2), scenes.synthetic_camera(w, h, grid=3), 1,
                 ob.MODE_AS_SHIPPED)
+    if name == "analytic_close_d0":          # depth 0: the refracted child of the dielectric cylinder (level 0 * 2) is alive
+        return scenes.analytic_scene(), scenes.close_camera(320, 240), 0, ob.MODE_TRUE_NEAREST
     if name == "bob_full_bboxfixed_d10":
         return scenes.obj_scene("bob_tri.obj"), scenes.stock_camera(w, h), 10, ob.MODE_BBOX_FIXED
     raise KeyError(name)

@@ -82,5 +82,5 @@ def test_headless_lumina_binary(host, tmp_path):
     header = b"P6\n160 120\n255\n"            # 161x121 rounded down to even like lumina.cpp:484-485
     assert data.startswith(header)
     img = np.frombuffer(data[len(header):], np.uint8).reshape(120, 160, 3)[::-1]
-    ref = flat(scenes.obj_scene("bob_tri.obj"), scenes.stock_camera(160, 120), 10)[0]
+    ref = flat(scenes.obj_scene("bob_tri.obj", 2000), scenes.stock_camera(160, 120), 10)[0]     # the :266 cap is the default
     assert np.array_equal(img, ref)

@@ -89,3 +89,112 @@ def test_camera_rays_equal_the_oracle_camera(host, port_oracle):
         d = -w * float(focal) + u * float(xw) + v * float(yw)
         d = d / np.sqrt((d * d).sum())
         assert np.array_equal(out, d), (i, j)
+
+
+# ---- round 2: the loader's reference defaults, the literal texel mode, per-object intersect, input validation ------
+def _load2(host, obj, tex, max_faces, texel_mode, default_cap, cap=20000):
+    host.rt_host_load_obj2.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_char_p, C.c_int]
+    v = np.zeros((cap, 9), np.float32)
+    rgb = np.zeros((cap, 9), np.float32)
+    err = C.create_string_buffer(512)
+    obj_path = obj if os.path.isabs(obj) else os.path.join(ASSETS, obj)
+    tex_path = None if not tex else (tex if os.path.isabs(tex) else os.path.join(ASSETS, tex))
+    n = host.rt_host_load_obj2(obj_path.encode(), tex_path.encode() if tex_path else None, max_faces, texel_mode, default_cap,
+                               v.ctypes.data, rgb.ctypes.data, cap, err, 512)
+    return n, v[:max(n, 0)], rgb[:max(n, 0)], err.value.decode()
+
+
+def test_the_same_call_loads_the_same_scene_as_the_reference(host):
+    """load_image_from_obj(world, file) with no further arguments keeps the first 2000 faces (lumina.cpp:266)."""
+    from realtrace_b200 import objio
+    n, v, _, err = _load2(host, "bob_tri.obj", None, 0, 0, 1)
+    assert n == 2000, err
+    tri, _, _, _ = objio.triangles_from_obj(os.path.join(ASSETS, "bob_tri.obj"), 2000)
+    assert np.array_equal(v, tri)
+
+
+def test_literal_texel_mode_equals_the_python_restatement(host):
+    """RT_TEXEL_LITERAL: lumina.cpp:175-187 + the un-decremented vt index of :249, in C++ and in objio.py."""
+    from realtrace_b200 import objio
+    path = os.path.join(ASSETS, "bob_tri.obj")
+    _, _, tex, faces = objio.triangles_from_obj(path, None)
+    want = objio.vertex_colours(faces, tex, objio.load_texture(os.path.join(ASSETS, "bob_diffuse.png")), "literal")
+    n, _, rgb, err = _load2(host, "bob_tri.obj", "bob_diffuse.png", -1, 1, 0)
+    assert n == len(faces), err
+    assert np.array_equal(rgb, want)
+    assert rgb.max() > 1.5          # texels are NOT divided by 255 in this mode
+
+
+def test_loader_rejects_bad_files_instead_of_reading_out_of_bounds(host, tmp_path):
+    bad_index = tmp_path / "bad_index.obj"
+    bad_index.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 7\n")
+    n, _, _, err = _load2(host, str(bad_index), None, -1, 0, 0)
+    assert n == -1 and "vertex 7" in err
+    relative = tmp_path / "relative.obj"
+    relative.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf -3 -2 -1\n")
+    n, _, _, err = _load2(host, str(relative), None, -1, 0, 0)
+    assert n == -1 and "not supported" in err
+    ok_obj = tmp_path / "ok.obj"
+    ok_obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nf 1/1 2/2 3/9\n")
+    png = open(os.path.join(ASSETS, "bob_diffuse.png"), "rb").read()
+    n, _, _, err = _load2(host, str(ok_obj), os.path.join(ASSETS, "bob_diffuse.png"), -1, 0, 0)
+    assert n == -1 and "texture vertex 9" in err
+    # a PNG whose IHDR chunk is cut short, and one that claims a 2^31-pixel-wide image
+    short = tmp_path / "short.png"
+    short.write_bytes(png[:8] + (5).to_bytes(4, "big") + b"IHDR" + png[16:21] + png[29:33] + png[33:])
+    n, _, _, err = _load2(host, str(ok_obj), str(short), -1, 0, 0)
+    assert n == -1 and "cannot decode" in err
+    huge = bytearray(png)
+    huge[16:20] = (0x80000000).to_bytes(4, "big")
+    hp = tmp_path / "huge.png"
+    hp.write_bytes(bytes(huge))
+    n, _, _, err = _load2(host, str(ok_obj), str(hp), -1, 0, 0)
+    assert n == -1 and "cannot decode" in err
+
+
+def test_object_intersect_of_every_kind_follows_the_reference(host):
+    """Object::intersect (object.h:15) of Sphere / Plane / Cylinder / Triangle, one object at a time, against the
+    oracle's trace of a scene that holds just that object: the known-answer rays of tests/kat.py."""
+    import kat
+    from oracle import binding as ob
+    import __graft_entry__ as entry
+    entry.build_oracle()
+    orc = ob.best_available()
+    host.rt_host_object_intersect.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    scene = kat.kat_scene()
+    names, rays = kat.kat_rays()
+    geoms = [(0, np.asarray(scene.sph[0], np.float64)), (1, np.asarray(scene.pln[0], np.float64)),
+             (2, np.asarray(scene.cyl[0], np.float64)), (3, np.asarray(scene.tri_v[0], np.float64))]
+    from realtrace_b200.scene import Scene
+    checked = 0
+    for kind, g in geoms:
+        kw = dict(materials=scene.materials, lights=scene.lights, ambient=scene.ambient, background=scene.background)
+        if kind == 0:
+            one = Scene(sph=[tuple(g)], sph_material=[0], sph_object_id=[0], **kw)
+        elif kind == 1:
+            one = Scene(pln=[tuple(g)], pln_material=[0], pln_object_id=[0], **kw)
+        elif kind == 2:
+            one = Scene(cyl=[tuple(g)], cyl_material=[0], cyl_object_id=[0], **kw)
+        else:
+            one = Scene(tri_v=np.asarray([g], np.float32), tri_material=np.zeros(1, np.uint32), **kw)
+        prim, t = orc.trace_rays(one.normalise(), rays, ob.MODE_TRUE_NEAREST)
+        for r, p, tt in zip(rays, prim, t):
+            out = C.c_float()
+            ray = np.asarray(r, np.float64)
+            host.rt_host_object_intersect(kind, g.ctypes.data, ray.ctypes.data, C.byref(out))
+            if p >= 0:
+                assert out.value == tt, (kind, r, out.value, tt)
+                checked += 1
+            else:
+                assert out.value == np.finfo(np.float32).max, (kind, r, out.value)
+    assert checked >= 12
+
+
+def test_camera_builds_without_a_gpu_and_frames_are_page_locked_with_one(host):
+    """Camera owns its bitmap (camera.cpp:19): page-locked through rt_host_alloc where a CUDA device exists, plain
+    memory otherwise — either way the constructor works on a machine without a GPU."""
+    pos, tgt, up = (np.asarray(x, np.float64) for x in ((60, 60, 0), (0, 0, 0), (0, 1, 0)))
+    out = np.zeros(3, np.float64)
+    host.rt_host_camera_ray(pos.ctypes.data, tgt.ctypes.data, up.ctypes.data, 45.0, 64, 48, 3, 4, out.ctypes.data)
+    assert abs(np.linalg.norm(out) - 1.0) < 1e-12
