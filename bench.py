@@ -172,8 +172,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "width": cam.width, "height": cam.height,
-                       "max_depth": depth, "triangles": int(len(scene.tri_v))},
+            "config": base_config(args.workload, desc, cam, depth, scene),
+            "rays_per_frame": {"total": float(info["rays_total"]) * col_step, "note": "sample x column step (estimate)"},
+            "run": {"parallelism": f"{threads} host threads over columns", "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": orc.kind, "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -181,7 +182,38 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
+def base_config(workload, desc, cam, depth, scene):
+    """The workload as both arms (ours / --impl reference) describe it: identical keys AND values."""
+    return {"workload": workload, "description": desc, "width": cam.width, "height": cam.height, "max_depth": depth,
+            "triangles": int(len(scene.tri_v)), "lights": int(len(scene.lights))}
+
+
+def ncu_counts(workload):
+    """Per-launch counters of the dominant kernel from the committed ncu capture (profiles/ncu_counts.json, written by
+    profiles/summarize_ncu.py from `ncu --set full`): executed warp instructions, DRAM and L2 bytes."""
+    path = os.path.join(ROOT, "profiles", "ncu_counts.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(workload)
+
+
+def moving_cameras(workload, cam, n):
+    """n cameras on a circle around the workload's target, same height and distance: every timed frame sees the scene
+    from a new direction (so the heavy-tiles-first order of the previous frame is only a prediction)."""
+    import math
+    from realtrace_b200.scene import Camera
+    tx, ty, tz = cam.target
+    dx, dz = cam.pos[0] - tx, cam.pos[2] - tz
+    r, a0 = math.hypot(dx, dz), math.atan2(dx, dz)
+    out = []
+    for k in range(n):
+        a = a0 + math.radians(3.0) * (k + 1)
+        out.append(Camera(pos=(tx + r * math.sin(a), cam.pos[1], tz + r * math.cos(a)), target=cam.target, up=cam.up,
+                          fovy=cam.fovy, width=cam.width, height=cam.height))
+    return out
+
+
+def measure_gpu(args, workload, steps, warmup, dist_ctx, main_leg):
     import torch
     from realtrace_b200 import api, multigpu, scenes
 
@@ -190,6 +222,11 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     torch.cuda.set_device(dev)
     scene, cam, depth, desc = scenes.workload(workload)
     W, H = cam.width, cam.height
+
+    def host_barrier():
+        """All ranks line up WITHOUT device work (gloo): used around the legs in which rank 0 alone drives every GPU."""
+        if world > 1:
+            torch.distributed.barrier(group=dist_ctx["gloo"])
 
     ctx = api.Context(dist_ctx["local_rank"])
     stream = torch.cuda.current_stream()
@@ -200,6 +237,8 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     ctx.set_scene(scene)
     bstats = ctx.commit()
     commit_s = time.time() - t0
+    # a second, warm build: allocations and module loading are behind us
+    bstats_warm = ctx.commit()
 
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     # tile size of the interleaved ownership: the library default (64x32) up to 2 GPUs; from 4 GPUs on 32x16, whose
@@ -214,9 +253,9 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
     tick = torch.zeros(1, dtype=torch.int32, device=dev)
 
     # ---- N > 1: frame assembly.  Preferred: rank 0 owns the frame in a CUDA-IPC buffer that every
-    # rank maps over NVLink; each rank's resolve kernel stores its tiles straight into it and one tiny
-    # all-reduce is the completion barrier.  Fallback (--assemble gather, or IPC unavailable): packed
-    # tiles + NCCL gather + scatter kernel on rank 0.
+    # rank maps over NVLink; each rank stores its tiles straight into it and signals a flag in peer memory
+    # (no collective).  Fallback (--assemble gather, or IPC unavailable): packed tiles + NCCL gather + scatter
+    # kernel on rank 0.
     assemble = "single"
     packed = gathered = None
     cursor_ptr = sync_ptr = None
@@ -303,16 +342,10 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
                 st = ctx.render_device(cam, depth, frame_ptr, tile=tile, rank=rank, world=world, want_stats=want_stats,
                                        steal=(args.steal_div, k, cursor_ptr))
                 ctx.peer_sync(sync_ptr, rank, world, k, 1)   # completion handshake: after it, rank 0 holds the frame
-            elif want_stats:    # own tiles into a local packed buffer, then one kernel pushes them over NVLink
-                st = ctx.render_device(cam, depth, packed.data_ptr(), tile=tile, rank=rank, world=world,
-                                       flags=api.FLAG_PACKED_TILES, want_stats=True)
-                ctx.peer_sync(sync_ptr, rank, world, k, 0)
-                ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr, tile=tile)
-                ctx.peer_sync(sync_ptr, rank, world, k, 1)
-            else:               # the same four steps in one library call (one ctypes transition per frame)
-                st = None
-                ctx.render_push(cam, push_params, packed.data_ptr(), frame_ptr, sync_ptr, k)
-            return st
+                return st
+            # render + push into rank 0's frame + handshake: one library call, only enqueued
+            ctx.render_push(cam, push_params, packed.data_ptr(), frame_ptr, sync_ptr, k)
+            return None
         st = ctx.render_device(cam, depth, packed.data_ptr(), tile=tile, rank=rank, world=world, flags=api.FLAG_PACKED_TILES,
                                want_stats=want_stats)
         multigpu.gather_packed(packed, rank, world, gathered)
@@ -321,46 +354,97 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
                 ctx.assemble_tiles(gathered[r].data_ptr(), r, world, W, H, frame_ptr, tile=tile)
         return st
 
+    def share_stats(flags=0):
+        """Statistics of this rank's share of the frame (ray counts, per-kernel times): rendered into the local packed
+        buffer, nothing pushed."""
+        if world == 1:
+            return ctx.render_device(cam, depth, frame_ptr, flags=flags)
+        return ctx.render_device(cam, depth, packed.data_ptr(), tile=tile, rank=rank, world=world,
+                                 flags=api.FLAG_PACKED_TILES | flags)
+
     # ---- value: device-resident frames, CUDA events around every step, L2 flushed between steps.
-    # Warm-up frames carry statistics (ray counts, per-kernel times); timed frames are enqueued
-    # asynchronously and only the final barrier synchronises.
+    # Warm-up frames run through the timed path; statistics come from separate share renders.
     sampler = ClockSampler(dist_ctx["local_rank"])
     sampler.start()
-    stats = [step_device(True) for _ in range(max(warmup, 3) + 2)]   # statistics frames; the first (cold) one is dropped from the per-kernel medians
-    barrier()
-    sampler.t_begin = time.perf_counter()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    t_host0 = time.perf_counter()
-    launches0 = ctx.frame_launches()
-    for k in range(steps):
-        flush.fill_(k & 0xff)
-        if world > 1:
-            # untimed alignment: without it the L2 flush of a lagging rank (outside its own event pair) would be
-            # counted inside the event pair of every rank that waits for it
-            align_ranks()
-        evs[k][0].record(stream)
+    stats = [share_stats() for _ in range(3)]
+    for _ in range(max(warmup, 3) + 2):
         step_device(False)
-        evs[k][1].record(stream)
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps
     barrier()
-    ctx.synchronize()                                   # raises if any timed frame flagged an error
+    ctx.synchronize()
+
+    def timed_loop(n_steps, cams=None):
+        nonlocal cam
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        t_host0 = time.perf_counter()
+        launches0 = ctx.frame_launches()
+        for k in range(n_steps):
+            flush.fill_(k & 0xff)
+            if cams is not None:
+                cam = cams[k]
+            if world > 1:
+                # untimed alignment: without it the L2 flush of a lagging rank (outside its own event pair) would be
+                # counted inside the event pair of every rank that waits for it
+                align_ranks()
+            evs[k][0].record(stream)
+            step_device(False)
+            evs[k][1].record(stream)
+        host_ms = (time.perf_counter() - t_host0) * 1e3 / n_steps
+        barrier()
+        ctx.synchronize()                                   # raises if any timed frame flagged an error
+        per = np.array([a.elapsed_time(b) for a, b in evs])
+        return per, host_ms, ctx.frame_launches() - launches0
+
+    sampler.t_begin = time.perf_counter()
+    per_step, host_enqueue_ms, launches = timed_loop(steps)
     sampler.t_end = time.perf_counter()
-    per_step = np.array([a.elapsed_time(b) for a, b in evs])
     ms = float(per_step.sum())
-    launches = ctx.frame_launches() - launches0          # kernels the library enqueued between the event pairs (NCCL's gather kernels not included)
     rays_local = total_rays(stats[-1]) * steps          # static scene + camera: every frame casts the same rays
     if orbit:                                           # moving camera: count the rays of the timed frames exactly
         orbit_k[0] -= steps
-        rays_local = sum(total_rays(step_device(True)) for _ in range(steps))
+        rays_local = 0
+        for _ in range(steps):
+            ctx.commit(api.COMMIT_REFIT, want_stats=False)
+            cam = orbit_cams[orbit_k[0] % 120]
+            orbit_k[0] += 1
+            rays_local += total_rays(share_stats())
+    ray_classes = np.array([stats[-1]["rays_primary"], stats[-1]["rays_shadow"], stats[-1]["rays_secondary"]], np.float64)
     if world > 1:
         t = torch.tensor([ms, float(rays_local), float(launches)], dtype=torch.float64, device=dev)
         tmax = t.clone()
         torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
         ms, rays_total, launches = float(tmax[0]), float(t[1]), int(t[2])
+        rc = torch.tensor(ray_classes, dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(rc, op=torch.distributed.ReduceOp.SUM)
+        ray_classes = rc.cpu().numpy()
     else:
         rays_total = float(rays_local)
     value = rays_total / (ms * 1e-3) / 1e6
+
+    # ---- the same with a moving camera (main leg, static workloads): no frame repeats the previous one
+    moving = None
+    if main_leg and not orbit:
+        mcams_py = moving_cameras(workload, cam_py, steps)
+        mcams = [api.camera_struct(c) for c in mcams_py]
+        keep = cam
+        m_rays = 0.0
+        for c in mcams:
+            cam = c
+            m_rays += total_rays(share_stats())
+        cam = keep
+        barrier()
+        m_per, _, _ = timed_loop(steps, mcams)
+        cam = keep
+        m_ms = float(m_per.sum())
+        if world > 1:
+            t = torch.tensor([m_ms, m_rays], dtype=torch.float64, device=dev)
+            tmax = t.clone()
+            torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+            m_ms, m_rays = float(tmax[0]), float(t[1])
+        moving = {"value": m_rays / (m_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": m_ms / steps,
+                  "what": "the camera moves 3 degrees around the scene before every timed frame (no frame repeats, "
+                          "the heavy-tiles-first order comes from a different view)"}
 
     # ---- N > 1: is the frame the ranks assembled in rank 0's memory the frame one GPU renders?  One more frame
     # through the timed path (untimed), then rank 0 renders the whole frame by itself and compares byte for byte.
@@ -370,6 +454,7 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
         barrier()
         step_device(False)
         barrier()
+        ctx.synchronize()
         if rank == 0:
             try:
                 got = np.empty((H, W, 3), np.uint8)
@@ -385,93 +470,166 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, with_cpu):
                 frame_check = {"error": repr(e)}
         barrier()
 
-    # ---- N > 1 diagnostics (RT_BENCH_PHASES=1): where does a frame's time go on each rank?  Same asynchronous
-    # frame loop as the timed one, with extra events between the phases (p2p path without stealing).
-    if world > 1 and assemble == "p2p" and not cursor_ptr and os.environ.get("RT_BENCH_PHASES"):
-        nfr = 20
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nfr)]
-        for f_ in range(nfr):
-            k = frame_no[0]
-            frame_no[0] += 1
-            flush.fill_(f_ & 0xff)
-            align_ranks()
-            ev[f_][0].record(stream)
-            ctx.render_device(cam, depth, packed.data_ptr(), tile=tile, rank=rank, world=world, flags=api.FLAG_PACKED_TILES, want_stats=False)
-            ev[f_][1].record(stream)
-            ctx.peer_sync(sync_ptr, rank, world, k, 0)
-            ctx.assemble_tiles(packed.data_ptr(), rank, world, W, H, frame_ptr, tile=tile)
-            ev[f_][2].record(stream)
-            ctx.peer_sync(sync_ptr, rank, world, k, 1)
-            ev[f_][3].record(stream)
-        barrier()
-        acc = np.array([[e[a].elapsed_time(e[a + 1]) for a in range(3)] for e in ev]).mean(axis=0)
-        print(f"[phases rank {rank}] render {acc[0]:.3f} ms, wait+push {acc[1]:.3f} ms, handshake {acc[2]:.3f} ms", file=sys.stderr, flush=True)
+    # ---- work counts + per-kernel times of this rank's share (roofline inputs)
+    cnt = share_stats(api.FLAG_COUNT_WORK)
+    share = [share_stats() for _ in range(5)]
+    kernel_ms = {"primary wave: trace + fused shadow rays (+ shading when the frame is one k_frame launch)":
+                 float(np.median([s_["ms_trace"] for s_ in share])),
+                 "k_traverse<shadow> (any hit)": float(np.median([s_["ms_shadow"] for s_ in share])),
+                 "k_shade<primary>": float(np.median([s_["ms_shade"] for s_ in share])),
+                 "k_paths (all bounce generations)": float(np.median([s_["ms_secondary"] for s_ in share])),
+                 "k_resolve": float(np.median([s_["ms_resolve"] for s_ in share]))}
+    n_rays_share = total_rays(cnt)
+    work = {"rays": n_rays_share, "node_visits": cnt["node_visits"] + cnt["shadow_node_visits"],
+            "tri_tests": cnt["tri_tests"] + cnt["shadow_tri_tests"],
+            "nearest": {"rays": cnt["rays_primary"] + cnt["rays_secondary"], "node_visits": cnt["node_visits"], "tri_tests": cnt["tri_tests"]},
+            "shadow": {"rays": cnt["rays_shadow"], "node_visits": cnt["shadow_node_visits"], "tri_tests": cnt["shadow_tri_tests"]},
+            "share_ms_device": float(np.median([s_["ms_device"] for s_ in share]))}
 
-    # ---- e2e: host buffers through rt_render (N = 1) / render + gather + D2H of the frame (N > 1)
-    host_frame = torch.empty(H * W * 3, dtype=torch.uint8, pin_memory=True)
-    host_np = host_frame.numpy().reshape(H, W, 3)
+    micro = None
+    if main_leg:
+        micro = ctx.microbench()
 
-    def step_e2e():
-        if world == 1:
-            return ctx.render(cam, depth, out=host_np)[3]
-        st = step_device(True)
-        if rank == 0:
-            ctx.download(frame_ptr, host_np)            # waits for the barrier all-reduce, then D2H
-        return st
-
-    for _ in range(max(1, warmup // 2)):
-        step_e2e()
-    barrier()
-    e2e_steps = max(3, steps // 2)
-    t0 = time.perf_counter()
-    e_rays = 0
-    for _ in range(e2e_steps):
-        e_rays += total_rays(step_e2e())
-    barrier()
-    e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e_s, float(e_rays)], dtype=torch.float64, device=dev)
-        tmax = t.clone()
-        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
-        e_s, e_rays = float(tmax[0]), float(t[1])
-    e2e_value = e_rays / e_s / 1e6
-
-    sampler.stop()
     out = {"value": value, "ms_per_step": ms / steps,
-           "ms_per_step_p50": float(np.percentile(per_step, 50)), "ms_per_step_p99": float(np.percentile(per_step, 99)), "e2e_value": e2e_value, "e2e_ms_per_step": e_s / e2e_steps * 1e3,
-           "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": sampler.summary(), "desc": desc, "assemble": assemble, "tile": (tile[0] or 64, tile[1] or 32), "frame_check": frame_check, "cam": cam_py, "depth": depth,
-           "scene": scene, "build": bstats, "commit_s": commit_s, "last": stats[-1], "rays_per_frame": rays_total / steps}
+           "ms_per_step_p50": float(np.percentile(per_step, 50)), "ms_per_step_p99": float(np.percentile(per_step, 99)),
+           "launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "desc": desc, "assemble": assemble,
+           "tile": (tile[0] or 64, tile[1] or 32), "frame_check": frame_check, "cam": cam_py, "depth": depth,
+           "scene": scene, "build": bstats, "build_warm": bstats_warm, "commit_s": commit_s, "rays_per_frame": rays_total / steps,
+           "ray_classes": [float(x) for x in ray_classes], "kernel_ms": kernel_ms, "work": work, "micro": micro, "moving": moving}
 
-    # ---- roofline of the dominant kernel + work counts (single GPU, rank 0)
-    if world == 1:
-        cnt = ctx.render_device(cam, depth, frame_ptr, flags=api.FLAG_COUNT_WORK)
-        n_rays = total_rays(cnt)
-        n_near = cnt["rays_primary"] + cnt["rays_secondary"]
-        ms_k = {"k_traverse<primary> (nearest hit + fused shadow rays)": float(np.median([s["ms_trace"] for s in stats[1:]])),
-                "k_traverse<shadow> (any hit)": float(np.median([s["ms_shadow"] for s in stats[1:]])),
-                "k_shade<primary>": float(np.median([s["ms_shade"] for s in stats[1:]])),
-                "k_paths (all bounce generations)": float(np.median([s["ms_secondary"] for s in stats[1:]])),
-                "k_resolve": float(np.median([s["ms_resolve"] for s in stats[1:]]))}
-        out["kernel_ms"] = {k: float(v) for k, v in ms_k.items()}
-        nodes_all = cnt["node_visits"] + cnt["shadow_node_visits"]
-        tris_all = cnt["tri_tests"] + cnt["shadow_tri_tests"]
-        out["work"] = {"node_visits_per_ray": nodes_all / n_rays, "tri_tests_per_ray": tris_all / n_rays,
-                       "node_visits": nodes_all, "tri_tests": tris_all, "rays": n_rays,
-                       "nearest": {"rays": n_near, "node_visits_per_ray": cnt["node_visits"] / max(n_near, 1),
-                                   "tri_tests_per_ray": cnt["tri_tests"] / max(n_near, 1)},
-                       "shadow": {"rays": cnt["rays_shadow"],
-                                  "node_visits_per_ray": cnt["shadow_node_visits"] / max(cnt["rays_shadow"], 1),
-                                  "tri_tests_per_ray": cnt["shadow_tri_tests"] / max(cnt["rays_shadow"], 1)}}
-        # cold e2e: scene upload + LBVH build + one frame to the host
+    # ---- e2e: the public host-buffer API.  Frames go through rt_render_enqueue / rt_render_wait into two page-locked
+    # host buffers (camera in, RGB8 frame out, two frames in flight: the copy of frame k overlaps the rendering of
+    # frame k+1); `latency` is one synchronous rt_render.  At N > 1 rank 0 drives ALL N GPUs through ONE multi-device
+    # context (rt_create_multi — what RenderEngine::render() does); the other ranks wait on the host meanwhile.
+    barrier()
+    ctx.synchronize()
+    e2e = None
+    host_barrier()
+    if rank == 0:
+        ectx = ctx
+        if world > 1:
+            ectx = api.Context(devices=list(range(world)))
+            ectx.set_scene(scene)
+            ectx.commit()
+        bufs = [api.host_alloc(H * W * 3), api.host_alloc(H * W * 3)]
+        ecams = [cam] if not orbit else orbit_cams
+
+        def e2e_frame(k, slot):
+            if orbit:
+                ectx.commit(api.COMMIT_REFIT, want_stats=False)
+            ectx.render_enqueue(ecams[k % len(ecams)], depth, bufs[slot], slot)
+
+        for _ in range(max(2, warmup)):                 # warm: frames, allocations, pinned registrations
+            st_e = ectx.render(ecams[0], depth, out=bufs[0].reshape(H, W, 3))[3]
+        e_rays_frame = total_rays(st_e)
+        lat = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            ectx.render(ecams[0], depth, out=bufs[0].reshape(H, W, 3))
+            lat.append((time.perf_counter() - t0) * 1e3)
+        e2e_steps = max(steps, 10)
+        e2e_frame(0, 0)
+        ectx.render_wait(0)
         t0 = time.perf_counter()
-        ctx.set_scene(scene)
-        ctx.commit()
-        st = ctx.render(cam, depth, out=host_np)[3]
-        out["e2e_cold_ms"] = (time.perf_counter() - t0) * 1e3
+        e2e_frame(0, 0)
+        for k in range(1, e2e_steps + 1):
+            if k < e2e_steps:
+                e2e_frame(k, k % 2)
+            ectx.render_wait((k - 1) % 2)
+        e_s = time.perf_counter() - t0
+        e_rays = e_rays_frame * e2e_steps
+        if orbit:
+            e_rays = rays_total / steps * e2e_steps      # (per-frame counts differ slightly along the orbit)
+        same = None
+        if world > 1 and frame_check is not None and "error" not in frame_check:
+            one = np.empty((H, W, 3), np.uint8)
+            ctx.render(cam, depth, out=one)
+            ectx.render(ecams[0], depth, out=bufs[1].reshape(H, W, 3))
+            same = bool(np.array_equal(one, bufs[1].reshape(H, W, 3)))
+        e2e = {"value": e_rays / e_s / 1e6, "ms_per_step": e_s / e2e_steps * 1e3, "latency_ms": float(np.median(lat)),
+               "steps": e2e_steps, "devices": ectx.device_count(), "equal_to_the_1_gpu_frame": same}
+        if world == 1 and main_leg:
+            # cold e2e: scene upload + LBVH build + one frame to the host
+            t0 = time.perf_counter()
+            ctx.set_scene(scene)
+            ctx.commit()
+            ctx.render(cam, depth, out=bufs[0].reshape(H, W, 3))
+            e2e["cold_ms_incl_scene_upload_and_bvh_build"] = (time.perf_counter() - t0) * 1e3
+        if ectx is not ctx:
+            ectx.close()
+        for b in bufs:
+            api.host_free(b)
+    host_barrier()
+    out["e2e"] = e2e
+    sampler.stop()
+    out["clocks"] = sampler.summary()
+    out["ms_refit"] = ctx.build_stats().get("ms_refit")
     ctx.close()
     del flush
     return out
+
+
+def roofline_of(main, workload, hbm_gbs, peak_src, sm_max_mhz):
+    """max(T_issue, T_fma, T_l2, T_hbm) / T_kernel for this rank's share."""
+    work, kms, micro = main["work"], main["kernel_ms"], main["micro"]
+    dom = max(kms, key=kms.get)
+    t_kernel = kms[dom] * 1e-3
+    n_rays = work["rays"]
+    nodes_per_ray = work["node_visits"] / max(n_rays, 1)
+    tris_per_ray = work["tri_tests"] / max(n_rays, 1)
+    frame_ms = work["share_ms_device"]
+    # SURVEY 8(d): algorithmic work of ALL rays of the share against the time of ALL its traversal kernels
+    t_all = sum(kms.values()) * 1e-3
+    bytes_per_ray = 64.0 * nodes_per_ray + 48.0 * tris_per_ray + 84.0
+    fma_per_ray = 12.0 * nodes_per_ray + 30.0 * tris_per_ray + 60.0
+    alg_bytes, alg_fma = bytes_per_ray * n_rays, fma_per_ray * n_rays
+    fma_peak = micro["fma_lane_instr_per_s"] if micro else FMA_LANES_PER_CLK * sm_max_mhz * 1e6
+    issue_peak = micro["issue_warp_instr_per_s"] if micro else fma_peak / 32.0
+    l2_peak = micro["l2_read_gbs"] * 1e9 if micro else None
+    terms = {"T_kernels_ms": t_all * 1e3, "T_fma_ms": alg_fma / fma_peak * 1e3}
+    nc = ncu_counts(workload)
+    traffic = None
+    if nc and nc.get("rays"):
+        # the capture is of a whole 1-GPU frame: a rank's share executes its part of it
+        k = n_rays / float(nc["rays"])
+        nc = {**nc, **{key: nc[key] * k for key in ("inst_executed", "lts_bytes", "dram_bytes") if nc.get(key)}, "scaled_by": k}
+    if nc:
+        traffic = nc.get("dram_bytes")
+        if nc.get("inst_executed"):
+            terms["T_issue_ms"] = nc["inst_executed"] / issue_peak * 1e3
+        if nc.get("lts_bytes") and l2_peak:
+            terms["T_l2_ms"] = nc["lts_bytes"] / l2_peak * 1e3
+        if traffic:
+            terms["T_hbm_ms"] = traffic / (hbm_gbs * 1e9) * 1e3
+    cand = {k: v for k, v in terms.items() if k != "T_kernels_ms"}
+    bound_key = max(cand, key=cand.get)
+    bound = {"T_issue_ms": "issue", "T_fma_ms": "fma", "T_l2_ms": "l2", "T_hbm_ms": "hbm"}[bound_key]
+    frac = cand[bound_key] / terms["T_kernels_ms"]
+    if bound == "issue":
+        achieved, peak, unit = nc["inst_executed"] / t_all / 1e9, issue_peak / 1e9, "Gwarp-instr/s"
+    elif bound == "fma":
+        achieved, peak, unit = alg_fma / t_all / 1e12, fma_peak / 1e12, "T lane-instr/s"
+    elif bound == "l2":
+        achieved, peak, unit = nc["lts_bytes"] / t_all / 1e9, l2_peak / 1e9, "GB/s"
+    else:
+        achieved, peak, unit = traffic / t_all / 1e9, hbm_gbs, "GB/s"
+    return {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": frac, "traffic": traffic,
+            "peak_source": ("rt_microbench on this GPU in this run" if micro else "nominal") + "; HBM: " + peak_src,
+            "terms": terms, "dominant_kernel": dom, "kernel_ms": kms, "share_ms_device": frame_ms,
+            "algorithmic": {"rays": n_rays, "node_visits_per_ray": nodes_per_ray, "tri_tests_per_ray": tris_per_ray,
+                            "bytes_per_ray": bytes_per_ray, "fma_lane_instr_per_ray": fma_per_ray,
+                            "fma_frac_of_measured_peak": alg_fma / t_all / fma_peak,
+                            "hbm_yardstick": {"achieved_gbs": alg_bytes / t_all / 1e9, "peak_gbs": hbm_gbs,
+                                              "frac": alg_bytes / t_all / 1e9 / hbm_gbs,
+                                              "note": "SURVEY 8(d)'s algorithmic bytes over the HBM copy peak: NOT a physical "
+                                                      "fraction here — neighbouring rays share nodes through L1/L2, DRAM moves "
+                                                      "only `traffic` bytes per launch"}},
+            "measured_peaks": micro,
+            "ncu": nc,
+            "note": "frac = max(T_issue, T_fma, T_l2, T_hbm) / T_kernels over this rank's share of the frame: T_issue = warp "
+                    "instructions executed (ncu capture in profiles/) / measured issue rate, T_fma = SURVEY 8(d)'s algorithmic "
+                    "FMA lane-instructions / measured FMA rate, T_l2 and T_hbm = bytes the capture saw at L2 / DRAM over the "
+                    "measured bandwidths.  Traversal is bound by instruction issue and dependent-fetch latency, not by HBM."}
 
 
 def run_gpu_arm(args):
@@ -481,104 +639,83 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    gloo = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dist_ctx = {"rank": rank, "world": world, "local_rank": local_rank}
+        gloo = torch.distributed.new_group(backend="gloo")
+    dist_ctx = {"rank": rank, "world": world, "local_rank": local_rank, "gloo": gloo}
     hbm_gbs, peak_src, sm_max_mhz = peaks()
 
     main = measure_gpu(args, args.workload, args.steps, args.warmup, dist_ctx, True)
     cam, scene, depth = main["cam"], main["scene"], main["depth"]
+    rp, rs, rsec = main["ray_classes"]
 
     line = {"metric": METRIC, "value": main["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "ms_per_step_p50": main["ms_per_step_p50"],
             "ms_per_step_p99": main["ms_per_step_p99"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": main["desc"], "width": cam.width, "height": cam.height,
-                       "max_depth": depth, "triangles": int(len(scene.tri_v)), "lights": int(len(scene.lights)),
-                       "rays_per_frame": main["rays_per_frame"],
-                       "parallelism": (f"{world} GPUs, interleaved {main['tile'][0]}x{main['tile'][1]} tiles, scene replicated, frame assembly: "
-                                       + {"p2p": "every rank writes its pixels into rank 0's frame over NVLink (CUDA IPC peer stores: from "
-                                                 "inside the one trace+shade kernel on bounce-free scenes, else a push kernel per rank) + "
-                                                 "flag handshake in peer memory (no collective)"
-                                                 + (f", dynamic tile stealing (1/{args.steal_div} of the tile groups pooled)" if args.steal_div > 0 else ""),
-                                          "gather": "packed tiles + NCCL gather + scatter kernel"}[main["assemble"]])
-                       if world > 1 else "1 GPU",
-                       "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"},
-            "e2e": {"value": main["e2e_value"], "unit": "Mrays/s", "ms_per_step": main["e2e_ms_per_step"],
-                    "h2d_bytes_per_step": 64 + 24, "d2h_bytes_per_step": cam.width * cam.height * 3,
-                    "what": ("rt_render: camera + params in, RGB8 frame into pinned host memory (scene resident)" if world == 1 else
-                             "per frame and rank: render its tiles + push into rank 0's frame + handshake, synchronised; "
-                             "rank 0 then copies the assembled RGB8 frame into pinned host memory (wall clock, max over ranks)")},
+            "config": base_config(args.workload, main["desc"], cam, depth, scene),
+            "rays_per_frame": {"total": main["rays_per_frame"], "R_primary": rp, "R_shadow": rs, "R_secondary": rsec},
+            "run": {"parallelism": (f"{world} GPUs, interleaved {main['tile'][0]}x{main['tile'][1]} tiles, scene replicated, frame assembly: "
+                                    + {"p2p": "every rank copies its tiles into rank 0's frame over NVLink (CUDA IPC peer stores) from inside "
+                                              "its one frame kernel on bounce-free scenes (else a push kernel per rank) and signals a flag in "
+                                              "peer memory; no collective"
+                                              + (f", dynamic tile stealing (1/{args.steal_div} of the tile groups pooled)" if args.steal_div > 0 else ""),
+                                       "gather": "packed tiles + NCCL gather + scatter kernel"}[main["assemble"]])
+                    if world > 1 else "1 GPU",
+                    "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"},
             "gpu_launches": main["launches"], "clocks": main["clocks"],
             **({"frame_check": main["frame_check"]} if main.get("frame_check") is not None else {}),
             "host_enqueue_ms_per_step": main["host_enqueue_ms_per_step"],
-            "build": {"commit_s": main["commit_s"], **main["build"]}}
+            "build": {"commit_s": main["commit_s"], **main["build"], "ms_build_warm": main["build_warm"]["ms_build"]}}
+    if main["moving"]:
+        line["moving_camera"] = main["moving"]
+    if rank == 0:
+        e = main["e2e"]
+        line["e2e"] = {"value": e["value"], "unit": "Mrays/s", "ms_per_step": e["ms_per_step"], "latency_ms": e["latency_ms"],
+                       "h2d_bytes_per_step": 64 + 40, "d2h_bytes_per_step": cam.width * cam.height * 3,
+                       "devices": e["devices"],
+                       **({"cold_ms_incl_scene_upload_and_bvh_build": e["cold_ms_incl_scene_upload_and_bvh_build"]}
+                          if "cold_ms_incl_scene_upload_and_bvh_build" in e else {}),
+                       **({"equal_to_the_1_gpu_frame": e["equal_to_the_1_gpu_frame"]} if e.get("equal_to_the_1_gpu_frame") is not None else {}),
+                       "what": "rt_render_enqueue / rt_render_wait: camera + params in, RGB8 frame into page-locked host memory, two "
+                               "frames in flight (the copy of frame k overlaps the rendering of frame k+1); latency_ms = one "
+                               "synchronous rt_render"
+                               + ("" if world == 1 else f"; ONE multi-device context (rt_create_multi) on rank 0 drives all {world} GPUs: "
+                                  "frame striped over the GPUs' memories, every GPU copies its granules over its own PCIe link")}
+        line["roofline"] = roofline_of(main, args.workload, hbm_gbs, peak_src, sm_max_mhz)
 
-    if world == 1:
-        work = main["work"]
-        kms = main["kernel_ms"]
-        dom = max(kms, key=kms.get)
-        # algorithmic bytes / FMA lane-instructions per ray: SURVEY §8(d), applied to the rays the dominant
-        # kernel traces (nearest-hit rays for k_traverse<primary>, any-hit rays for k_traverse<shadow>)
-        fused = kms.get("k_traverse<shadow> (any hit)", 0.0) < 0.01     # shadow rays ride in the primary kernel
-        if "k_traverse<primary>" in dom and fused:
-            cls = {"rays": work["nearest"]["rays"] + work["shadow"]["rays"] - main["last"]["rays_secondary"],
-                   "node_visits_per_ray": None, "tri_tests_per_ray": None}
-            # wave-0 rays only: primary + their shadow rays (bounce rays are traced by k_paths)
-            if main["last"]["rays_secondary"] == 0:
-                cls = {"rays": work["rays"], "node_visits_per_ray": work["node_visits_per_ray"],
-                       "tri_tests_per_ray": work["tri_tests_per_ray"]}
-            else:
-                cls = work["nearest"]          # approximation for bounce scenes: per-ray work of nearest-hit rays
-        else:
-            cls = work["shadow"] if "k_traverse<shadow>" in dom else work["nearest"]
-        bytes_per_ray = 64.0 * cls["node_visits_per_ray"] + 48.0 * cls["tri_tests_per_ray"] + 84.0
-        fma_per_ray = 12.0 * cls["node_visits_per_ray"] + 30.0 * cls["tri_tests_per_ray"] + 60.0
-        dom_ms = kms[dom]
-        achieved = bytes_per_ray * cls["rays"] / (dom_ms * 1e-3) / 1e9
-        sm_mhz = main["clocks"].get("sm_mhz") or sm_max_mhz
-        fma_peak = FMA_LANES_PER_CLK * sm_max_mhz * 1e6
-        fma_ach = fma_per_ray * cls["rays"] / (dom_ms * 1e-3)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic = tj.get(args.workload, {}).get("k_traverse<shadow>" if "k_traverse<shadow>" in dom else "k_traverse<primary>")
-        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                            "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
-                            "kernel": dom, "kernel_ms": kms, "rays_in_kernel": cls["rays"],
-                            "algorithmic_bytes_per_ray": bytes_per_ray,
-                            "node_visits_per_ray": cls["node_visits_per_ray"],
-                            "tri_tests_per_ray": cls["tri_tests_per_ray"],
-                            "fma": {"achieved_lane_instr_per_s": fma_ach, "peak_lane_instr_per_s": fma_peak,
-                                    "frac": fma_ach / fma_peak, "lane_instr_per_ray": fma_per_ray,
-                                    "sm_mhz_under_load": sm_mhz},
-                            "frame_totals": {"node_visits_per_ray": work["node_visits_per_ray"],
-                                             "tri_tests_per_ray": work["tri_tests_per_ray"], "rays": work["rays"]},
-                            "note": "algorithmic bytes are SURVEY 8(d)'s 64 B per node visit + 48 B per triangle test + 84 B "
-                                    "per ray; neighbouring rays share nodes through L1/L2 (ncu: L1 hit ~80 %, DRAM < 3 % "
-                                    "busy), so achieved can exceed the HBM copy peak — `traffic` is what DRAM really moved "
-                                    "per launch; the binding limit is instruction issue, see fma.frac and DESIGN.md 6"}
-        line["e2e"]["cold_ms_incl_scene_upload_and_bvh_build"] = main["e2e_cold_ms"]
+    if world == 1 and not args.no_cpu:
         # the reference's CPU renderer on a bounded sample of the same workload, 1 core
-        if not args.no_cpu:
-            orc, col_step, build_s = cpu_render_sample(scene, cam, depth, 12.0, 1)
-            info = cpu_step(orc, scene, cam, depth, col_step, 1)
-            line["cpu_baseline"] = {"value": info["rays_total"] / info["render_seconds"] / 1e6, "unit": "Mrays/s",
-                                    "cores": 1, "kind": orc.kind,
-                                    "sample": f"every {col_step}th column of the {cam.width}x{cam.height} frame "
-                                              f"({info['columns_rendered']} columns, {info['rays_total']} rays, "
-                                              f"{info['render_seconds']:.1f}s), grid as shipped; build {build_s:.2f}s excluded"}
-        if not args.no_others and args.workload == "synth1m":
-            other = measure_gpu(args, "bob1080", max(5, args.steps), args.warmup, dist_ctx, False)
-            line["other_workloads"] = {"bob1080": {"value": other["value"], "unit": "Mrays/s",
-                                                   "ms_per_step": other["ms_per_step"], "e2e_value": other["e2e_value"],
-                                                   "e2e_ms_per_step": other["e2e_ms_per_step"],
-                                                   "rays_per_frame": other["rays_per_frame"],
-                                                   "description": other["desc"], "kernel_ms": other["kernel_ms"],
-                                                   "work": other["work"]}}
+        orc, col_step, build_s = cpu_render_sample(scene, cam, depth, 12.0, 1)
+        info = cpu_step(orc, scene, cam, depth, col_step, 1)
+        line["cpu_baseline"] = {"value": info["rays_total"] / info["render_seconds"] / 1e6, "unit": "Mrays/s",
+                                "cores": 1, "kind": orc.kind,
+                                "sample": f"every {col_step}th column of the {cam.width}x{cam.height} frame "
+                                          f"({info['columns_rendered']} columns, {info['rays_total']} rays, "
+                                          f"{info['render_seconds']:.1f}s), grid as shipped; build {build_s:.2f}s excluded"}
+    if not args.no_others and args.workload == "synth1m":
+        others = {}
+        for name in ("bob1080", "blub4k", "orbit"):
+            o = measure_gpu(args, name, max(5, min(args.steps, 10)), args.warmup, dist_ctx, False)
+            ent = {"value": o["value"], "unit": "Mrays/s", "ms_per_step": o["ms_per_step"], "rays_per_frame": o["rays_per_frame"],
+                   "description": o["desc"], "kernel_ms": o["kernel_ms"], "frame_check": o["frame_check"]}
+            if rank == 0:
+                ent["e2e_value"] = o["e2e"]["value"]
+                ent["e2e_ms_per_step"] = o["e2e"]["ms_per_step"]
+            if name == "orbit":
+                ent["ms_refit"] = o["ms_refit"]
+            if world == 1 and not args.no_cpu and name == "bob1080":
+                sc, cm, dp = o["scene"], o["cam"], o["depth"]
+                orc, col_step, build_s = cpu_render_sample(sc, cm, dp, 6.0, 1)
+                info = cpu_step(orc, sc, cm, dp, col_step, 1)
+                ent["cpu_baseline"] = {"value": info["rays_total"] / info["render_seconds"] / 1e6, "unit": "Mrays/s", "cores": 1,
+                                       "kind": orc.kind, "sample": f"every {col_step}th column ({info['rays_total']} rays, "
+                                                                    f"{info['render_seconds']:.1f}s), grid as shipped"}
+            others[name] = ent
+        line["other_workloads"] = others
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

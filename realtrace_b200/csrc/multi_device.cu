@@ -242,7 +242,7 @@ void rt_multi_collect(rt_ctx* c, rt_frame_stats* stats) {
     for (rt_ctx* x : ranks) {
         try {
             RT_CUDA(cudaSetDevice(x->device));
-            RT_CUDA(cudaMemcpyAsync(x->h_frame, x->d_frame.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, x->stream));
+            RT_CUDA(cudaMemcpyAsync(x->h_frame, x->last_frame_ctr ? x->last_frame_ctr : x->d_frame.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, x->stream));
             rt_sync_and_check(x);
             if (stats) {
                 stats->rays_primary += x->h_frame->rays_primary;

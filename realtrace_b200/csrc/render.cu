@@ -712,18 +712,22 @@ __global__ void __launch_bounds__(SHADE_TPB, RT_SHADE_MIN_BLOCKS) k_shade(const 
 // launches whose gaps and tails are a third of an 8-GPU frame.  Here the persistent warps run all of it:
 //   phase 1  traverse_body<PRIMARY, FUSE>: nearest hits + their shadow rays; misses write their pixel, hits go to
 //            the compacted hit queue (same code as k_traverse)
-//   barrier  a warp that finds the ray cursor empty adds the work items it claimed to done[0] and waits until the
-//            sum is the whole share — a barrier on WORK, not on CTAs, so it cannot deadlock on CTAs that are not
-//            resident yet (they find nothing to claim and pass straight through)
-//   phase 2  the hit queue is shaded with full warps (k_shade's code), pixels written as RGB8
-//   barrier  the same on done[1] == number of hits
+//   barrier  over the CTAs of the grid (one atomic + one poller per CTA on a cumulative counter); the launch is
+//            cooperative, so all CTAs are resident and the barrier cannot deadlock
+//   phase 2  the hit queue is shaded with full warps (k_shade's code), rounds of 32 hits dealt out statically, pixels
+//            written as RGB8
+//   barrier  (frame elsewhere) the same
 //   phase 3  (frame elsewhere) this rank's packed tiles -> the shared frame with 16-byte stores over NVLink, after
 //            rank 0's "previous frame consumed" flag
 //   exit     the last CTA to finish (done[2]) signals rank 0's arrival slot with a system-scope atomic; on rank 0 it
 //            waits for the other ranks' arrivals instead, so the completion of rank 0's kernel IS the completion of
 //            the frame.  No handshake kernels, no collective.
 struct FrameSyncDev {
-    uint32_t* done;                 // [0] work items traced, [1] hits shaded, [2] CTAs finished; zero between frames
+    uint32_t* done;                 // CTAs past [0] tracing, [1] shading, [2] the push — cumulative over all frames, never
+                                    // reset: this launch's barriers release at target[k] (the counters wrap)
+    uint32_t target[3];
+    uint32_t* zero_words;           // the counter set of the NEXT frame (double-buffered): cleared by this launch
+    uint32_t n_zero_words;
     uint32_t* sync;                 // rt_peer_sync layout in rank 0's memory (peer mapped), or nullptr: no other ranks
     uint32_t frame, rank, world;
 };
@@ -738,6 +742,8 @@ struct FrameArgs {
     FrameSyncDev y;
     PushDev push;
     int max_depth;
+    unsigned long long* phase_times;   // debug (RT_FLAG_WARP_TIMES): 8 time stamps per warp
+    int phase1_only;                   // debug (RT_FK_SPLIT=1): stop after the tracing phase; the host launches k_shade
 };
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
@@ -751,11 +757,27 @@ __device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t want, 
     }
 }
 
+// The same for a cumulative counter that wraps: until *p has reached `target`.
+__device__ __forceinline__ void spin_until_reached(const uint32_t* p, uint32_t target, uint32_t* sticky, unsigned ns) {
+    long long t0 = clock64();
+    while ((int32_t)(ld_volatile_u32(p) - target) < 0) {
+        if (clock64() - t0 > 4000000000ll) { atomicOr(sticky, 4u); break; }
+        __nanosleep(ns);
+    }
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(const __grid_constant__ FrameArgs a) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const bool pushing = a.push.packed != nullptr;
+    // (nothing is kept live across phase 1 that phase 1 does not need: its loop sits exactly at the register budget)
+    auto stamp = [&](int k) {
+        if (a.phase_times && (threadIdx.x & 31) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.phase_times[8 * (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + k] = t;
+        }
+    };
+    stamp(0);
+    if (blockIdx.x == 0 && threadIdx.x < a.y.n_zero_words) a.y.zero_words[threadIdx.x] = 0u;   // next frame's counters
     // rank 0 opens the frame for the other ranks: everything enqueued on its stream for the previous frame (a copy to
     // the host, say) has finished before this kernel started
     if (a.y.sync && a.y.rank == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -764,24 +786,27 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(c
         __threadfence_system();
     }
     // ---- phase 1
-    uint32_t claimed = traverse_body<MODE_PRIMARY, COUNT, true, 0, false>(a.t, nullptr);
-    const uint32_t n_items = a.t.f.n_local_pix;
-    if (lane == 0) {
+    traverse_body<MODE_PRIMARY, COUNT, true, 0, false>(a.t, nullptr);
+    stamp(1);
+    if (a.phase1_only) return;
+    // every hit of the frame is in the queue once all CTAs are here
+    __syncthreads();
+    if (threadIdx.x == 0) {
         __threadfence();
-        if (claimed) atomicAdd(a.y.done + 0, claimed);
-        spin_until_ge(a.y.done + 0, n_items, a.t.sticky, 100);
+        atomicAdd(a.y.done + 0, 1u);
+        spin_until_reached(a.y.done + 0, a.y.target[0], a.t.sticky, 200);
         __threadfence();
     }
-    __syncwarp();
-    // ---- phase 2: shade the hit queue (World::shade_ray's local term, world.cpp:40-63, :126-137)
+    __syncthreads();
+    stamp(2);
+    // ---- phase 2: shade the hit queue (World::shade_ray's local term, world.cpp:40-63, :126-137), 32 hits per warp
+    // and round, rounds dealt out statically
+    const int lane = threadIdx.x & 31;
+    const bool pushing = a.push.packed != nullptr;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t n_hits = __ldcg(&a.t.wave->n_hits);
     const f3 bg = mk3(a.t.s.background[0], a.t.s.background[1], a.t.s.background[2]);
-    uint32_t shaded = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&a.t.wave->fetch_shade, 32u);
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= n_hits) break;
+    for (uint32_t base = gwarp * 32u; base < n_hits; base += n_warps * 32u) {
         uint32_t pos = base + lane;
         if (pos < n_hits) {
             uint32_t idx = __ldcg(a.t.hitq + pos);
@@ -800,18 +825,22 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(c
             f3 contrib = out.local + out.bg_weight * bg;
             write_pixel_direct(a.t.direct_rgb, pixel_byte_offset(a.t.f, pi, pj, a.t.direct_packed), contrib);
         }
-        shaded += min(32u, n_hits - base);
     }
-    if (pushing && lane == 0) {
+    stamp(3);
+    if (!pushing) return;                                  // pixels were written in place: the frame is done
+    // barrier: every CTA has shaded its rounds
+    __syncthreads();
+    if (threadIdx.x == 0) {
         __threadfence();
-        if (shaded) atomicAdd(a.y.done + 1, shaded);
-        spin_until_ge(a.y.done + 1, n_hits, a.t.sticky, 100);
+        atomicAdd(a.y.done + 1, 1u);
+        spin_until_reached(a.y.done + 1, a.y.target[1], a.t.sticky, 200);
         if (a.y.sync && a.y.rank != 0) spin_until_ge(a.y.sync + 64, a.y.frame, a.t.sticky, 200);   // frame open?
         __threadfence();
     }
-    __syncwarp();
+    __syncthreads();
+    stamp(4);
     // ---- phase 3: packed tiles -> the shared frame
-    if (pushing) {
+    {
         const FrameDev& f = a.t.f;
         const uint32_t world = (uint32_t)f.world, src = a.y.rank;
         const uint32_t n_owned = a.push.tiles_total > src ? (a.push.tiles_total - src + world - 1) / world : 0u;
@@ -853,12 +882,13 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(c
             }
         }
     }
+    stamp(5);
     // ---- exit: the last CTA completes the frame
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();                            // this CTA's stores (peer memory included) are out
         uint32_t prev = atomicAdd(a.y.done + 2, 1u);
-        if (prev == gridDim.x - 1) {
+        if (prev + 1u == a.y.target[2]) {
             if (a.y.sync && a.y.world > 1) {
                 uint32_t* slot = a.y.sync + (a.y.frame % 64u);
                 if (a.y.rank != 0) {
@@ -869,10 +899,9 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(c
                     *(volatile uint32_t*)(a.y.sync + ((a.y.frame + 32u) % 64u)) = 0u;   // the slot that comes into use 32 frames on
                 }
             }
-            a.y.done[0] = 0; a.y.done[1] = 0; a.y.done[2] = 0;                         // ready for the next frame
-            __threadfence();
         }
     }
+    stamp(6);
 }
 
 // ---- k_paths: every bounce generation in ONE launch --------------------------------------------------
@@ -1572,7 +1601,7 @@ bool rt_frame_pushes_inline(const rt_ctx* c, const rt_render_params* p) {
 bool rt_frame_kernel_ok(const rt_ctx* c, const rt_render_params* p, bool pushing) {
     const bool stealing = p->world_size > 1 && p->steal_pool_div > 0;
     return (c->frame_kernel == 2 || (c->frame_kernel == 1 && pushing)) && !rt_scene_bounces(c, p->max_depth) && c->fuse_shadow &&
-           c->scene.n_lights > 0 && c->scene.n_lights <= 8 && !stealing && !(p->flags & RT_FLAG_WARP_TIMES);
+           c->scene.n_lights > 0 && c->scene.n_lights <= 8 && !stealing;
 }
 
 // Waits for the context's stream and turns the sticky device error word into an exception.
@@ -1613,6 +1642,8 @@ void rt_render_init(rt_ctx* c) {
     c->frame_blocks = persistent_blocks(k_frame<false>, TRAV_TPB, c->sm_count);
     c->d_fsync.reserve(4);
     RT_CUDA(cudaMemset(c->d_fsync.p, 0, 4 * sizeof(uint32_t)));
+    c->d_fk.reserve(2);
+    RT_CUDA(cudaMemset(c->d_fk.p, 0, 2 * sizeof(FrameKernelCounters)));
     if (c->blocks_per_sm > 0) {   // RT_BLOCKS_PER_SM: cap the persistent grids (tuning)
         int cap = c->blocks_per_sm * c->sm_count;
         c->trace_blocks = lo(c->trace_blocks, cap);
@@ -1642,14 +1673,35 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     ensure_queues(c, pix_cap, bounce);
     c->d_accum.reserve(3 * (pix_cap ? pix_cap : 1));
 
-    RT_CUDA(cudaEventRecord(c->ev[0], st));
-    RT_CUDA(cudaMemsetAsync(c->d_waves.p, 0, RT_WAVE_SLOTS * sizeof(WaveCounters), st));
-    RT_CUDA(cudaMemsetAsync(c->d_frame.p, 0, sizeof(FrameCounters), st));
+    // no bounces => one contribution per pixel => RGB8 straight from the wave-0 kernels (stolen blocks keep
+    // the accumulator path: their packed offset is not defined)
+    const bool direct = !bounce && rgb_dev != nullptr && f.steal_cursor == nullptr;
+    const bool has_work = f.n_local_pix > 0 || f.steal_cursor != nullptr;
+    const bool pushing = c->push.frame != nullptr;
+    const bool use_fk = direct && rt_frame_kernel_ok(c, p, pushing) && (has_work || pushing);
+    // event records only where somebody reads them: each one is a serialisation point on the stream
+    auto mark = [&](int k) { if (stats) RT_CUDA(cudaEventRecord(c->ev[k], st)); };
+    mark(0);
+    WaveCounters* waves_dev = c->d_waves.p;
+    FrameCounters* frame_dev_ctr = c->d_frame.p;
+    uint32_t* zero_next = nullptr;
+    if (use_fk) {
+        // k_frame's counters are double-buffered and cleared by the previous launch: no memset on the stream
+        FrameKernelCounters* set = c->d_fk.p + (c->fk_epoch & 1u);
+        zero_next = (uint32_t*)(c->d_fk.p + ((c->fk_epoch + 1u) & 1u));
+        c->fk_epoch++;
+        waves_dev = &set->wave;
+        frame_dev_ctr = &set->fc;
+    } else {
+        RT_CUDA(cudaMemsetAsync(c->d_waves.p, 0, RT_WAVE_SLOTS * sizeof(WaveCounters), st));
+        RT_CUDA(cudaMemsetAsync(c->d_frame.p, 0, sizeof(FrameCounters), st));
+    }
+    c->last_frame_ctr = frame_dev_ctr;
 
     TravArgs ta;
     memset(&ta, 0, sizeof ta);
     ta.s = c->scene; ta.cam = make_cam(cam); ta.f = f;
-    ta.accum = c->d_accum.p; ta.fc = c->d_frame.p; ta.sticky = c->d_sticky.p;
+    ta.accum = c->d_accum.p; ta.fc = frame_dev_ctr; ta.sticky = c->d_sticky.p;
     ta.aux_prim = aux_dev ? aux_dev->prim_id : nullptr;
     ta.aux_t = aux_dev ? aux_dev->t : nullptr;
     ta.brute = (p->flags & RT_FLAG_BRUTE_FORCE) ? 1u : 0u;
@@ -1668,29 +1720,37 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         c->d_warp_times.reserve(2 * (size_t)mb * (TRAV_TPB / 32));
         ta.warp_times = c->d_warp_times.p;
     }
-    // no bounces => one contribution per pixel => RGB8 straight from the wave-0 kernels (stolen blocks keep
-    // the accumulator path: their packed offset is not defined)
-    const bool direct = !bounce && rgb_dev != nullptr && f.steal_cursor == nullptr;
     if (direct) {
         ta.direct_rgb = sa.direct_rgb = (uint8_t*)rgb_dev;
         ta.direct_packed = sa.direct_packed = (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0;
     }
     ta.remote_out = (c->remote_output && direct) ? 1 : 0;
     uint32_t launches = 0;
-    const bool has_work = f.n_local_pix > 0 || f.steal_cursor != nullptr;
-    const bool pushing = c->push.frame != nullptr;
-    if (direct && rt_frame_kernel_ok(c, p, pushing) && (has_work || pushing)) {
+    if (use_fk) {
         // the whole frame in one launch: trace + shadow rays, shade, (push + handshake)
         FrameArgs fa;
         memset(&fa, 0, sizeof fa);
         ta.q = queue_of(c, 0);
-        ta.wave = c->d_waves.p;
+        ta.wave = waves_dev;
         ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p; ta.occl = c->d_occl.p;
         ta.refill_min = c->refill_primary_fused;
         ta.loop_style = c->loop_primary;
         fa.t = ta;
         fa.max_depth = p->max_depth;
+        static const bool fk_split = getenv("RT_FK_SPLIT") != nullptr;
+        fa.phase1_only = (fk_split && !pushing) ? 1 : 0;
         fa.y.done = c->d_fsync.p;
+        fa.y.zero_words = zero_next;
+        fa.y.n_zero_words = (uint32_t)(sizeof(FrameKernelCounters) / sizeof(uint32_t));
+        if (!fa.phase1_only) c->fsync_target[0] += (uint32_t)c->frame_blocks;
+        if (pushing) { c->fsync_target[1] += (uint32_t)c->frame_blocks; c->fsync_target[2] += (uint32_t)c->frame_blocks; }
+        for (int k = 0; k < 3; k++) fa.y.target[k] = c->fsync_target[k];
+        if (p->flags & RT_FLAG_WARP_TIMES) {
+            c->d_warp_times.reserve(8 * (size_t)c->frame_blocks * (TRAV_TPB / 32));
+            RT_CUDA(cudaMemsetAsync(c->d_warp_times.p, 0, 8 * (size_t)c->frame_blocks * (TRAV_TPB / 32) * sizeof(unsigned long long), st));
+            fa.phase_times = c->d_warp_times.p;
+            fa.t.warp_times = nullptr;
+        }
         if (pushing) {
             fa.y.sync = c->push.world > 1 ? (uint32_t*)c->push.sync : nullptr;
             fa.y.frame = c->push.frame_index; fa.y.rank = (uint32_t)c->push.rank; fa.y.world = (uint32_t)c->push.world;
@@ -1700,20 +1760,30 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
             fa.push.wide16 = (f.W * 3) % 16 == 0 && (f.tile_w * 3) % 16 == 0 && ((uintptr_t)rgb_dev & 15) == 0 &&
                              ((uintptr_t)c->push.frame & 15) == 0;
         }
-        if (count) k_frame<true><<<c->frame_blocks, TRAV_TPB, 0, st>>>(fa);
-        else k_frame<false><<<c->frame_blocks, TRAV_TPB, 0, st>>>(fa);
+        {
+            // the phases are separated by barriers over CTAs: a cooperative launch guarantees that all of them are resident
+            void* kargs[] = {(void*)&fa};
+            const void* fn = count ? (const void*)k_frame<true> : (const void*)k_frame<false>;
+            RT_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)c->frame_blocks), dim3(TRAV_TPB), kargs, 0, st));
+        }
         RT_CUDA(cudaGetLastError());
         launches++;
         c->push.done = true;
-        RT_CUDA(cudaEventRecord(c->ev[1], st));
-        RT_CUDA(cudaEventRecord(c->ev[2], st));
+        mark(1);
+        mark(2);
+        if (fa.phase1_only) {
+            sa.qin = queue_of(c, 0); sa.qout = queue_of(c, 1);
+            sa.wave = waves_dev; sa.next = waves_dev; sa.occl = c->d_occl.p; sa.occl_bits = 1;
+            launch_shade<true>(c, sa);
+            launches++;
+        }
     } else if (has_work) {
-        launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, c->ev[1], c->ev[2]);
+        launches += launch_wave<true>(c, ta, sa, 0, 1, 0, count, true, stats ? c->ev[1] : nullptr, stats ? c->ev[2] : nullptr);
     } else {
-        RT_CUDA(cudaEventRecord(c->ev[1], st));
-        RT_CUDA(cudaEventRecord(c->ev[2], st));
+        mark(1);
+        mark(2);
     }
-    RT_CUDA(cudaEventRecord(c->ev[3], st));
+    mark(3);
 
     WaveResult wr;
     const bool use_paths = c->path_kernel && c->scene.n_lights <= 8;
@@ -1730,7 +1800,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
             launches += wr.launches;
         }
     }
-    RT_CUDA(cudaEventRecord(c->ev[6], st));
+    mark(6);
 
     if (has_work && rgb_dev && !direct) {
         uint32_t quads = f.n_tiles_owned * (uint32_t)(f.tile_pix / 4) + (f.steal_cursor ? f.n_pool_blocks * 8u : 0u);
@@ -1749,13 +1819,18 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
     }
     c->frames_in_layout++;
     c->launch_total += launches;
-    RT_CUDA(cudaEventRecord(c->ev[7], st));
+    mark(7);
 
     // Without a stats request the frame is left in flight: nothing below synchronises, errors stay in
     // the sticky word until rt_synchronize / the next stats-bearing call.
     if (!stats) return;
-    RT_CUDA(cudaMemcpyAsync(c->h_waves, c->d_waves.p, RT_WAVE_SLOTS * sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
-    RT_CUDA(cudaMemcpyAsync(c->h_frame, c->d_frame.p, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
+    if (use_fk) {
+        memset(c->h_waves, 0, RT_WAVE_SLOTS * sizeof(WaveCounters));
+        RT_CUDA(cudaMemcpyAsync(c->h_waves, waves_dev, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+    } else {
+        RT_CUDA(cudaMemcpyAsync(c->h_waves, c->d_waves.p, RT_WAVE_SLOTS * sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+    }
+    RT_CUDA(cudaMemcpyAsync(c->h_frame, frame_dev_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, st));
     rt_sync_and_check(c);
     uint64_t secondary = wr.secondary;
     uint32_t max_queue = wr.max_queue;

@@ -75,6 +75,12 @@ struct FrameCounters {
     unsigned long long node_visits[2], tri_tests[2];   // [0] nearest-hit rays, [1] any-hit (shadow) rays
 };
 
+// k_frame's own counters (two sets: the launch of frame k clears the set of frame k+1)
+struct FrameKernelCounters {
+    WaveCounters wave;
+    FrameCounters fc;
+};
+
 // Ray queue in SoA float4 records (48 B per ray).
 struct RayQueue {
     float4* o_pix;   // origin.xyz, as_float(local pixel index)
@@ -196,7 +202,11 @@ struct rt_ctx {
     bool remote_output = false;            // rt_render_push: the frame being rendered into sits in another GPU's memory
     int frame_kernel = 2;                  // whole bounce-free frames in one k_frame launch (RT_FRAME_KERNEL): 0 never, 1 when pushed to a shared frame, 2 always
     int frame_blocks = 0;
-    DevBuf<uint32_t> d_fsync;              // k_frame's phase counters (zero between frames)
+    DevBuf<uint32_t> d_fsync;              // k_frame's phase counters
+    uint32_t fsync_target[3] = {0, 0, 0};  // where the cumulative barrier counters stand after the launch being built (wrap)
+    DevBuf<FrameKernelCounters> d_fk;      // k_frame's double-buffered counters
+    uint32_t fk_epoch = 0;
+    FrameCounters* last_frame_ctr = nullptr;   // device counters of the frame enqueued last (d_frame or a d_fk set)
     struct PushTarget {                    // set by rt_push_frame around rt_render_frame: where this rank's tiles go
         void* frame = nullptr;             // the shared frame (nullptr: not pushing)
         void* sync = nullptr;

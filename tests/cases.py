@@ -6,7 +6,7 @@ SMALL = (160, 120)
 
 GOLDEN_CASES = [
     "tetra_d10", "bob2000_d10", "analytic_close_d5", "analytic_notetra_d5", "analytic_stock_d1",
-    "bobtex_d3", "blubmixed_d5", "synth_small_d1", "bob_full_bboxfixed_d10", "analytic_close_d0",
+    "bobtex_d3", "blubmixed_d5", "synth_small_d1", "bob_full_bboxfixed_d10", "glass_ball_d0",
 ]
 
 
@@ -30,11 +30,25 @@ def build_case(name):
     if name == "synth_small_d1":
         return (scenes.synthetic_sphere_grid(grid=3, level=2), scenes.synthetic_camera(w, h, grid=3), 1,
                 ob.MODE_AS_SHIPPED)
-    if name == "analytic_close_d0":          # depth 0: the refracted child of the dielectric cylinder (level 0 * 2) is alive
-        return scenes.analytic_scene(), scenes.close_camera(320, 240), 0, ob.MODE_TRUE_NEAREST
+    if name == "glass_ball_d0":              # depth 0: the refracted child of a dielectric hit (level 0 * 2 = 0) is alive
+        return glass_ball_scene(), scenes.close_camera(320, 240), 0, ob.MODE_TRUE_NEAREST
     if name == "bob_full_bboxfixed_d10":
         return scenes.obj_scene("bob_tri.obj"), scenes.stock_camera(w, h), 10, ob.MODE_BBOX_FIXED
     raise KeyError(name)
+
+
+def glass_ball_scene():
+    """A dielectric sphere (eta 1.5: refraction succeeds over the middle of the disc) in front of a diffuse sphere,
+    over a diffuse floor."""
+    import numpy as np
+    from realtrace_b200.scene import Scene, make_materials
+    mats = make_materials([dict(color=(1.0, 1.0, 1.0), ka=0.4, kd=0.9, ks=0.4, kr=0.1, kt=0.8, eta=1.5),
+                           dict(color=(0.8, 0.1, 0.0), ka=0.2, kd=0.9, ks=0.4),
+                           dict(color=(0.5, 0.5, 0.5), ka=0.1, kd=0.9, ks=0.2)])
+    return Scene(sph=[(0.0, 0.0, 6.0, 4.0), (3.0, 1.0, -6.0, 4.0)], sph_material=[0, 1], sph_object_id=[0, 1],
+                 pln=[(20, -5, 20, -20, -5, 20, -20, -5, -20, 20, -5, -20)], pln_material=[2], pln_object_id=[2],
+                 materials=mats, lights=np.asarray([scenes.STOCK_LIGHT], np.float32), ambient=scenes.STOCK_AMBIENT,
+                 background=scenes.STOCK_BACKGROUND, name="glass_ball").normalise()
 
 
 # ---- edge cases (no golden fixtures: checked against the oracle on the spot) --------------------------------------

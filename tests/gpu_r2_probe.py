@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 VARIANTS = [
     {"RT_FRAME_KERNEL": "0"},
     {"RT_FRAME_KERNEL": "2"},
-    {"RT_FRAME_KERNEL": "0", "RT_FUSE_SHADE": "0"},
+    {"RT_FRAME_KERNEL": "2", "RT_FK_SPLIT": "1"},
 ]
 
 
@@ -52,11 +52,19 @@ def child():
         # warp finish times of the share (cold)
         flush.fill_(1)
         st = ctx.render_device(cam, depth, buf.data_ptr(), tile=tile, rank=0, world=world, flags=fl | api.FLAG_WARP_TIMES)
-        t = ctx.warp_times().astype(np.int64)
-        t = t[t[:, 1] > 0]
-        if len(t):
-            end = (t[:, 1] - t[:, 0].min()) / 1e3
-            out[f"w{world}_warp_end_us"] = {q: round(float(np.percentile(end, q)), 1) for q in (50, 90, 99, 100)}
+        raw = ctx.warp_times(1 << 17).astype(np.int64)
+        if os.environ.get("RT_FRAME_KERNEL") == "2":
+            ph = raw.reshape(-1)[: (raw.size // 8) * 8].reshape(-1, 8)
+            ph = ph[ph[:, 0] > 0]
+            t0 = ph[:, 0].min()
+            out[f"w{world}_phase_us"] = {name: {q: round(float(np.percentile((ph[:, k] - t0) / 1e3, q)), 1) for q in (0, 50, 99, 100)}
+                                         for k, name in enumerate(["start", "traced", "barrier1", "shaded", "barrier2", "pushed", "exit"])
+                                         if (ph[:, k] > 0).any()}
+        else:
+            t = raw[raw[:, 1] > 0]
+            if len(t):
+                end = (t[:, 1] - t[:, 0].min()) / 1e3
+                out[f"w{world}_warp_end_us"] = {q: round(float(np.percentile(end, q)), 1) for q in (50, 90, 99, 100)}
         out[f"w{world}_stats"] = {k: round(st[k], 4) for k in ("ms_device", "ms_trace", "ms_shade")}
     # the multi-GPU frame step of a rank > 0 (render + push + its half of the handshake), frame and flags on this GPU
     world, tile, rank = 8, (32, 16), 1
@@ -83,6 +91,19 @@ def child():
     ctx.synchronize()
     t = np.array([a.elapsed_time(b) for a, b in evs])
     out["w8_push_cold_ms"] = [round(float(np.median(t)), 4), round(float(t.min()), 4)]
+    if os.environ.get("RT_FRAME_KERNEL") == "2":
+        flush.fill_(3)
+        ctx.peer_sync(sync_ptr, 0, world, k, 0)
+        params.flags |= api.FLAG_WARP_TIMES
+        ctx.render_push(cs, params, packed.data_ptr(), frame.data_ptr(), sync_ptr, k)
+        ctx.synchronize()
+        raw = ctx.warp_times(1 << 17).astype(np.int64)
+        ph = raw.reshape(-1)[: (raw.size // 8) * 8].reshape(-1, 8)
+        ph = ph[ph[:, 0] > 0]
+        t0 = ph[:, 0].min()
+        out["w8_push_phase_us"] = {name: {q: round(float(np.percentile((ph[:, kk] - t0) / 1e3, q)), 1) for q in (0, 50, 99, 100)}
+                                   for kk, name in enumerate(["start", "traced", "barrier1", "shaded", "barrier2", "pushed", "exit"])
+                                   if (ph[:, kk] > 0).any()}
     print(json.dumps(out), flush=True)
     ctx.close()
 
