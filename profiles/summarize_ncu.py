@@ -1,9 +1,12 @@
 #!/usr/bin/env python3
 """Turns gpurun_out ncu artefacts into the committed summaries under profiles/.
-usage: summarize_ncu.py <tag> <launches.csv> <prof.ncu-rep | -> [workload]   ("-": launch list only)"""
+usage: summarize_ncu.py <tag> <launches.csv> <prof.ncu-rep | -> [workload] [rays_per_frame]   ("-": launch list only)
+With rays_per_frame the per-launch counters of the frame kernels (executed warp instructions, L2 and DRAM bytes) are
+also written to ncu_counts.json, which bench.py reads for the issue / L2 / HBM terms of its roofline."""
 import collections, csv, json, os, subprocess, sys
 tag, launches, rep = sys.argv[1:4]
 workload = sys.argv[4] if len(sys.argv) > 4 else "synth1m"
+rays_per_frame = float(sys.argv[5]) if len(sys.argv) > 5 else None
 here = os.path.dirname(os.path.abspath(__file__))
 # ---- launch list -> per-kernel shares
 rows = list(csv.reader(open(launches)))
@@ -45,6 +48,9 @@ def mb(val, unit):
     v = float(val.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 traffic = {}
+counts = {"inst_executed": 0.0, "lts_bytes": 0.0, "dram_bytes": 0.0, "kernels": [], "rays": rays_per_frame,
+          "source": f"profiles/{tag}_ncu_full.md (ncu --set full, one launch per kernel of a frame)"}
+FRAME_KERNELS = ("k_frame", "k_traverse", "k_shade", "k_paths", "k_resolve")
 with open(os.path.join(here, f"{tag}_ncu_full.md"), "w") as f:
     f.write(f"# {tag}: ncu --set full --clock-control none (one launch per kernel), {workload}\n\n")
     for r in rows[2:]:
@@ -53,6 +59,13 @@ with open(os.path.join(here, f"{tag}_ncu_full.md"), "w") as f:
         for k in keep:
             if k in idx: f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
         f.write("\n")
+        if any(k in name for k in FRAME_KERNELS) and "smsp__inst_executed.sum" in idx:
+            counts["inst_executed"] += float(r[idx["smsp__inst_executed.sum"]].replace(",", ""))
+            if "lts__t_bytes.sum" in idx:
+                counts["lts_bytes"] += mb(r[idx["lts__t_bytes.sum"]], units[idx["lts__t_bytes.sum"]])
+            counts["dram_bytes"] += mb(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + \
+                                    mb(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+            counts["kernels"].append(name.split("(")[0][-60:])
         short = "k_traverse<primary>" if "k_traverse<0" in name else "k_traverse<queue>" if "k_traverse<1" in name else \
                 "k_traverse<shadow>" if "k_traverse<2" in name else \
                 "k_shade" if "k_shade" in name else "k_resolve" if "k_resolve" in name else name.split("(")[0].split("::")[-1]
@@ -63,5 +76,11 @@ tj = json.load(open(tp)) if os.path.exists(tp) else {}
 tj[workload] = traffic
 tj["_source"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/{tag}_ncu_full.md"
 json.dump(tj, open(tp, "w"), indent=1, sort_keys=True)
+if rays_per_frame:
+    cp = os.path.join(here, "ncu_counts.json")
+    cj = json.load(open(cp)) if os.path.exists(cp) else {}
+    cj[workload] = counts
+    json.dump(cj, open(cp, "w"), indent=1, sort_keys=True)
 print(open(os.path.join(here, f"{tag}_launches.md")).read())
 print(json.dumps(traffic))
+print(json.dumps(counts))

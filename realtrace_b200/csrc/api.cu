@@ -2,6 +2,7 @@
 // entry point converts failures into a negative rt_status and records the text for rt_last_error.
 #include <cmath>
 #include <cstring>
+#include <ctime>
 
 #include "rt_context.h"
 
@@ -70,6 +71,7 @@ static rt_ctx* make_ctx(int device) {
         env_int("RT_FUSE_SHADOW", 0, 1, c->fuse_shadow);
         env_int("RT_FUSE_SHADE", 0, 2, c->fuse_shade);
         env_int("RT_FRAME_KERNEL", 0, 2, c->frame_kernel);
+        env_int("RT_PUSH_INLINE", 0, 1, c->push_inline);
         env_int("RT_TILE_BUCKET_BITS", 0, 8, c->tile_bucket_bits);
         env_int("RT_PATH_KERNEL", 0, 1, c->path_kernel);
         env_int("RT_TILE_FEEDBACK", 0, 1, c->tile_feedback);
@@ -526,12 +528,23 @@ static void wait_slot(rt_ctx* ctx, int slot) {
 }
 
 // Frame `slot`: render into the slot's device frame, then copy it to the host on the copy streams.
+
+static double host_now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static void enqueue_slot(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint8_t* rgb_out, int slot,
                          const rt_aux_out* aux_dev) {
+    static const bool trace = getenv("RT_TRACE_HOST") != nullptr;
+    double t0 = trace ? host_now_ms() : 0.0;
     size_t bytes = (size_t)cam->width * cam->height * 3;
     ensure_slot(ctx, slot, bytes);
+    if (slot == 0 && ctx->pipelined) ensure_slot(ctx, 1, bytes);   // (allocating a shared frame takes milliseconds)
     rt_ctx::FrameSlot& s = ctx->slots[slot];
     if (s.in_flight) wait_slot(ctx, slot);           // the slot's previous frame must have left its device frame
+    double t1 = trace ? host_now_ms() : 0.0;
     if (ctx->kids.empty()) {
         rt_render_params q = *p;
         q.flags &= ~(uint32_t)RT_FLAG_PACKED_TILES;
@@ -540,9 +553,12 @@ static void enqueue_slot(rt_ctx* ctx, const rt_camera* cam, const rt_render_para
     } else {
         rt_multi_enqueue_frame(ctx, cam, p, s.frame.va, aux_dev);
     }
+    double t2 = trace ? host_now_ms() : 0.0;
     RT_CUDA(cudaEventRecord(s.ready, ctx->stream));
     rt_frame_download_async(ctx, s.frame, rgb_out, bytes, s.ready, s.done, s.h_sticky);
     s.in_flight = true;
+    if (trace) fprintf(stderr, "[rt host] enqueue_slot %d: slot wait %.3f ms, frame enqueue %.3f ms, download enqueue %.3f ms\n", slot,
+                       t1 - t0, t2 - t1, host_now_ms() - t2);
 }
 
 int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_render_params* p, uint8_t* rgb_out, const rt_aux_out* aux,
@@ -614,14 +630,23 @@ int rt_render_enqueue(rt_ctx* ctx, const rt_camera* cam, const rt_render_params*
         check_render_args(ctx, cam, p);
         need(rgb_out != nullptr && (slot == 0 || slot == 1), "rt_render_enqueue: rgb_out is NULL or slot is not 0/1");
         need(!(p->flags & RT_FLAG_PACKED_TILES) && p->world_size <= 1, "rt_render_enqueue renders whole frames");
-        // an asynchronous copy needs a page-locked destination: lock the caller's buffer the first time it is seen
-        cudaPointerAttributes at;
-        cudaError_t e = cudaPointerGetAttributes(&at, rgb_out);
-        if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered) {
-            cudaGetLastError();
-            size_t bytes = (size_t)cam->width * cam->height * 3;
-            if (cudaHostRegister(rgb_out, bytes, cudaHostRegisterPortable) == cudaSuccess) ctx->host_registered.push_back(rgb_out);
-            else cudaGetLastError();                  // stays pageable: the copy is then staged by the driver
+        ctx->pipelined = true;                         // both frame slots are set up at the first call
+        // an asynchronous copy needs a page-locked destination: lock the caller's buffer the first time it is seen.
+        // (The pointer query takes a driver-wide lock and was measured at 0.1 - 15 ms while frames are in flight, so
+        // every destination is looked at once.)
+        bool known = false;
+        for (void* q : ctx->host_checked) known |= q == (void*)rgb_out;
+        if (!known) {
+            cudaPointerAttributes at;
+            cudaError_t e = cudaPointerGetAttributes(&at, rgb_out);
+            if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered) {
+                cudaGetLastError();
+                size_t bytes = (size_t)cam->width * cam->height * 3;
+                if (cudaHostRegister(rgb_out, bytes, cudaHostRegisterPortable) == cudaSuccess) ctx->host_registered.push_back(rgb_out);
+                else cudaGetLastError();              // stays pageable: the copy is then staged by the driver
+            }
+            if (ctx->host_checked.size() >= 64) ctx->host_checked.clear();
+            ctx->host_checked.push_back(rgb_out);
         }
         enqueue_slot(ctx, cam, p, rgb_out, slot, nullptr);
     });

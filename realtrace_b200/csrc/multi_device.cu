@@ -19,6 +19,7 @@
 #include <cudaTypedefs.h>
 
 #include <cstring>
+#include <ctime>
 #include <thread>
 
 #include "rt_context.h"
@@ -220,8 +221,11 @@ void rt_multi_enqueue_frame(rt_ctx* c, const rt_camera* cam, const rt_render_par
         q.tile_h = n >= 4 ? 16 : 32;
     }
     const uint32_t k = c->mg_frame++;
+    static const bool trace = getenv("RT_TRACE_HOST") != nullptr;
     for (int r = 0; r < n; r++) {
         rt_ctx* x = ranks[r];
+        timespec ts0;
+        if (trace) clock_gettime(CLOCK_MONOTONIC, &ts0);
         RT_CUDA(cudaSetDevice(x->device));
         q.rank = r;
         uint32_t total, owned, tb;
@@ -230,6 +234,12 @@ void rt_multi_enqueue_frame(rt_ctx* c, const rt_camera* cam, const rt_render_par
         if (r == 0) RT_CUDA(cudaEventRecord(c->mg_ev[0], x->stream));
         rt_push_frame(x, cam, &q, x->d_packed.p, frame_dev, c->mg_sync, k, aux_dev);
         if (r == 0) RT_CUDA(cudaEventRecord(c->mg_ev[1], x->stream));
+        if (trace) {
+            timespec ts1;
+            clock_gettime(CLOCK_MONOTONIC, &ts1);
+            fprintf(stderr, "[rt host] frame %u rank %d enqueued in %.3f ms\n", k, r,
+                    (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
+        }
     }
     RT_CUDA(cudaSetDevice(c->device));
 }

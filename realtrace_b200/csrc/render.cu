@@ -886,9 +886,13 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(c
     // ---- exit: the last CTA completes the frame
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();                            // this CTA's stores (peer memory included) are out
+        // this CTA's stores are ordered before its count at GPU scope; the last CTA, which has observed every count,
+        // publishes all of them at system scope with ONE fence before it signals (causality order is cumulative) —
+        // a system-scope fence per CTA cost 7 us at the end of every frame
+        __threadfence();
         uint32_t prev = atomicAdd(a.y.done + 2, 1u);
         if (prev + 1u == a.y.target[2]) {
+            __threadfence_system();
             if (a.y.sync && a.y.world > 1) {
                 uint32_t* slot = a.y.sync + (a.y.frame % 64u);
                 if (a.y.rank != 0) {
@@ -902,6 +906,58 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(c
         }
     }
     stamp(6);
+}
+
+// ---- k_frame_push: the multi-GPU frame of a bounce-free scene in ONE launch ------------------------------------------
+// k_frame's push phase sends a rank's whole share at the END of the frame: at 8 GPUs seven ranks then store 21.8 MB into
+// rank 0 at the same moment, and that burst is bound by rank 0's NVLink ingress (measured: +50 us on a 190 us frame).
+// Here the stores are spread over the frame instead: the traversal body runs in its SHADE form — a warp shades the
+// hits of its 32-pixel batch when the batch is done and stores the finished 8x4 block straight into the shared frame
+// with 8-byte stores — and the handshake is folded into the same launch:
+//   start   rank 0 publishes "frame open" (everything it enqueued for the previous frame is done); the other ranks'
+//           CTAs wait for that flag before their first store (one poll per CTA)
+//   exit    every CTA counts itself after a GPU-scope fence; the last one publishes all stores with one system-scope
+//           fence and signals rank 0's arrival slot — on rank 0 it waits for the other ranks' arrivals instead, so the
+//           end of rank 0's launch IS the completion of the frame.  No handshake kernels, no collective, no barrier
+//           inside the grid (an ordinary launch).
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame_push(const __grid_constant__ FrameArgs a) {
+    __shared__ float s_pdir[3 * TRAV_TPB];
+    if (blockIdx.x == 0 && threadIdx.x < a.y.n_zero_words) a.y.zero_words[threadIdx.x] = 0u;   // next frame's counters
+    if (a.y.sync && a.y.world > 1) {
+        if (a.y.rank == 0) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                volatile uint32_t* consumed = a.y.sync + 64;
+                if (*consumed < a.y.frame) *consumed = a.y.frame;
+                __threadfence_system();
+            }
+        } else {
+            if (threadIdx.x == 0) {
+                spin_until_ge(a.y.sync + 64, a.y.frame, a.t.sticky, 200);
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
+    }
+    traverse_body<MODE_PRIMARY, COUNT, true, 0, true>(a.t, s_pdir);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t prev = atomicAdd(a.y.done + 2, 1u);
+        if (prev + 1u == a.y.target[2]) {
+            __threadfence_system();
+            if (a.y.sync && a.y.world > 1) {
+                uint32_t* slot = a.y.sync + (a.y.frame % 64u);
+                if (a.y.rank != 0) {
+                    atomicAdd_system(slot, 1u);
+                } else {
+                    spin_until_ge(slot, a.y.world - 1, a.t.sticky, 100);
+                    __threadfence_system();
+                    *(volatile uint32_t*)(a.y.sync + ((a.y.frame + 32u) % 64u)) = 0u;
+                }
+            }
+        }
+    }
 }
 
 // ---- k_paths: every bounce generation in ONE launch --------------------------------------------------
@@ -1640,6 +1696,7 @@ void rt_render_init(rt_ctx* c) {
     c->shade_blocks = lo(persistent_blocks(k_shade<true>, SHADE_TPB, c->sm_count),
                          persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
     c->frame_blocks = persistent_blocks(k_frame<false>, TRAV_TPB, c->sm_count);
+    c->frame_push_blocks = persistent_blocks(k_frame_push<false>, TRAV_TPB, c->sm_count);
     c->d_fsync.reserve(4);
     RT_CUDA(cudaMemset(c->d_fsync.p, 0, 4 * sizeof(uint32_t)));
     c->d_fk.reserve(2);
@@ -1650,6 +1707,7 @@ void rt_render_init(rt_ctx* c) {
         c->fused_blocks = lo(c->fused_blocks, cap);
         c->fused_shade_blocks = lo(c->fused_shade_blocks, cap);
         c->frame_blocks = lo(c->frame_blocks, cap);
+        c->frame_push_blocks = lo(c->frame_push_blocks, cap);
         c->shadow_blocks = lo(c->shadow_blocks, cap);
         c->path_blocks = lo(c->path_blocks, cap);
     }
@@ -1742,9 +1800,6 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         fa.y.done = c->d_fsync.p;
         fa.y.zero_words = zero_next;
         fa.y.n_zero_words = (uint32_t)(sizeof(FrameKernelCounters) / sizeof(uint32_t));
-        if (!fa.phase1_only) c->fsync_target[0] += (uint32_t)c->frame_blocks;
-        if (pushing) { c->fsync_target[1] += (uint32_t)c->frame_blocks; c->fsync_target[2] += (uint32_t)c->frame_blocks; }
-        for (int k = 0; k < 3; k++) fa.y.target[k] = c->fsync_target[k];
         if (p->flags & RT_FLAG_WARP_TIMES) {
             c->d_warp_times.reserve(8 * (size_t)c->frame_blocks * (TRAV_TPB / 32));
             RT_CUDA(cudaMemsetAsync(c->d_warp_times.p, 0, 8 * (size_t)c->frame_blocks * (TRAV_TPB / 32) * sizeof(unsigned long long), st));
@@ -1754,13 +1809,31 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         if (pushing) {
             fa.y.sync = c->push.world > 1 ? (uint32_t*)c->push.sync : nullptr;
             fa.y.frame = c->push.frame_index; fa.y.rank = (uint32_t)c->push.rank; fa.y.world = (uint32_t)c->push.world;
-            fa.push.packed = (const uint8_t*)rgb_dev;
-            fa.push.frame = (uint8_t*)c->push.frame;
-            fa.push.tiles_total = (uint32_t)c->layout.tiles_x * (uint32_t)c->layout.tiles_y;
-            fa.push.wide16 = (f.W * 3) % 16 == 0 && (f.tile_w * 3) % 16 == 0 && ((uintptr_t)rgb_dev & 15) == 0 &&
-                             ((uintptr_t)c->push.frame & 15) == 0;
         }
-        {
+        if (pushing && c->push_inline) {
+            // stores spread over the frame: every finished 8x4 block goes straight into the shared frame
+            fa.t.direct_rgb = (uint8_t*)c->push.frame;
+            fa.t.direct_packed = 0;
+            fa.t.remote_out = 1;
+            fa.t.refill_min = 32;
+            fa.t.qout = queue_of(c, 1);
+            fa.t.next = waves_dev;                 // (bounce-free: nothing is ever appended)
+            fa.t.max_depth = p->max_depth;
+            c->fsync_target[2] += (uint32_t)c->frame_push_blocks;
+            fa.y.target[2] = c->fsync_target[2];
+            if (count) k_frame_push<true><<<c->frame_push_blocks, TRAV_TPB, 0, st>>>(fa);
+            else k_frame_push<false><<<c->frame_push_blocks, TRAV_TPB, 0, st>>>(fa);
+        } else {
+            if (pushing) {
+                fa.push.packed = (const uint8_t*)rgb_dev;
+                fa.push.frame = (uint8_t*)c->push.frame;
+                fa.push.tiles_total = (uint32_t)c->layout.tiles_x * (uint32_t)c->layout.tiles_y;
+                fa.push.wide16 = (f.W * 3) % 16 == 0 && (f.tile_w * 3) % 16 == 0 && ((uintptr_t)rgb_dev & 15) == 0 &&
+                                 ((uintptr_t)c->push.frame & 15) == 0;
+            }
+            if (!fa.phase1_only) c->fsync_target[0] += (uint32_t)c->frame_blocks;
+            if (pushing) { c->fsync_target[1] += (uint32_t)c->frame_blocks; c->fsync_target[2] += (uint32_t)c->frame_blocks; }
+            for (int k = 0; k < 3; k++) fa.y.target[k] = c->fsync_target[k];
             // the phases are separated by barriers over CTAs: a cooperative launch guarantees that all of them are resident
             void* kargs[] = {(void*)&fa};
             const void* fn = count ? (const void*)k_frame<true> : (const void*)k_frame<false>;

@@ -111,6 +111,7 @@ struct rt_ctx {
     uint32_t mg_frame = 0;                 // frames rendered through the multi-device path (handshake slot counter)
     cudaEvent_t mg_ev[2] = {};
     std::vector<void*> host_registered;    // caller buffers page-locked on first use by rt_render_enqueue (unregistered at destroy)
+    std::vector<void*> host_checked;       // destinations whose memory kind has been looked up already
     cudaStream_t copy_stream = nullptr;    // frame -> host copies of this rank (its own PCIe link), overlapping the next frame
     DevBuf<uint8_t> d_packed;              // this rank's tiles back to back (scenes with bounces: resolve target before the push)
     // A frame every rank can store into: for n > 1 a virtual address range whose granules are physically spread
@@ -130,6 +131,7 @@ struct rt_ctx {
         bool in_flight = false;
     };
     FrameSlot slots[2];
+    bool pipelined = false;                // rt_render_enqueue has been used: keep both slots allocated
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
     int sm_count = 148;
@@ -201,7 +203,8 @@ struct rt_ctx {
                                            // 1 when that kernel also pushes finished tiles to a remote frame, 2 always
     bool remote_output = false;            // rt_render_push: the frame being rendered into sits in another GPU's memory
     int frame_kernel = 2;                  // whole bounce-free frames in one k_frame launch (RT_FRAME_KERNEL): 0 never, 1 when pushed to a shared frame, 2 always
-    int frame_blocks = 0;
+    int frame_blocks = 0, frame_push_blocks = 0;
+    int push_inline = 1;                   // multi-GPU bounce-free frames: finished 8x4 blocks go straight into the shared frame (k_frame_push) instead of a push phase at the end (RT_PUSH_INLINE)
     DevBuf<uint32_t> d_fsync;              // k_frame's phase counters
     uint32_t fsync_target[3] = {0, 0, 0};  // where the cumulative barrier counters stand after the launch being built (wrap)
     DevBuf<FrameKernelCounters> d_fk;      // k_frame's double-buffered counters

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 VARIANTS = [
     {"RT_FRAME_KERNEL": "0"},
     {"RT_FRAME_KERNEL": "2"},
-    {"RT_FRAME_KERNEL": "2", "RT_FK_SPLIT": "1"},
+    {"RT_FRAME_KERNEL": "2", "RT_PUSH_INLINE": "0"},
 ]
 
 
@@ -100,10 +100,10 @@ def child():
         raw = ctx.warp_times(1 << 17).astype(np.int64)
         ph = raw.reshape(-1)[: (raw.size // 8) * 8].reshape(-1, 8)
         ph = ph[ph[:, 0] > 0]
-        t0 = ph[:, 0].min()
+        t0 = ph[:, 0].min() if len(ph) else 0
         out["w8_push_phase_us"] = {name: {q: round(float(np.percentile((ph[:, kk] - t0) / 1e3, q)), 1) for q in (0, 50, 99, 100)}
                                    for kk, name in enumerate(["start", "traced", "barrier1", "shaded", "barrier2", "pushed", "exit"])
-                                   if (ph[:, kk] > 0).any()}
+                                   if len(ph) and (ph[:, kk] > 0).any()}
     print(json.dumps(out), flush=True)
     ctx.close()
 
