@@ -470,6 +470,30 @@ def measure_gpu(args, workload, steps, warmup, dist_ctx, main_leg):
                 frame_check = {"error": repr(e)}
         barrier()
 
+    # ---- N > 1 diagnostics (RT_BENCH_PHASES=1, with RT_PUSH_INLINE=0): per-rank phase times of k_frame inside a frame
+    if world > 1 and assemble == "p2p" and not cursor_ptr and os.environ.get("RT_BENCH_PHASES"):
+        pp = api.Context._params(depth, tile=tile, rank=rank, world=world, flags=api.FLAG_PACKED_TILES | api.FLAG_WARP_TIMES)
+        rows = []
+        for f_ in range(6):
+            k = frame_no[0]
+            frame_no[0] += 1
+            flush.fill_(f_ & 0xff)
+            align_ranks()
+            ctx.render_push(cam, pp, packed.data_ptr(), frame_ptr, sync_ptr, k)
+            barrier()
+            ctx.synchronize()
+            raw = ctx.warp_times(1 << 17).astype(np.int64)
+            ph = raw.reshape(-1)[: (raw.size // 8) * 8].reshape(-1, 8)
+            ph = ph[ph[:, 0] > 0]
+            if len(ph):
+                t0_ = ph[:, 0].min()
+                rows.append([float((ph[:, kk].max() - t0_) / 1e3) if (ph[:, kk] > 0).any() else 0.0 for kk in range(7)] +
+                            [float(np.median(ph[:, 1] - t0_) / 1e3)])
+        if rows:
+            r_ = np.median(np.array(rows[1:]), axis=0)
+            print(f"[phases rank {rank}] traced p50 {r_[7]:.1f} last {r_[1]:.1f} | barrier1 (inline push: frame open) {r_[2]:.1f} | shaded {r_[3]:.1f} | barrier2 {r_[4]:.1f} | "
+                  f"pushed {r_[5]:.1f} | exit {r_[6]:.1f} us", file=sys.stderr, flush=True)
+
     # ---- work counts + per-kernel times of this rank's share (roofline inputs)
     cnt = share_stats(api.FLAG_COUNT_WORK)
     share = [share_stats() for _ in range(5)]

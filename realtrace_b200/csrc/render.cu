@@ -832,9 +832,10 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(c
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
+        // frame open?  one CTA asks rank 0 over NVLink, BEFORE it joins the barrier: the others learn it from the barrier
+        if (blockIdx.x == 0 && a.y.sync && a.y.rank != 0) spin_until_ge(a.y.sync + 64, a.y.frame, a.t.sticky, 100);
         atomicAdd(a.y.done + 1, 1u);
         spin_until_reached(a.y.done + 1, a.y.target[1], a.t.sticky, 200);
-        if (a.y.sync && a.y.rank != 0) spin_until_ge(a.y.sync + 64, a.y.frame, a.t.sticky, 200);   // frame open?
         __threadfence();
     }
     __syncthreads();
@@ -923,6 +924,14 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(c
 template <bool COUNT>
 __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame_push(const __grid_constant__ FrameArgs a) {
     __shared__ float s_pdir[3 * TRAV_TPB];
+    auto stamp = [&](int k) {
+        if (a.phase_times && (threadIdx.x & 31) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.phase_times[8 * (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + k] = t;
+        }
+    };
+    stamp(0);
     if (blockIdx.x == 0 && threadIdx.x < a.y.n_zero_words) a.y.zero_words[threadIdx.x] = 0u;   // next frame's counters
     if (a.y.sync && a.y.world > 1) {
         if (a.y.rank == 0) {
@@ -932,14 +941,25 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame_p
                 __threadfence_system();
             }
         } else {
+            // ONE thread of the rank polls rank 0's flag over NVLink and republishes it in local memory, where the other
+            // CTAs wait for it (thousands of remote pollers cost 20 us at the start of every frame)
             if (threadIdx.x == 0) {
-                spin_until_ge(a.y.sync + 64, a.y.frame, a.t.sticky, 200);
-                __threadfence_system();
+                if (blockIdx.x == 0) {
+                    spin_until_ge(a.y.sync + 64, a.y.frame, a.t.sticky, 100);
+                    __threadfence_system();
+                    *(volatile uint32_t*)(a.y.done + 3) = a.y.frame + 1u;
+                    __threadfence();
+                } else {
+                    spin_until_reached(a.y.done + 3, a.y.frame + 1u, a.t.sticky, 100);
+                    __threadfence();
+                }
             }
             __syncthreads();
         }
     }
+    stamp(2);
     traverse_body<MODE_PRIMARY, COUNT, true, 0, true>(a.t, s_pdir);
+    stamp(1);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -958,6 +978,7 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame_p
             }
         }
     }
+    stamp(6);
 }
 
 // ---- k_paths: every bounce generation in ONE launch --------------------------------------------------
