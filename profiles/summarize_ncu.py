@@ -27,7 +27,10 @@ with open(os.path.join(here, f"{tag}_launches.md"), "w") as f:
 if rep == "-":
     print(open(os.path.join(here, f"{tag}_launches.md")).read()); sys.exit(0)
 # ---- full capture -> key metrics + DRAM traffic
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# (a .ncu-rep, or the `ncu -i rep --page raw --csv` dump of one made on the GPU box: the reports themselves are too
+# large to bring back)
+raw = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]; idx = {x: i for i, x in enumerate(hdr)}
 keep = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
@@ -36,7 +39,7 @@ keep = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
@@ -59,13 +62,17 @@ with open(os.path.join(here, f"{tag}_ncu_full.md"), "w") as f:
         for k in keep:
             if k in idx: f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
         f.write("\n")
-        if any(k in name for k in FRAME_KERNELS) and "smsp__inst_executed.sum" in idx:
+        # the first launch of each frame kernel is the whole 1-GPU frame (tests/gpu_profile_r2.py profiles a rank's
+        # share of an 8-GPU frame afterwards: same kernels again, or k_frame_push)
+        short_name = name.split("(")[0]
+        if any(k in name for k in FRAME_KERNELS) and "k_frame_push" not in name and short_name not in counts["kernels"] \
+                and "smsp__inst_executed.sum" in idx:
             counts["inst_executed"] += float(r[idx["smsp__inst_executed.sum"]].replace(",", ""))
-            if "lts__t_bytes.sum" in idx:
-                counts["lts_bytes"] += mb(r[idx["lts__t_bytes.sum"]], units[idx["lts__t_bytes.sum"]])
+            if "lts__t_sectors.sum" in idx:
+                counts["lts_bytes"] += 32.0 * float(r[idx["lts__t_sectors.sum"]].replace(",", ""))
             counts["dram_bytes"] += mb(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + \
                                     mb(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
-            counts["kernels"].append(name.split("(")[0][-60:])
+            counts["kernels"].append(short_name)
         short = "k_traverse<primary>" if "k_traverse<0" in name else "k_traverse<queue>" if "k_traverse<1" in name else \
                 "k_traverse<shadow>" if "k_traverse<2" in name else \
                 "k_shade" if "k_shade" in name else "k_resolve" if "k_resolve" in name else name.split("(")[0].split("::")[-1]

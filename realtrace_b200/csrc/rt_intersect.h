@@ -22,8 +22,11 @@ RT_HD bool accept_t(float par, float& tcur) {
 //   beta*A  = det(a-o, e2, d)         = s  . c,  s = a - o
 //   gamma*A = det(e1, s, d)           = d  . q,  q = e1 x s
 //   t*A     = det(e1, e2, s)          = -(e2 . q)
-// Returns 0 = barycentric test failed, 1 = inside but t rejected, 2 = accepted (tcur/beta/gamma updated).
-RT_HD int tri_test(f3 a, f3 e1, f3 e2, f3 o, f3 d, float& tcur, float& beta, float& gamma) {
+// Returns 0 = barycentric test failed, 1 = inside but t rejected, 2 = accepted (tcur/beta/gamma updated),
+// 3 = inside and EXACTLY as far as the current hit (tie_bg, if given, receives this triangle's beta/gamma): the
+// caller breaks the tie by the lower object index — the order in which the reference's linear loop meets them
+// (world.cpp:7-14 keeps the first of two equal t), and independent of the order a traversal visits them in.
+RT_HD int tri_test(f3 a, f3 e1, f3 e2, f3 o, f3 d, float& tcur, float& beta, float& gamma, float* tie_bg = nullptr) {
     float cx = e2.y * d.z - d.y * e2.z;
     float cy = e2.x * d.z - d.x * e2.z;
     float cz = e2.x * d.y - d.x * e2.y;
@@ -39,7 +42,10 @@ RT_HD int tri_test(f3 a, f3 e1, f3 e2, f3 o, f3 d, float& tcur, float& beta, flo
     if (!(b > 0.0f && g > 0.0f && b + g < aa)) return 0;
     float inv = rt_rcp(A);
     float t = -dot(e2, q) * inv;
-    if (!accept_t(t, tcur)) return 1;
+    if (!accept_t(t, tcur)) {
+        if (t == tcur && t > RT_SMALLEST_DIST && tie_bg) { tie_bg[0] = bA * inv; tie_bg[1] = gA * inv; return 3; }
+        return 1;
+    }
     beta = bA * inv;
     gamma = gA * inv;
     return 2;

@@ -52,10 +52,20 @@ RT_HD bool leaf_test(const SceneDev& s, int code, const RayPrep& r, HitRec& hit,
         const float4* rec = s.tris + 3 * (size_t)(first + k);
         float4 r0 = ldg(rec), r1 = ldg(rec + 1), r2 = ldg(rec + 2);
         if (wc) wc->tris++;
-        if (tri_test(mk3(r0), mk3(r1), mk3(r2), r.o, r.d, hit.t, hit.beta, hit.gamma) == 2) {
+        float tie[2];
+        int rc = tri_test(mk3(r0), mk3(r1), mk3(r2), r.o, r.d, hit.t, hit.beta, hit.gamma, tie);
+        if (rc == 2) {
             hit.prim = (int)(first + k);
             found = true;
             if (any_hit) return true;
+        } else if (rc == 3 && !any_hit && hit.prim >= 0 && hit.prim != (int)(first + k)) {
+            // two triangles at exactly the same distance: the one that comes first in the object list wins, whatever
+            // order the walk (or several lanes sharing one ray's walk) met them in
+            if (as_uint(r0.w) < as_uint(ldg(s.tris + 3 * (size_t)hit.prim).w)) {
+                hit.prim = (int)(first + k);
+                hit.beta = tie[0];
+                hit.gamma = tie[1];
+            }
         }
     }
     return found;
@@ -147,10 +157,18 @@ RT_HD bool brute_walk(const SceneDev& s, const RayPrep& r, HitRec& hit, WorkCoun
         const float4* rec = s.tris + 3 * (size_t)i;
         float4 r0 = ldg(rec), r1 = ldg(rec + 1), r2 = ldg(rec + 2);
         if (wc) wc->tris++;
-        if (tri_test(mk3(r0), mk3(r1), mk3(r2), r.o, r.d, hit.t, hit.beta, hit.gamma) == 2) {
+        float tie[2];
+        int rc = tri_test(mk3(r0), mk3(r1), mk3(r2), r.o, r.d, hit.t, hit.beta, hit.gamma, tie);
+        if (rc == 2) {
             hit.prim = i;
             found = true;
             if (ANY_HIT) return true;
+        } else if (rc == 3 && !ANY_HIT && hit.prim >= 0 && hit.prim != i) {
+            if (as_uint(r0.w) < as_uint(ldg(s.tris + 3 * (size_t)hit.prim).w)) {
+                hit.prim = i;
+                hit.beta = tie[0];
+                hit.gamma = tie[1];
+            }
         }
     }
     return found;

@@ -11,9 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    {"RT_FRAME_KERNEL": "0"},
-    {"RT_FRAME_KERNEL": "2"},
-    {"RT_FRAME_KERNEL": "2", "RT_PUSH_INLINE": "0"},
+    {"RT_TAIL_SPLIT": "0"},
+    {"RT_TAIL_SPLIT": "1"},
 ]
 
 
@@ -53,7 +52,7 @@ def child():
         flush.fill_(1)
         st = ctx.render_device(cam, depth, buf.data_ptr(), tile=tile, rank=0, world=world, flags=fl | api.FLAG_WARP_TIMES)
         raw = ctx.warp_times(1 << 17).astype(np.int64)
-        if os.environ.get("RT_FRAME_KERNEL") == "2":
+        if os.environ.get("RT_FRAME_KERNEL", "2") == "2":
             ph = raw.reshape(-1)[: (raw.size // 8) * 8].reshape(-1, 8)
             ph = ph[ph[:, 0] > 0]
             t0 = ph[:, 0].min()
@@ -91,7 +90,7 @@ def child():
     ctx.synchronize()
     t = np.array([a.elapsed_time(b) for a, b in evs])
     out["w8_push_cold_ms"] = [round(float(np.median(t)), 4), round(float(t.min()), 4)]
-    if os.environ.get("RT_FRAME_KERNEL") == "2":
+    if os.environ.get("RT_FRAME_KERNEL", "2") == "2":
         flush.fill_(3)
         ctx.peer_sync(sync_ptr, 0, world, k, 0)
         params.flags |= api.FLAG_WARP_TIMES
