@@ -565,7 +565,9 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
             } else {
                 // "if-if": every lane advances one step of whatever kind per iteration, for a bounded
                 // number of iterations before the warp looks at its refill state again
-                for (int it = 0; it < a.loop_style && node != RT_DONE; it++) {
+                // (tail splitting: short bursts, so that idle lanes get a chance to take work every few steps)
+                const int burst_len = (SPLIT && exhausted && a.tail_split) ? a.tail_split : a.loop_style;
+                for (int it = 0; it < burst_len && node != RT_DONE; it++) {
                     if (rt_is_internal(node)) {
                         if (COUNT) wcp->nodes++;
                         node = WIDE == 1

@@ -389,76 +389,92 @@ void init_material_from_obj(Material* m) {                                      
     m->ka = 0.2; m->kd = 0.9; m->ks = 0.4; m->kr = 0.4; m->kt = 0.0; m->eta = 3.0; m->n = 128;
 }
 
+// load_image_from_obj (lumina.cpp:195-290), restated line by line of the OBJ file: `v` records scaled by 15 (:43, :275),
+// `vt` keeps two components, `f` reads its first three corners `v[/vt[/vn]]`, at most max_faces faces are kept (:266),
+// a textured face gets a BarycentricMaterial from the three fetched texels, any other face the loader's default
+// material (:163-172).  For the well-formed files the reference ships, reading by lines and reading by tokens (what
+// the reference does) see the same records.
 void load_image_from_obj(World* world, std::string file_name, std::string texture_file_name, std::string, int max_faces,
                          int texel_mode) {
-    std::ifstream is(file_name);
-    if (!is.is_open()) throw std::runtime_error("load_image_from_obj: could not open " + file_name);   // lumina.cpp:197-200 exits
+    std::ifstream obj(file_name);
+    if (!obj.is_open()) throw std::runtime_error("load_image_from_obj: could not open " + file_name);   // lumina.cpp:197-200 exits
     Image tex;
-    bool has_texture = false;
-    if (!texture_file_name.empty()) {
-        if (!read_png(texture_file_name, tex)) throw std::runtime_error("load_image_from_obj: cannot decode " + texture_file_name);
-        has_texture = true;
-    }
-    const double SCALING_FACTOR = 15;                                                       // lumina.cpp:43
-    std::vector<Vector3D> vertices;
-    std::vector<std::pair<double, double>> texture_vertices;
-    std::vector<Triangle*> all_triangles;
-    std::string c;
-    double v[3];
-    while (is >> c) {                                                                       // lumina.cpp:234-287
-        if (c == "f") {
-            std::vector<int> idx[3];
-            std::string data, token;
-            for (int i = 0; i < 3; i++) {
-                is >> data;
-                std::stringstream ss(data);
-                while (getline(ss, token, '/')) idx[i].push_back(token.empty() ? 0 : stoi(token));
+    const bool use_texture = !texture_file_name.empty();
+    if (use_texture && !read_png(texture_file_name, tex))
+        throw std::runtime_error("load_image_from_obj: cannot decode " + texture_file_name);
+    const double scale = 15.0;                                                              // SCALING_FACTOR, lumina.cpp:43
+    std::vector<Vector3D> pos;
+    std::vector<std::pair<double, double>> uv;
+    std::vector<Triangle*> kept;
+
+    struct Corner { int v = 0, vt = 0; bool has_vt = false; };
+    auto parse_corner = [](const std::string& word) {
+        Corner c;
+        size_t s1 = word.find('/');
+        c.v = std::stoi(word.substr(0, s1));
+        if (s1 != std::string::npos) {
+            size_t s2 = word.find('/', s1 + 1);
+            std::string mid = word.substr(s1 + 1, s2 == std::string::npos ? std::string::npos : s2 - s1 - 1);
+            if (!mid.empty()) { c.vt = std::stoi(mid); c.has_vt = true; }
+        }
+        return c;
+    };
+    auto fetch = [&](int vt_index) {
+        if (texel_mode == RT_TEXEL_LITERAL) {
+            // texture_vertices[idx] without the -1 (lumina.cpp:249); one past the end is UB there, the error colour here
+            size_t k = (size_t)vt_index;
+            if (k >= uv.size()) return Color(0.8, 0.1, 0.0);
+            return texel_literal(tex, uv[k].first, uv[k].second);
+        }
+        return texel(tex, uv[vt_index - 1].first, uv[vt_index - 1].second);
+    };
+
+    std::string line;
+    while (std::getline(obj, line)) {
+        std::istringstream in(line);
+        std::string kind;
+        if (!(in >> kind)) continue;
+        if (kind == "v") {
+            double x = 0, y = 0, z = 0;
+            in >> x >> y >> z;
+            pos.push_back(Vector3D(x * scale, y * scale, z * scale));
+        } else if (kind == "vt") {
+            double u = 0, v = 0;
+            in >> u >> v;
+            uv.push_back(std::make_pair(u, v));
+        } else if (kind == "f") {
+            Corner c[3];
+            std::string word;
+            for (int k = 0; k < 3; k++) {
+                if (!(in >> word)) throw std::runtime_error("load_image_from_obj: face with fewer than three corners");
+                c[k] = parse_corner(word);
             }
-            if (max_faces >= 0 && (int)all_triangles.size() >= max_faces) continue;          // lumina.cpp:266
-            for (int i = 0; i < 3; i++)
-                if (idx[i].empty() || idx[i][0] < 1 || (size_t)idx[i][0] > vertices.size())
-                    throw std::runtime_error("load_image_from_obj: face refers to vertex " + std::to_string(idx[i].empty() ? 0 : idx[i][0]) +
-                                             " of " + std::to_string(vertices.size()) + " (negative/relative indices are not supported)");
-            const Vector3D &a = vertices[idx[0][0] - 1], &b = vertices[idx[1][0] - 1], &cc = vertices[idx[2][0] - 1];
+            if (max_faces >= 0 && (int)kept.size() >= max_faces) continue;                   // lumina.cpp:266
+            for (int k = 0; k < 3; k++)
+                if (c[k].v < 1 || (size_t)c[k].v > pos.size())
+                    throw std::runtime_error("load_image_from_obj: face refers to vertex " + std::to_string(c[k].v) + " of " +
+                                             std::to_string(pos.size()) + " (negative/relative indices are not supported)");
+            const Vector3D &p0 = pos[c[0].v - 1], &p1 = pos[c[1].v - 1], &p2 = pos[c[2].v - 1];
             Material* m;
-            bool textured = has_texture && idx[0].size() >= 2 && idx[1].size() >= 2 && idx[2].size() >= 2 &&
-                            idx[0][1] != 0 && idx[1][1] != 0 && idx[2][1] != 0;       // `f v//vn` carries no vt
-            if (textured) {
-                for (int i = 0; i < 3; i++)
-                    if (idx[i][1] < 1 || (size_t)idx[i][1] > texture_vertices.size())
-                        throw std::runtime_error("load_image_from_obj: face refers to texture vertex " + std::to_string(idx[i][1]) +
-                                                 " of " + std::to_string(texture_vertices.size()));
-                auto tv = [&](int k) {
-                    if (texel_mode == RT_TEXEL_LITERAL) {
-                        // texture_vertices[idx] without the -1 (lumina.cpp:249); one past the end is UB there, the error colour here
-                        size_t ti = (size_t)idx[k][1];
-                        if (ti >= texture_vertices.size()) return Color(0.8, 0.1, 0.0);
-                        return texel_literal(tex, texture_vertices[ti].first, texture_vertices[ti].second);
-                    }
-                    const auto& p = texture_vertices[idx[k][1] - 1];
-                    return texel(tex, p.first, p.second);
-                };
-                m = new BarycentricMaterial(world, a, b, cc, tv(0), tv(1), tv(2));
+            if (use_texture && c[0].has_vt && c[1].has_vt && c[2].has_vt) {
+                for (int k = 0; k < 3; k++)
+                    if (c[k].vt < 1 || (size_t)c[k].vt > uv.size())
+                        throw std::runtime_error("load_image_from_obj: face refers to texture vertex " + std::to_string(c[k].vt) +
+                                                 " of " + std::to_string(uv.size()));
+                m = new BarycentricMaterial(world, p0, p1, p2, fetch(c[0].vt), fetch(c[1].vt), fetch(c[2].vt));
                 // the textured workloads keep the loader's coefficients so that depth > 0 has mirror bounces
                 m->ka = 0.2; m->kd = 0.9; m->ks = 0.4; m->kr = 0.4; m->kt = 0.0; m->eta = 3.0;
             } else {
                 m = new Material(world);
                 init_material_from_obj(m);
             }
-            Triangle* t = new Triangle(a, b, cc, m);
-            all_triangles.push_back(t);
+            Triangle* t = new Triangle(p0, p1, p2, m);
+            kept.push_back(t);
             world->addObject(t);
-        } else if (c == "v") {
-            is >> v[0] >> v[1] >> v[2];
-            vertices.push_back(Vector3D(v[0] * SCALING_FACTOR, v[1] * SCALING_FACTOR, v[2] * SCALING_FACTOR));
-        } else if (c == "vt") {
-            is >> v[0] >> v[1];
-            texture_vertices.push_back(std::make_pair(v[0], v[1]));
-        } else {
-            getline(is, c);
         }
+        // every other record kind (vn, comments, groups, materials) is skipped like lumina.cpp:282-286 does
     }
-    world->uniform_grid = UniformGrid(all_triangles);                                       // lumina.cpp:289 (a no-op shim here)
+    world->uniform_grid = UniformGrid(kept);                                                // lumina.cpp:289 (a no-op shim here)
 }
 
 // ---- image output (lumina.cpp:424-439) ---------------------------------------------------------------

@@ -12,7 +12,10 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     {"RT_TAIL_SPLIT": "0"},
-    {"RT_TAIL_SPLIT": "1"},
+    {"RT_TAIL_SPLIT": "2"},
+    {"RT_TAIL_SPLIT": "4"},
+    {"RT_TAIL_SPLIT": "8"},
+    {"RT_TAIL_SPLIT": "16"},
 ]
 
 
