@@ -72,7 +72,6 @@ static rt_ctx* make_ctx(int device) {
         env_int("RT_FUSE_SHADE", 0, 2, c->fuse_shade);
         env_int("RT_FRAME_KERNEL", 0, 2, c->frame_kernel);
         env_int("RT_PUSH_INLINE", 0, 1, c->push_inline);
-        env_int("RT_TAIL_SPLIT", 0, 64, c->tail_split);
         env_int("RT_TILE_BUCKET_BITS", 0, 8, c->tile_bucket_bits);
         env_int("RT_PATH_KERNEL", 0, 1, c->path_kernel);
         env_int("RT_TILE_FEEDBACK", 0, 1, c->tile_feedback);

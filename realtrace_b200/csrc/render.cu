@@ -187,7 +187,6 @@ struct TravArgs {
     WaveCounters* next;       // SHADE: their counter
     int max_depth;            // SHADE
     int remote_out;           // SHADE: direct_rgb is another GPU's frame (informational: same code path)
-    int tail_split;           // fused primary wave: once the cursor is empty, idle lanes take subtrees off busy lanes' stacks
 };
 
 // Appends the bounce rays of this warp's shaded hits to the next wave's queue: exclusive prefix over the
@@ -330,11 +329,6 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
     bool pending = false, qfull = false;   // SHADE: this lane's hit waits for the end of the batch
     uint32_t px_rgb = 0;                   // SHADE, RGB8 output: the lane's finished pixel, stored with its 8x4 block
     bool px_have = false;
-    // tail splitting (see below): owner = lane whose ray this lane is walking; helping = it is somebody else's ray;
-    // outstanding = lanes currently walking subtrees of THIS lane's ray
-    constexpr bool SPLIT = FUSE && MODE == MODE_PRIMARY && !COUNT;
-    int owner = lane, outstanding = 0;
-    bool helping = false;
     auto start_shadow = [&](int li) {
         f3 toL = mk3(__ldg(a.s.lights + 2 * li)) - P;
         f3 sd = normalize(toL);
@@ -472,71 +466,6 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
                 }
             }
         }
-        // ---- tail splitting.  When the cursor is empty the warp's last batch is a few long rays and many idle lanes, and
-        // the frame ends when the longest CHAIN of dependent node fetches ends (profiles/r1_tuning.md 15).  An idle lane
-        // then takes the top entry off a busy lane's traversal stack and walks that subtree with a copy of the ray
-        // (same query: nearest hit bounded by the owner's current t, or the owner's shadow ray); when it is done its
-        // result is merged into the owner (min t, ties by object order; any-hit: or), which finishes its ray only once
-        // nobody is walking for it any more.  Speculative (a subtree may turn out to lie behind the final hit) but
-        // exact: every subtree the sequential walk would have entered is entered by somebody with a bound that is no
-        // tighter than the sequential one.
-        if (SPLIT && exhausted && steal_done && a.tail_split) {
-            // (1) helpers that ran out of nodes report to their owners
-            uint32_t hm = __ballot_sync(FULL, active && helping && node == RT_DONE);
-            while (hm) {
-                int src = __ffs(hm) - 1;
-                hm &= hm - 1;
-                int ow = __shfl_sync(FULL, owner, src);
-                float ht = __shfl_sync(FULL, hit.t, src), hb = __shfl_sync(FULL, hit.beta, src), hg = __shfl_sync(FULL, hit.gamma, src);
-                int hp = __shfl_sync(FULL, hit.prim, src);
-                int hf = __shfl_sync(FULL, found ? 1 : 0, src);
-                if (lane == ow) {
-                    outstanding--;
-                    if (hf) {
-                        if (phase >= 0) {
-                            found = true;                                   // any hit occludes: the owner's own walk is moot
-                            node = RT_DONE;
-                            sp = 0;
-                        } else {
-                            bool better = ht < hit.t;
-                            if (ht == hit.t && hp >= 0 && hit.prim >= 0 && hp != hit.prim)
-                                better = __float_as_uint(__ldg(a.s.tris + 3 * (size_t)hp).w) < __float_as_uint(__ldg(a.s.tris + 3 * (size_t)hit.prim).w);
-                            if (better || !found) { hit.t = ht; hit.prim = hp; hit.beta = hb; hit.gamma = hg; }
-                            found = true;
-                        }
-                    }
-                }
-                if (lane == src) { active = false; helping = false; owner = lane; }
-            }
-            // (2) idle lanes take work: the k-th idle lane from the k-th lane that has something on its stack
-            uint32_t idle = __ballot_sync(FULL, !active);
-            uint32_t busy = __ballot_sync(FULL, active && node != RT_DONE && sp > 0);
-            while (idle && busy) {
-                int dst = __ffs(idle) - 1, src = __ffs(busy) - 1;
-                idle &= idle - 1;
-                busy &= busy - 1;
-                int e = 0;
-                if (lane == src) e = stack[--sp];
-                e = __shfl_sync(FULL, e, src);
-                int ow = __shfl_sync(FULL, owner, src);
-                int ph = __shfl_sync(FULL, phase, src);
-                float bt = __shfl_sync(FULL, hit.t, src);
-                f3 so = mk3(__shfl_sync(FULL, r.o.x, src), __shfl_sync(FULL, r.o.y, src), __shfl_sync(FULL, r.o.z, src));
-                f3 sd = mk3(__shfl_sync(FULL, r.d.x, src), __shfl_sync(FULL, r.d.y, src), __shfl_sync(FULL, r.d.z, src));
-                if (lane == ow) outstanding++;
-                if (lane == dst) {
-                    r = prep_ray(so, sd);
-                    hit.t = bt; hit.prim = RT_MISS; hit.beta = hit.gamma = 0.0f;
-                    found = false;
-                    phase = ph;
-                    owner = ow;
-                    helping = true;
-                    active = true;
-                    sp = 0;
-                    node = e;
-                }
-            }
-        }
         if (!__any_sync(FULL, active)) {
             if (exhausted && steal_done) {
                 if (MODE == MODE_PRIMARY) finish_batch();      // a last batch that lies outside the frame
@@ -565,9 +494,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
             } else {
                 // "if-if": every lane advances one step of whatever kind per iteration, for a bounded
                 // number of iterations before the warp looks at its refill state again
-                // (tail splitting: short bursts, so that idle lanes get a chance to take work every few steps)
-                const int burst_len = (SPLIT && exhausted && a.tail_split) ? a.tail_split : a.loop_style;
-                for (int it = 0; it < burst_len && node != RT_DONE; it++) {
+                for (int it = 0; it < a.loop_style && node != RT_DONE; it++) {
                     if (rt_is_internal(node)) {
                         if (COUNT) wcp->nodes++;
                         node = WIDE == 1
@@ -585,7 +512,6 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
         }
         // ---- rays that ran out of nodes: linear primitives, then the result
         bool fin = active && node == RT_DONE;
-        if (SPLIT) fin = fin && !helping && outstanding == 0;      // helpers report at the top of the loop; owners wait for them
         bool emit = false;
         if (fin) {
             bool finite = r.d.x == r.d.x && r.d.y == r.d.y && r.d.z == r.d.z;
@@ -1878,7 +1804,6 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         ta.direct_packed = sa.direct_packed = (p->flags & RT_FLAG_PACKED_TILES) ? 1 : 0;
     }
     ta.remote_out = (c->remote_output && direct) ? 1 : 0;
-    ta.tail_split = c->tail_split;
     uint32_t launches = 0;
     if (use_fk) {
         // the whole frame in one launch: trace + shadow rays, shade, (push + handshake)

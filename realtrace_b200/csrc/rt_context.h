@@ -204,7 +204,6 @@ struct rt_ctx {
     bool remote_output = false;            // rt_render_push: the frame being rendered into sits in another GPU's memory
     int frame_kernel = 2;                  // whole bounce-free frames in one k_frame launch (RT_FRAME_KERNEL): 0 never, 1 when pushed to a shared frame, 2 always
     int frame_blocks = 0, frame_push_blocks = 0;
-    int tail_split = 4;                    // idle lanes share the traversal stacks of the last rays of a frame; the value is the number of steps between two hand-overs, 0 = off (RT_TAIL_SPLIT)
     int push_inline = 1;                   // multi-GPU bounce-free frames: finished 8x4 blocks go straight into the shared frame (k_frame_push) instead of a push phase at the end (RT_PUSH_INLINE)
     DevBuf<uint32_t> d_fsync;              // k_frame's phase counters
     uint32_t fsync_target[3] = {0, 0, 0};  // where the cumulative barrier counters stand after the launch being built (wrap)

@@ -11,11 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    {"RT_TAIL_SPLIT": "0"},
-    {"RT_TAIL_SPLIT": "2"},
-    {"RT_TAIL_SPLIT": "4"},
-    {"RT_TAIL_SPLIT": "8"},
-    {"RT_TAIL_SPLIT": "16"},
+    {"RT_FRAME_KERNEL": "0"},
+    {"RT_FRAME_KERNEL": "2"},
 ]
 
 
