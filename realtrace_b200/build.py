@@ -32,6 +32,16 @@ def build_all(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """An A/B build of the CUDA library with extra -D flags (tuning runs: RT_LIB_PATH selects it in the Python
+    harness).  Not part of build_all(); the shipped library is the one without extra flags."""
+    out = os.path.join(HERE, f"librt_variant_{name}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return out
+
+
 def build_host(force=False):
     """The C++ mirror of the reference's scene API (realtrace_b200/host) + its demo driver."""
     host = os.path.join(HERE, "host")

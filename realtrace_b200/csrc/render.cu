@@ -33,8 +33,80 @@
 namespace {
 
 constexpr int TRAV_TPB = 128;
+// The traversal stack of a lane in the persistent kernels (RT_STACK_KIND, compile time):
+//   0  per-thread array (local memory: STL/LDL through L1, up to 32 different lines per warp access)
+//   1  the same with the top entry cached in a register (a pop's load leaves the dependent chain)
+//   2  the first RT_SMEM_STACK entries in shared memory, laid out [entry][thread] so that a warp's access is free of
+//      bank conflicts whatever each lane's depth, deeper entries in local memory
+//   3  2 + the top entry in a register
+#ifndef RT_STACK_KIND
+#define RT_STACK_KIND 0
+#endif
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 16
+#endif
 // min CTAs/SM in __launch_bounds__ measured: 10 (48 regs) = no bound (55 regs, 9 CTAs/SM); 12 and 16 spill and lose 15-50 %
 constexpr int SHADE_TPB = 128;
+
+// Scalars and pointers only (the arrays are declared next to it by RT_LANE_STACK_DECL): a struct that also held the
+// array would be placed in local memory as a whole, `sp` included.
+struct LaneStack {
+    int* e;                                    // local-memory entries (kinds 2/3: the entries beyond RT_SMEM_STACK)
+    int* sm;                                   // kinds 2/3: this thread's column of the CTA's shared block
+    int sp;
+    int top;                                   // kinds 1/3: entry sp-1; memory holds entries 0 .. sp-2
+#if RT_STACK_KIND >= 2
+    __device__ __forceinline__ int ld(int i) const { return i < RT_SMEM_STACK ? sm[i * TRAV_TPB] : e[i - RT_SMEM_STACK]; }
+    __device__ __forceinline__ void st(int i, int v) {
+        if (i < RT_SMEM_STACK) sm[i * TRAV_TPB] = v;
+        else e[i - RT_SMEM_STACK] = v;
+    }
+#else
+    __device__ __forceinline__ int ld(int i) const { return e[i]; }
+    __device__ __forceinline__ void st(int i, int v) { e[i] = v; }
+#endif
+#if RT_STACK_KIND & 1
+    __device__ __forceinline__ bool push(int v) {
+        if (sp >= RT_STACK_SIZE) return false;
+        if (sp > 0) st(sp - 1, top);
+        top = v;
+        sp++;
+        return true;
+    }
+    __device__ __forceinline__ int pop() {
+        int v = top;
+        if (--sp > 0) top = ld(sp - 1);
+        return v;
+    }
+#else
+    __device__ __forceinline__ bool push(int v) {
+        if (sp >= RT_STACK_SIZE) return false;
+        st(sp++, v);
+        return true;
+    }
+    __device__ __forceinline__ int pop() { return ld(--sp); }
+#endif
+    __device__ __forceinline__ void clear() { sp = 0; }
+    __device__ __forceinline__ bool empty() const { return sp == 0; }
+};
+#if RT_STACK_KIND >= 2
+#define RT_LANE_STACK_DECL(stk)                                   \
+    __shared__ int s_lane_stack[RT_SMEM_STACK * TRAV_TPB];        \
+    int lane_stack_mem[RT_STACK_SIZE - RT_SMEM_STACK];            \
+    LaneStack stk;                                                \
+    stk.e = lane_stack_mem;                                       \
+    stk.sm = s_lane_stack + threadIdx.x;                          \
+    stk.sp = 0;                                                   \
+    stk.top = 0
+#else
+#define RT_LANE_STACK_DECL(stk)                                   \
+    int lane_stack_mem[RT_STACK_SIZE];                            \
+    LaneStack stk;                                                \
+    stk.e = lane_stack_mem;                                       \
+    stk.sm = nullptr;                                             \
+    stk.sp = 0;                                                   \
+    stk.top = 0
+#endif
 
 enum { MODE_PRIMARY = 0, MODE_QUEUE = 1, MODE_SHADOW = 2 };
 #define RT_STEAL_RUN 1        // 8x4-pixel blocks claimed per system-scope atomic.  Measured at 2 GPUs: runs of 4 lengthen
@@ -307,8 +379,8 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
     // per-lane ray state
     RayPrep r;
     HitRec hit;
-    int stack[RT_STACK_SIZE];
-    int node = RT_DONE, sp = 0;
+    RT_LANE_STACK_DECL(stk);
+    int node = RT_DONE;
     bool active = false, found = false, exhausted = false, overflow = false;
     bool steal_done = !(MODE == MODE_PRIMARY && a.f.steal_cursor != nullptr && a.f.n_pool_blocks > 0);
     uint32_t steal_left = 0, steal_slot = 0;
@@ -335,7 +407,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
         r = prep_ray(fma3(toL, 0.01f, P), sd);                 // world.cpp:45
         hit.t = RT_FLT_MAX; hit.prim = RT_MISS;
         found = false;
-        sp = 0;
+        stk.clear();
         node = (use_bvh && sd.x == sd.x && sd.y == sd.y && sd.z == sd.z) ? 0 : RT_DONE;
         traced_shadow++;
     };
@@ -457,7 +529,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
                     found = false;
                     active = true;
                     phase = -1;
-                    sp = 0;
+                    stk.clear();
                                 // a NaN direction (ignored refract() failure, world.cpp:83) misses everything
                     bool finite = d.x == d.x && d.y == d.y && d.z == d.z;
                     r = prep_ray(o, d);
@@ -481,33 +553,22 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
                 while (rt_is_internal(node)) {
                     if (COUNT) wcp->nodes++;
                     node = WIDE == 1
-                               ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
-                               : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
+                               ? bvh4_node_step(a.s, r, hit.t, node, stk, &overflow)
+                               : bvh_node_step(a.s, r, hit.t, node, stk, &overflow);
                 }
                 while (node < 0) {
                     if (leaf_test(a.s, node, r, hit, any, wcp)) {
                         found = true;
                         if (any) { node = RT_DONE; break; }
                     }
-                    node = sp ? stack[--sp] : RT_DONE;
+                    node = stk.empty() ? RT_DONE : stk.pop();
                 }
             } else {
                 // "if-if": every lane advances one step of whatever kind per iteration, for a bounded
                 // number of iterations before the warp looks at its refill state again
-                for (int it = 0; it < a.loop_style && node != RT_DONE; it++) {
-                    if (rt_is_internal(node)) {
-                        if (COUNT) wcp->nodes++;
-                        node = WIDE == 1
-                                   ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
-                                   : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
-                    } else {
-                        if (leaf_test(a.s, node, r, hit, any, wcp)) {
-                            found = true;
-                            if (any) { node = RT_DONE; break; }
-                        }
-                        node = sp ? stack[--sp] : RT_DONE;
-                    }
-                }
+                for (int it = 0; it < a.loop_style && node != RT_DONE; it++)
+                    node = WIDE == 1 ? bvh4_step_unified(a.s, r, hit, node, stk, any, found, &overflow, wcp)
+                                     : bvh_step_unified(a.s, r, hit, node, stk, any, found, &overflow, wcp);
             }
         }
         // ---- rays that ran out of nodes: linear primitives, then the result
@@ -1020,9 +1081,9 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
 
     RayPrep r;
     HitRec hit, nh;
-    int stack[RT_STACK_SIZE];
+    RT_LANE_STACK_DECL(stk);
     float4 pend[3 * RT_PATH_STACK];           // parked rays: (o, pix) (d, level) (w, -)
-    int node = RT_DONE, sp = 0, psp = 0;
+    int node = RT_DONE, psp = 0;
     bool active = false, found = false, exhausted = false, overflow = false, pend_overflow = false;
     int phase = -1;                           // < 0 nearest-hit query, li >= 0 shadow ray of light li
     f3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 1), w = mk3(1, 1, 1), P = mk3(0, 0, 0);
@@ -1039,7 +1100,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
         hit.t = RT_FLT_MAX; hit.prim = RT_MISS; hit.beta = hit.gamma = 0.0f;
         found = false;
         phase = -1;
-        sp = 0;
+        stk.clear();
         node = (use_bvh && finite) ? 0 : RT_DONE;
         active = true;
         n_secondary++;
@@ -1050,7 +1111,7 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
         r = prep_ray(fma3(toL, 0.01f, P), sd);
         hit.t = RT_FLT_MAX; hit.prim = RT_MISS;
         found = false;
-        sp = 0;
+        stk.clear();
         node = (use_bvh && sd.x == sd.x && sd.y == sd.y && sd.z == sd.z) ? 0 : RT_DONE;
         n_shadow++;
     };
@@ -1092,19 +1153,9 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
         const bool any = phase >= 0;
         WorkCount* wcp = COUNT ? (any ? &wcs : &wc) : nullptr;
         if (active) {
-            for (int it = 0; it < burst && node != RT_DONE; it++) {
-                if (rt_is_internal(node)) {
-                    if (COUNT) wcp->nodes++;
-                    node = WIDE ? bvh4_node_step(a.s, r, hit.t, node, stack, sp, &overflow)
-                                 : bvh_node_step(a.s, r, hit.t, node, stack, sp, &overflow);
-                } else {
-                    if (leaf_test(a.s, node, r, hit, any, wcp)) {
-                        found = true;
-                        if (any) { node = RT_DONE; break; }
-                    }
-                    node = sp ? stack[--sp] : RT_DONE;
-                }
-            }
+            for (int it = 0; it < burst && node != RT_DONE; it++)
+                node = WIDE ? bvh4_step_unified(a.s, r, hit, node, stk, any, found, &overflow, wcp)
+                            : bvh_step_unified(a.s, r, hit, node, stk, any, found, &overflow, wcp);
         }
         if (active && node == RT_DONE) {
             bool finite = r.d.x == r.d.x && r.d.y == r.d.y && r.d.z == r.d.z;

@@ -71,14 +71,31 @@ RT_HD bool leaf_test(const SceneDev& s, int code, const RayPrep& r, HitRec& hit,
     return found;
 }
 
+// Traversal stacks.  The step functions below take any type with clear() / empty() / push(v) -> false when full /
+// pop() (needs !empty()); the persistent kernels bring their own (render.cu: LaneStack), everything else uses this.
+struct StackView {             // over an array and a depth the caller owns (kept apart: a struct holding the array would
+                               // be placed in local memory as a whole on the device, the depth included)
+    int* e;
+    int& sp;
+    RT_HD StackView(int* e_, int& sp_) : e(e_), sp(sp_) {}
+    RT_HD void clear() { sp = 0; }
+    RT_HD bool empty() const { return sp == 0; }
+    RT_HD bool push(int v) {
+        if (sp >= RT_STACK_SIZE) return false;
+        e[sp++] = v;
+        return true;
+    }
+    RT_HD int pop() { return e[--sp]; }
+};
+
 // Traversal state codes: 0 <= node < RT_DONE is an internal node, node < 0 a leaf, RT_DONE = finished.
 #define RT_DONE 0x7fffffff
 RT_HD bool rt_is_internal(int node) { return (unsigned)node < (unsigned)RT_DONE; }
 
 // One internal-node step: tests both child boxes against [0, tmax] and returns where to go next —
 // the nearer hit child (the farther one is pushed), the only hit child, or the popped stack top.
-RT_HD int bvh_node_step(const SceneDev& s, const RayPrep& r, float tmax, int node, int* stack, int& sp,
-                        bool* overflow) {
+template <class STK>
+RT_HD int bvh_node_step(const SceneDev& s, const RayPrep& r, float tmax, int node, STK& stk, bool* overflow) {
     const float4* n = s.nodes + RT_NODE_FLOAT4S * (size_t)node;
     float4 n0 = ldg(n), n1 = ldg(n + 1), n2 = ldg(n + 2), n3 = ldg(n + 3);
     float t0, t1;
@@ -87,13 +104,65 @@ RT_HD int bvh_node_step(const SceneDev& s, const RayPrep& r, float tmax, int nod
     int c0 = (int)as_uint(n3.x), c1 = (int)as_uint(n3.y);
     if (h0 && h1) {
         if (t1 < t0) { int tmp = c0; c0 = c1; c1 = tmp; }
-        if (sp < RT_STACK_SIZE) stack[sp++] = c1;
-        else if (overflow) *overflow = true;
+        if (!stk.push(c1) && overflow) *overflow = true;
         return c0;
     }
     if (h0) return c0;
     if (h1) return c1;
-    return sp ? stack[--sp] : RT_DONE;
+    return stk.empty() ? RT_DONE : stk.pop();
+}
+
+// One step of the "if-if" walk with ONE fetch for both kinds of step.  In a warp whose lanes disagree (some at an internal
+// node, some at a leaf) the separate functions above run one after the other and each waits for its own loads; here the
+// three float4 loads every lane needs — the two child boxes of a node, or the 48-byte record of a leaf's first triangle —
+// are issued together from an address chosen per lane, so a diverged iteration waits for memory once instead of twice.
+// Same arithmetic, same order of tests, same results as bvh_node_step / leaf_test.
+template <class STK>
+RT_HD int bvh_step_unified(const SceneDev& s, const RayPrep& r, HitRec& hit, int node, STK& stk, bool any_hit, bool& found,
+                           bool* overflow, WorkCount* wc) {
+    const bool internal = rt_is_internal(node);
+    const uint32_t first = rt_leaf_first(node);
+    const float4* p = internal ? s.nodes + RT_NODE_FLOAT4S * (size_t)node : s.tris + 3 * (size_t)first;
+    const float4 q0 = ldg(p), q1 = ldg(p + 1), q2 = ldg(p + 2);
+    if (internal) {
+        if (wc) wc->nodes++;
+        const float4 q3 = ldg(p + 3);
+        float t0, t1;
+        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, r, hit.t, t0);
+        bool h1 = slab(q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, r, hit.t, t1);
+        int c0 = (int)as_uint(q3.x), c1 = (int)as_uint(q3.y);
+        if (h0 && h1) {
+            if (t1 < t0) { int tmp = c0; c0 = c1; c1 = tmp; }
+            if (!stk.push(c1) && overflow) *overflow = true;
+            return c0;
+        }
+        if (h0) return c0;
+        if (h1) return c1;
+        return stk.empty() ? RT_DONE : stk.pop();
+    }
+    // leaf: the first triangle from the registers, any further ones (RT_LEAF_SIZE > 1) fetched one by one
+    const uint32_t count = rt_leaf_count(node);
+    float4 r0 = q0, r1 = q1, r2 = q2;
+    for (uint32_t k = 0;;) {
+        if (wc) wc->tris++;
+        float tie[2];
+        int rc = tri_test(mk3(r0), mk3(r1), mk3(r2), r.o, r.d, hit.t, hit.beta, hit.gamma, tie);
+        if (rc == 2) {
+            hit.prim = (int)(first + k);
+            found = true;
+            if (any_hit) return RT_DONE;
+        } else if (rc == 3 && !any_hit && hit.prim >= 0 && hit.prim != (int)(first + k)) {
+            if (as_uint(r0.w) < as_uint(ldg(s.tris + 3 * (size_t)hit.prim).w)) {
+                hit.prim = (int)(first + k);
+                hit.beta = tie[0];
+                hit.gamma = tie[1];
+            }
+        }
+        if (++k >= count) break;
+        const float4* rec = s.tris + 3 * (size_t)(first + k);
+        r0 = ldg(rec); r1 = ldg(rec + 1); r2 = ldg(rec + 2);
+    }
+    return stk.empty() ? RT_DONE : stk.pop();
 }
 
 // The same step on the 4-wide view: four slab tests per fetch, hit children visited nearest first (the
@@ -102,8 +171,8 @@ RT_HD int bvh_node_step(const SceneDev& s, const RayPrep& r, float tmax, int nod
 RT_HD void sort2(float& ta, int& ca, float& tb, int& cb) {
     if (tb < ta) { float t = ta; ta = tb; tb = t; int c = ca; ca = cb; cb = c; }
 }
-RT_HD int bvh4_node_step(const SceneDev& s, const RayPrep& r, float tmax, int node, int* stack, int& sp,
-                         bool* overflow) {
+template <class STK>
+RT_HD int bvh4_node_step(const SceneDev& s, const RayPrep& r, float tmax, int node, STK& stk, bool* overflow) {
     const float4* n = s.nodes4 + RT_NODE4_FLOAT4S * (size_t)node;
     float4 lx = ldg(n), hx = ldg(n + 1), ly = ldg(n + 2), hy = ldg(n + 3), lz = ldg(n + 4), hz = ldg(n + 5), cd = ldg(n + 6);
     const float inf = RT_FLT_MAX;
@@ -115,36 +184,87 @@ RT_HD int bvh4_node_step(const SceneDev& s, const RayPrep& r, float tmax, int no
     int c0 = (int)as_uint(cd.x), c1 = (int)as_uint(cd.y), c2 = (int)as_uint(cd.z), c3 = (int)as_uint(cd.w);
     // 5-comparator network: ascending entry distance, misses (inf) last
     sort2(t0, c0, t1, c1); sort2(t2, c2, t3, c3); sort2(t0, c0, t2, c2); sort2(t1, c1, t3, c3); sort2(t1, c1, t2, c2);
-    if (t0 == inf) return sp ? stack[--sp] : RT_DONE;
-    if (t3 != inf) { if (sp < RT_STACK_SIZE) stack[sp++] = c3; else if (overflow) *overflow = true; }
-    if (t2 != inf) { if (sp < RT_STACK_SIZE) stack[sp++] = c2; else if (overflow) *overflow = true; }
-    if (t1 != inf) { if (sp < RT_STACK_SIZE) stack[sp++] = c1; else if (overflow) *overflow = true; }
+    if (t0 == inf) return stk.empty() ? RT_DONE : stk.pop();
+    if (t3 != inf) { if (!stk.push(c3) && overflow) *overflow = true; }
+    if (t2 != inf) { if (!stk.push(c2) && overflow) *overflow = true; }
+    if (t1 != inf) { if (!stk.push(c1) && overflow) *overflow = true; }
     return c0;
 }
 
+// The node steps over a caller-owned array (the CPU emulation's loop models keep their stacks that way).
+RT_HD int bvh_node_step(const SceneDev& s, const RayPrep& r, float tmax, int node, int* stack, int& sp, bool* overflow) {
+    StackView v(stack, sp);
+    return bvh_node_step(s, r, tmax, node, v, overflow);
+}
+RT_HD int bvh4_node_step(const SceneDev& s, const RayPrep& r, float tmax, int node, int* stack, int& sp, bool* overflow) {
+    StackView v(stack, sp);
+    return bvh4_node_step(s, r, tmax, node, v, overflow);
+}
+
+// The unified step on the 4-wide view: the first three float4 of the wide node (lo.x, hi.x, lo.y of the four children) or
+// the leaf's triangle record come from one fetch; a node lane then adds its other four float4.
+template <class STK>
+RT_HD int bvh4_step_unified(const SceneDev& s, const RayPrep& r, HitRec& hit, int node, STK& stk, bool any_hit, bool& found,
+                            bool* overflow, WorkCount* wc) {
+    const bool internal = rt_is_internal(node);
+    const uint32_t first = rt_leaf_first(node);
+    const float4* p = internal ? s.nodes4 + RT_NODE4_FLOAT4S * (size_t)node : s.tris + 3 * (size_t)first;
+    const float4 q0 = ldg(p), q1 = ldg(p + 1), q2 = ldg(p + 2);
+    if (internal) {
+        if (wc) wc->nodes++;
+        const float4 lx = q0, hx = q1, ly = q2, hy = ldg(p + 3), lz = ldg(p + 4), hz = ldg(p + 5), cd = ldg(p + 6);
+        const float inf = RT_FLT_MAX;
+        float t0, t1, t2, t3;
+        if (!slab(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, r, hit.t, t0)) t0 = inf;
+        if (!slab(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, r, hit.t, t1)) t1 = inf;
+        if (!slab(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, r, hit.t, t2)) t2 = inf;
+        if (!slab(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, r, hit.t, t3)) t3 = inf;
+        int c0 = (int)as_uint(cd.x), c1 = (int)as_uint(cd.y), c2 = (int)as_uint(cd.z), c3 = (int)as_uint(cd.w);
+        sort2(t0, c0, t1, c1); sort2(t2, c2, t3, c3); sort2(t0, c0, t2, c2); sort2(t1, c1, t3, c3); sort2(t1, c1, t2, c2);
+        if (t0 == inf) return stk.empty() ? RT_DONE : stk.pop();
+        if (t3 != inf) { if (!stk.push(c3) && overflow) *overflow = true; }
+        if (t2 != inf) { if (!stk.push(c2) && overflow) *overflow = true; }
+        if (t1 != inf) { if (!stk.push(c1) && overflow) *overflow = true; }
+        return c0;
+    }
+    const uint32_t count = rt_leaf_count(node);
+    float4 r0 = q0, r1 = q1, r2 = q2;
+    for (uint32_t k = 0;;) {
+        if (wc) wc->tris++;
+        float tie[2];
+        int rc = tri_test(mk3(r0), mk3(r1), mk3(r2), r.o, r.d, hit.t, hit.beta, hit.gamma, tie);
+        if (rc == 2) {
+            hit.prim = (int)(first + k);
+            found = true;
+            if (any_hit) return RT_DONE;
+        } else if (rc == 3 && !any_hit && hit.prim >= 0 && hit.prim != (int)(first + k)) {
+            if (as_uint(r0.w) < as_uint(ldg(s.tris + 3 * (size_t)hit.prim).w)) {
+                hit.prim = (int)(first + k);
+                hit.beta = tie[0];
+                hit.gamma = tie[1];
+            }
+        }
+        if (++k >= count) break;
+        const float4* rec = s.tris + 3 * (size_t)(first + k);
+        r0 = ldg(rec); r1 = ldg(rec + 1); r2 = ldg(rec + 2);
+    }
+    return stk.empty() ? RT_DONE : stk.pop();
+}
+
 // hit.t must hold the current upper bound (RT_FLT_MAX for a fresh ray), hit.prim = RT_MISS.
-// "while-while" order: descend internal nodes until a leaf is reached, then test leaves until the
-// stack yields an internal node again, so that in a warp the two phases run with many lanes each.
 template <bool ANY_HIT>
 RT_HD bool bvh_walk(const SceneDev& s, const RayPrep& r, HitRec& hit, WorkCount* wc, bool* overflow) {
     if (s.n_bvh_tris <= 0) return false;
-    int stack[RT_STACK_SIZE];
-    int sp = 0;
+    int entries[RT_STACK_SIZE];
+    int depth = 0;
+    StackView stk(entries, depth);
     int node = 0;
     bool found = false;
-    while (node != RT_DONE) {
-        while (rt_is_internal(node)) {
-            if (wc) wc->nodes++;
-            node = s.nodes4 ? bvh4_node_step(s, r, hit.t, node, stack, sp, overflow)
-                            : bvh_node_step(s, r, hit.t, node, stack, sp, overflow);
-        }
-        while (node < 0) {
-            if (leaf_test(s, node, r, hit, ANY_HIT, wc)) {
-                found = true;
-                if (ANY_HIT) return true;
-            }
-            node = sp ? stack[--sp] : RT_DONE;
-        }
+    // the steps the persistent kernels run (one fetch per step for node and leaf alike)
+    if (!s.nodes4) {
+        while (node != RT_DONE) node = bvh_step_unified(s, r, hit, node, stk, ANY_HIT, found, overflow, wc);
+    } else {
+        while (node != RT_DONE) node = bvh4_step_unified(s, r, hit, node, stk, ANY_HIT, found, overflow, wc);
     }
     return found;
 }

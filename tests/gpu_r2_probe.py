@@ -10,10 +10,17 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = [
-    {"RT_FRAME_KERNEL": "0"},
-    {"RT_FRAME_KERNEL": "2"},
-]
+# PROBE_LIBS: comma list of A/B builds ("" = the shipped library, "s1" = librt_variant_s1.so ...; build.build_variant),
+# PROBE_WORKLOADS: comma list of workloads; every pair runs in its own process
+LIBS = os.environ.get("PROBE_LIBS", "").split(",")
+WORKLOADS = os.environ.get("PROBE_WORKLOADS", "synth1m").split(",")
+VARIANTS = []
+for _w in WORKLOADS:
+    for _l in LIBS:
+        _v = {"PROBE_WORKLOAD": _w}
+        if _l:
+            _v["RT_LIB_PATH"] = os.path.join(ROOT, "realtrace_b200", f"librt_variant_{_l}.so")
+        VARIANTS.append(_v)
 
 
 def child():
@@ -29,7 +36,7 @@ def child():
     ctx.set_stream(stream.cuda_stream or 1)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     W, H = cam.width, cam.height
-    out = {"env": {k: v for k, v in os.environ.items() if k.startswith("RT_")}, "workload": name}
+    out = {"env": {k: os.path.basename(v) for k, v in os.environ.items() if k.startswith("RT_")}, "workload": name}
     for world, tile in ((1, (0, 0)), (8, (32, 16))):
         _, owned, tb = api.tile_layout(W, H, tile[0], tile[1], 0, world)
         buf = torch.zeros(max(owned * tb, W * H * 3), dtype=torch.uint8, device="cuda")
