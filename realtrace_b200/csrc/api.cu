@@ -79,6 +79,7 @@ static rt_ctx* make_ctx(int device) {
         env_int("RT_LOOP_PRIMARY", 0, 1024, c->loop_primary);
         env_int("RT_LOOP_QUEUE", 0, 1024, c->loop_queue);
         env_int("RT_LOOP_SHADOW", 0, 1024, c->loop_shadow);
+        if (const char* e = getenv("RT_DENSE_MIN_PIXELS")) c->dense_min_pixels = atoll(e);
         rt_render_init(c);
     } catch (...) {
         delete c;

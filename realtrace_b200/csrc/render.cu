@@ -116,6 +116,8 @@ struct CamDev {
     double pos[3], u[3], v[3], w[3];
     double focal, aspect;
     int W, H;
+    const float* xw;      // per column / per row window coordinates (k_camera_tables): they depend on the frame size and
+    const float* yw;      // the aspect only, so the two FP64 divisions of camera.cpp:36-37 leave the per-pixel path
 };
 
 struct FrameDev {
@@ -171,16 +173,24 @@ __device__ __forceinline__ size_t pixel_byte_offset(const FrameDev& f, int i, in
 // Camera::get_ray_direction (camera.cpp:33-44) + the Ray constructor's normalisation (ray.h:25-29),
 // evaluated in FP64 like the reference and rounded once to FP32.
 __device__ __forceinline__ void primary_ray(const CamDev& c, int i, int j, f3& o, f3& d) {
-    float xw = (float)(c.aspect * (i - c.W / 2.0 + 0.5) / c.W);
-    float yw = (float)((j - c.H / 2.0 + 0.5) / c.H);
+    float xw = __ldg(c.xw + i);
+    float yw = __ldg(c.yw + j);
     double dx = -c.w[0] * c.focal + c.u[0] * (double)xw + c.v[0] * (double)yw;
     double dy = -c.w[1] * c.focal + c.u[1] * (double)xw + c.v[1] * (double)yw;
     double dz = -c.w[2] * c.focal + c.u[2] * (double)xw + c.v[2] * (double)yw;
     // get_ray_direction normalises and Ray's constructor normalises again; the second pass moves the
     // FP64 value by <= 1 ulp, far below the final rounding to FP32, so one reciprocal length is used
-    double inv = 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+    double inv = rsqrt(dx * dx + dy * dy + dz * dz);
     d = mk3((float)(dx * inv), (float)(dy * inv), (float)(dz * inv));
     o = mk3((float)c.pos[0], (float)c.pos[1], (float)c.pos[2]);
+}
+
+// xw[i] = (float)(aspect (i - W/2 + 0.5) / W), yw[j] = (float)((j - H/2 + 0.5) / H): camera.cpp:36-37 in FP64 with the
+// reference's conversion to float; rebuilt only when the frame size or the aspect changes.
+__global__ void k_camera_tables(float* __restrict__ xw, float* __restrict__ yw, int W, int H, double aspect) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < W) xw[k] = (float)(aspect * (k - W / 2.0 + 0.5) / W);
+    else if (k < W + H) yw[k - W] = (float)((k - W - H / 2.0 + 0.5) / H);
 }
 
 // Color::clamp + Camera::drawPixel (color.cpp:19-28, camera.cpp:46-52): truncating 8-bit conversion of
@@ -350,6 +360,9 @@ __device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uin
 // hit and occlusion bits until the warp's 32-pixel batch is done, then the warp shades all its hits together
 // (World::shade_ray, world.cpp:32-111, same shade_hit as k_shade), writes the pixels and queues the bounce
 // rays.  One kernel per primary wave: no hit queue traffic, no second launch, no second tail.
+#ifndef RT_DENSE_MIN_BLOCKS
+#define RT_DENSE_MIN_BLOCKS 9           // k_frame / k_frame_push for large shares: 56 registers, 9 CTAs per SM
+#endif
 #ifndef RT_SHADE_FUSED_MIN_BLOCKS
 #define RT_SHADE_FUSED_MIN_BLOCKS 7     // SHADE: hold the kernel to the traversal loop's 72 registers (the once-per-batch shading spills)
 #endif
@@ -827,8 +840,12 @@ __device__ __forceinline__ void spin_until_reached(const uint32_t* p, uint32_t t
     }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(const __grid_constant__ FrameArgs a) {
+// MINB: resident CTAs per SM the register budget is held to.  RT_SHADE_FUSED_MIN_BLOCKS (7 -> 72 registers) gives the
+// fastest single warp and with it the shortest tail: right for a rank's share of a multi-GPU frame.  RT_DENSE_MIN_BLOCKS
+// (9 -> 56 registers, cold per-lane state spilled, the hot loop unchanged) gives 29 % more warps per SM: the bulk of a
+// large frame runs 6.5 % faster, the stragglers 15 % slower.  The host picks by the pixels this launch owns.
+template <bool COUNT, int MINB = RT_SHADE_FUSED_MIN_BLOCKS>
+__global__ void __launch_bounds__(TRAV_TPB, MINB) k_frame(const __grid_constant__ FrameArgs a) {
     // (nothing is kept live across phase 1 that phase 1 does not need: its loop sits exactly at the register budget)
     auto stamp = [&](int k) {
         if (a.phase_times && (threadIdx.x & 31) == 0) {
@@ -982,8 +999,8 @@ __global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame(c
 //           fence and signals rank 0's arrival slot — on rank 0 it waits for the other ranks' arrivals instead, so the
 //           end of rank 0's launch IS the completion of the frame.  No handshake kernels, no collective, no barrier
 //           inside the grid (an ordinary launch).
-template <bool COUNT>
-__global__ void __launch_bounds__(TRAV_TPB, RT_SHADE_FUSED_MIN_BLOCKS) k_frame_push(const __grid_constant__ FrameArgs a) {
+template <bool COUNT, int MINB = RT_SHADE_FUSED_MIN_BLOCKS>
+__global__ void __launch_bounds__(TRAV_TPB, MINB) k_frame_push(const __grid_constant__ FrameArgs a) {
     __shared__ float s_pdir[3 * TRAV_TPB];
     auto stamp = [&](int k) {
         if (a.phase_times && (threadIdx.x & 31) == 0) {
@@ -1437,13 +1454,24 @@ __global__ void __launch_bounds__(256) k_assemble16(const uint8_t* __restrict__ 
     }
 }
 
-CamDev make_cam(const rt_camera* c) {
+CamDev make_cam(rt_ctx* ctx, const rt_camera* c) {
     CamDev d;
     for (int k = 0; k < 3; k++) { d.pos[k] = c->pos[k]; d.u[k] = c->u[k]; d.v[k] = c->v[k]; d.w[k] = c->w[k]; }
     d.focal = c->focal_distance;
     d.aspect = c->aspect;
     d.W = c->width;
     d.H = c->height;
+    const int W = c->width > 0 ? c->width : 0, H = c->height > 0 ? c->height : 0;
+    if (ctx->cam_tab_W != W || ctx->cam_tab_H != H || ctx->cam_tab_aspect != c->aspect || !ctx->d_cam_tab.p) {
+        ctx->d_cam_tab.reserve((size_t)W + H + 1);
+        if (W + H > 0) {
+            k_camera_tables<<<(W + H + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_cam_tab.p, ctx->d_cam_tab.p + W, W, H, c->aspect);
+            RT_CUDA(cudaGetLastError());
+        }
+        ctx->cam_tab_W = W; ctx->cam_tab_H = H; ctx->cam_tab_aspect = c->aspect;
+    }
+    d.xw = ctx->d_cam_tab.p;
+    d.yw = ctx->d_cam_tab.p + W;
     return d;
 }
 
@@ -1769,6 +1797,8 @@ void rt_render_init(rt_ctx* c) {
                          persistent_blocks(k_shade<false>, SHADE_TPB, c->sm_count));
     c->frame_blocks = persistent_blocks(k_frame<false>, TRAV_TPB, c->sm_count);
     c->frame_push_blocks = persistent_blocks(k_frame_push<false>, TRAV_TPB, c->sm_count);
+    c->frame_blocks_dense = persistent_blocks(k_frame<false, RT_DENSE_MIN_BLOCKS>, TRAV_TPB, c->sm_count);
+    c->frame_push_blocks_dense = persistent_blocks(k_frame_push<false, RT_DENSE_MIN_BLOCKS>, TRAV_TPB, c->sm_count);
     c->d_fsync.reserve(4);
     RT_CUDA(cudaMemset(c->d_fsync.p, 0, 4 * sizeof(uint32_t)));
     c->d_fk.reserve(2);
@@ -1780,6 +1810,8 @@ void rt_render_init(rt_ctx* c) {
         c->fused_shade_blocks = lo(c->fused_shade_blocks, cap);
         c->frame_blocks = lo(c->frame_blocks, cap);
         c->frame_push_blocks = lo(c->frame_push_blocks, cap);
+        c->frame_blocks_dense = lo(c->frame_blocks_dense, cap);
+        c->frame_push_blocks_dense = lo(c->frame_push_blocks_dense, cap);
         c->shadow_blocks = lo(c->shadow_blocks, cap);
         c->path_blocks = lo(c->path_blocks, cap);
     }
@@ -1830,7 +1862,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
 
     TravArgs ta;
     memset(&ta, 0, sizeof ta);
-    ta.s = c->scene; ta.cam = make_cam(cam); ta.f = f;
+    ta.s = c->scene; ta.cam = make_cam(c, cam); ta.f = f;
     ta.accum = c->d_accum.p; ta.fc = frame_dev_ctr; ta.sticky = c->d_sticky.p;
     ta.aux_prim = aux_dev ? aux_dev->prim_id : nullptr;
     ta.aux_t = aux_dev ? aux_dev->t : nullptr;
@@ -1872,9 +1904,14 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         fa.y.done = c->d_fsync.p;
         fa.y.zero_words = zero_next;
         fa.y.n_zero_words = (uint32_t)(sizeof(FrameKernelCounters) / sizeof(uint32_t));
+        // large shares run the 9-CTAs-per-SM build of the kernel, small ones the 7-CTA build (see k_frame)
+        const bool dense = (long long)f.n_local_pix >= c->dense_min_pixels;
+        const int fk_blocks = dense ? c->frame_blocks_dense : c->frame_blocks;
+        const int fkp_blocks = dense ? c->frame_push_blocks_dense : c->frame_push_blocks;
         if (p->flags & RT_FLAG_WARP_TIMES) {
-            c->d_warp_times.reserve(8 * (size_t)c->frame_blocks * (TRAV_TPB / 32));
-            RT_CUDA(cudaMemsetAsync(c->d_warp_times.p, 0, 8 * (size_t)c->frame_blocks * (TRAV_TPB / 32) * sizeof(unsigned long long), st));
+            const size_t nw = 8 * (size_t)(fk_blocks > fkp_blocks ? fk_blocks : fkp_blocks) * (TRAV_TPB / 32);
+            c->d_warp_times.reserve(nw);
+            RT_CUDA(cudaMemsetAsync(c->d_warp_times.p, 0, nw * sizeof(unsigned long long), st));
             fa.phase_times = c->d_warp_times.p;
             fa.t.warp_times = nullptr;
         }
@@ -1891,10 +1928,15 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
             fa.t.qout = queue_of(c, 1);
             fa.t.next = waves_dev;                 // (bounce-free: nothing is ever appended)
             fa.t.max_depth = p->max_depth;
-            c->fsync_target[2] += (uint32_t)c->frame_push_blocks;
+            c->fsync_target[2] += (uint32_t)fkp_blocks;
             fa.y.target[2] = c->fsync_target[2];
-            if (count) k_frame_push<true><<<c->frame_push_blocks, TRAV_TPB, 0, st>>>(fa);
-            else k_frame_push<false><<<c->frame_push_blocks, TRAV_TPB, 0, st>>>(fa);
+            if (count) {
+                if (dense) k_frame_push<true, RT_DENSE_MIN_BLOCKS><<<fkp_blocks, TRAV_TPB, 0, st>>>(fa);
+                else k_frame_push<true><<<fkp_blocks, TRAV_TPB, 0, st>>>(fa);
+            } else {
+                if (dense) k_frame_push<false, RT_DENSE_MIN_BLOCKS><<<fkp_blocks, TRAV_TPB, 0, st>>>(fa);
+                else k_frame_push<false><<<fkp_blocks, TRAV_TPB, 0, st>>>(fa);
+            }
         } else {
             if (pushing) {
                 fa.push.packed = (const uint8_t*)rgb_dev;
@@ -1903,13 +1945,14 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
                 fa.push.wide16 = (f.W * 3) % 16 == 0 && (f.tile_w * 3) % 16 == 0 && ((uintptr_t)rgb_dev & 15) == 0 &&
                                  ((uintptr_t)c->push.frame & 15) == 0;
             }
-            if (!fa.phase1_only) c->fsync_target[0] += (uint32_t)c->frame_blocks;
-            if (pushing) { c->fsync_target[1] += (uint32_t)c->frame_blocks; c->fsync_target[2] += (uint32_t)c->frame_blocks; }
+            if (!fa.phase1_only) c->fsync_target[0] += (uint32_t)fk_blocks;
+            if (pushing) { c->fsync_target[1] += (uint32_t)fk_blocks; c->fsync_target[2] += (uint32_t)fk_blocks; }
             for (int k = 0; k < 3; k++) fa.y.target[k] = c->fsync_target[k];
             // the phases are separated by barriers over CTAs: a cooperative launch guarantees that all of them are resident
             void* kargs[] = {(void*)&fa};
-            const void* fn = count ? (const void*)k_frame<true> : (const void*)k_frame<false>;
-            RT_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)c->frame_blocks), dim3(TRAV_TPB), kargs, 0, st));
+            const void* fn = dense ? (count ? (const void*)k_frame<true, RT_DENSE_MIN_BLOCKS> : (const void*)k_frame<false, RT_DENSE_MIN_BLOCKS>)
+                                   : (count ? (const void*)k_frame<true> : (const void*)k_frame<false>);
+            RT_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)fk_blocks), dim3(TRAV_TPB), kargs, 0, st));
         }
         RT_CUDA(cudaGetLastError());
         launches++;

@@ -113,6 +113,9 @@ struct rt_ctx {
     std::vector<void*> host_registered;    // caller buffers page-locked on first use by rt_render_enqueue (unregistered at destroy)
     std::vector<void*> host_checked;       // destinations whose memory kind has been looked up already
     cudaStream_t copy_stream = nullptr;    // frame -> host copies of this rank (its own PCIe link), overlapping the next frame
+    DevBuf<float> d_cam_tab;               // window coordinate per column, then per row (k_camera_tables), for the cached size/aspect
+    int cam_tab_W = 0, cam_tab_H = 0;
+    double cam_tab_aspect = 0.0;
     DevBuf<uint8_t> d_packed;              // this rank's tiles back to back (scenes with bounces: resolve target before the push)
     // A frame every rank can store into: for n > 1 a virtual address range whose granules are physically spread
     // round robin over the ranks' GPUs (multi_device.cu), else a plain allocation on this device.
@@ -203,7 +206,8 @@ struct rt_ctx {
                                            // 1 when that kernel also pushes finished tiles to a remote frame, 2 always
     bool remote_output = false;            // rt_render_push: the frame being rendered into sits in another GPU's memory
     int frame_kernel = 2;                  // whole bounce-free frames in one k_frame launch (RT_FRAME_KERNEL): 0 never, 1 when pushed to a shared frame, 2 always
-    int frame_blocks = 0, frame_push_blocks = 0;
+    int frame_blocks = 0, frame_push_blocks = 0, frame_blocks_dense = 0, frame_push_blocks_dense = 0;
+    long long dense_min_pixels = 1500000;  // shares of at least this many pixels run the 9-CTAs-per-SM build of k_frame / k_frame_push (RT_DENSE_MIN_PIXELS)
     int push_inline = 1;                   // multi-GPU bounce-free frames: finished 8x4 blocks go straight into the shared frame (k_frame_push) instead of a push phase at the end (RT_PUSH_INLINE)
     DevBuf<uint32_t> d_fsync;              // k_frame's phase counters
     uint32_t fsync_target[3] = {0, 0, 0};  // where the cumulative barrier counters stand after the launch being built (wrap)
