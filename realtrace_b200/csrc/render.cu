@@ -124,6 +124,7 @@ struct FrameDev {
     int W, H, tile_w, tile_h, tiles_x, tile_pix, world;
     uint32_t n_tiles_owned, n_local_pix;   // the statically owned tiles and their pixel count
     const uint32_t* tile_ids;
+    const uint32_t* tile_ord;              // canonical ordinal of the tile at each position of tile_ids (index into tile_cost)
     // dynamic tile stealing: blocks of 8x4 pixels of the pool tiles, claimed through steal_cursor
     const uint32_t* pool_ids;              // pool tile ids (the same list on every rank)
     uint32_t n_pool_blocks;                // pool tiles * blocks per tile
@@ -438,7 +439,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
         }
         if (batch_tile == 0xffffffffu) return;
         // charge its duration to the tile
-        if (a.f.tile_cost && lane == 0) atomicMax(a.f.tile_cost + batch_tile, (uint32_t)((clock64() - batch_t0) >> 6));
+        if (a.f.tile_cost && lane == 0) atomicMax(a.f.tile_cost + __ldg(a.f.tile_ord + batch_tile), (uint32_t)((clock64() - batch_t0) >> 6));
         batch_tile = 0xffffffffu;
     };
 
@@ -1262,44 +1263,86 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
 // (slowest 32-pixel batch of the tile, descending), so that the LAST batches the persistent warps pick
 // up are cheap ones and the kernel does not end on a long tail of expensive batches.  One CTA, bitonic sort of <= 4096 keys
 // (cost << 32 | tile id) in shared memory.  Only the order of work changes, never a pixel.
-#define RT_SORT_TILES_MAX 4096
-__global__ void __launch_bounds__(1024) k_sort_tiles(uint32_t* __restrict__ tile_ids, uint32_t* __restrict__ cost, uint32_t n,
+#define RT_SORT_TILES_MAX 16384
+#define RT_SORT_CLASSES 256
+// Heavy tiles first: a STABLE counting sort of the owned tiles by cost class, descending; tiles of one class keep their
+// canonical (ascending tile id) order, which is the cache-friendly one.  One CTA, two passes of n / 1024 steps, ~5 us
+// for 2 k tiles (the bitonic sort this replaces took ~50 us and was limited to 4096 tiles).  Launch + run still cost a
+// 1/8 share 9 us, and a fresher order does not help a moving camera (profiles/r2_tuning.md section 14), so the order
+// is renewed every RT_TILE_SORT_EVERY-th frame (8).
+//   cost[o]      slowest batch of the tile with canonical ordinal o in the frame just rendered (cleared here)
+//   class        255 - (distance in cost buckets from the most expensive tile), clamped at 0; a bucket is the exponent
+//                and the top sub_bits mantissa bits of the cost
+//   ids0[o]      the canonical list;  tile_ids[p] / tile_ord[p]: tile and ordinal at position p of the new order
+__global__ void __launch_bounds__(1024) k_sort_tiles(uint32_t* __restrict__ tile_ids, uint32_t* __restrict__ tile_ord,
+                                                     const uint32_t* __restrict__ ids0, uint32_t* __restrict__ cost, uint32_t n,
                                                      int sub_bits) {
-    __shared__ unsigned long long key[RT_SORT_TILES_MAX];
-    uint32_t m = 1;
-    while (m < n) m <<= 1;
-    // key: the cost of the tile's slowest batch rounded to a few mantissa bits, then the tile id DEscending in the low word
-    // (stored inverted), so that tiles of similar cost keep their spatial (cache-friendly) order
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-        unsigned long long k = 0ull;
-        if (i < n) {
-            uint32_t c = cost[i], b = 0;
-            // bucket = exponent and the top sub_bits mantissa bits of the cost (1 bit: half octaves)
-            if (c) { int e = 31 - __clz((int)c); b = ((uint32_t)e << sub_bits) + (e >= sub_bits ? (c >> (e - sub_bits)) & ((1u << sub_bits) - 1u) : 0u) + 1u; }
-            k = ((unsigned long long)b << 32) | (0xffffffffu - tile_ids[i]);
-        }
-        key[i] = k;
+    __shared__ uint8_t cls[RT_SORT_TILES_MAX];
+    __shared__ uint16_t hist[32][RT_SORT_CLASSES];      // per warp: tiles of each class in the warp's range, then offsets
+    __shared__ uint32_t class_base[RT_SORT_CLASSES];
+    __shared__ uint32_t s_max;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto bucket = [&](uint32_t c) -> uint32_t {
+        if (!c) return 0u;
+        int e = 31 - __clz((int)c);
+        return ((uint32_t)e << sub_bits) + (e >= sub_bits ? (c >> (e - sub_bits)) & ((1u << sub_bits) - 1u) : 0u) + 1u;
+    };
+    if (threadIdx.x == 0) s_max = 0;
+    for (uint32_t i = threadIdx.x; i < 32 * RT_SORT_CLASSES; i += blockDim.x) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t bm = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) bm = max(bm, bucket(cost[i]));
+    for (int o = 16; o; o >>= 1) bm = max(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+    if (lane == 0) atomicMax(&s_max, bm);
+    __syncthreads();
+    bm = s_max;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint32_t b = bucket(cost[i]);
+        uint32_t d = bm - b;
+        cls[i] = (uint8_t)(b == 0 || d > 255u ? 0u : 255u - d);
+        cost[i] = 0;
     }
     __syncthreads();
-    for (uint32_t k = 2; k <= m; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                uint32_t l = i ^ j;
-                if (l > i) {
-                    unsigned long long a = key[i], b = key[l];
-                    bool desc = (i & k) == 0;          // descending overall
-                    if (desc ? a < b : a > b) { key[i] = b; key[l] = a; }
-                }
-            }
-            __syncthreads();
+    // every warp owns a contiguous range of ordinals (a multiple of 32 long)
+    const uint32_t per_warp = ((n + 1023u) / 1024u) * 32u;
+    const uint32_t lo = warp * per_warp, hi = min(n, lo + per_warp);
+    for (uint32_t g = lo; g < hi; g += 32) {
+        uint32_t o = g + lane;
+        bool in = o < hi;
+        uint32_t c = in ? cls[o] : 0xffffffffu;
+        uint32_t same = __match_any_sync(0xffffffffu, c);
+        if (in && lane == __ffs(same) - 1) hist[warp][c] += (uint16_t)__popc(same);
+        __syncwarp();
+    }
+    __syncthreads();
+    // offsets: classes descending, inside a class warps ascending
+    if (threadIdx.x < RT_SORT_CLASSES) {
+        uint32_t c = threadIdx.x, run = 0;
+        for (int w = 0; w < 32; w++) { uint32_t h = hist[w][c]; hist[w][c] = (uint16_t)run; run += h; }
+        class_base[c] = run;                            // total of the class for now
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int c = RT_SORT_CLASSES - 1; c >= 0; c--) { uint32_t t = class_base[c]; class_base[c] = run; run += t; }
+    }
+    __syncthreads();
+    for (uint32_t g = lo; g < hi; g += 32) {
+        uint32_t o = g + lane;
+        bool in = o < hi;
+        uint32_t c = in ? cls[o] : 0xffffffffu;
+        uint32_t same = __match_any_sync(0xffffffffu, c);
+        if (in) {
+            uint32_t pos = class_base[c] + hist[warp][c] + (uint32_t)__popc(same & ((1u << lane) - 1u));
+            tile_ids[pos] = ids0[o];
+            tile_ord[pos] = o;
         }
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        tile_ids[i] = 0xffffffffu - (uint32_t)(key[i] & 0xffffffffu);
-        cost[i] = 0;
+        __syncwarp();
+        if (in && lane == __ffs(same) - 1) hist[warp][c] += (uint16_t)__popc(same);
+        __syncwarp();
     }
 }
 
-// One thread per 4 horizontally adjacent pixels of an owned tile.
 __global__ void __launch_bounds__(256) k_resolve(FrameDev f, const long long* __restrict__ accum,
                                                 uint8_t* __restrict__ out, int packed,
                                                 const FrameCounters* __restrict__ fc) {
@@ -1509,11 +1552,19 @@ void setup_layout(rt_ctx* c, const rt_camera* cam, const rt_render_params* p) {
     L.n_tiles_owned = (uint32_t)ids.size();
     L.n_pool_tiles = (uint32_t)pool.size();
     c->d_tile_ids.reserve(ids.size() ? ids.size() : 1);
+    c->d_tile_ids0.reserve(ids.size() ? ids.size() : 1);
+    c->d_tile_ord.reserve(ids.size() ? ids.size() : 1);
     c->d_pool_ids.reserve(pool.size() ? pool.size() : 1);
     uint32_t bpt = (uint32_t)(L.tile_w * L.tile_h) / 32u;
     c->d_stolen_map.reserve(pool.size() ? pool.size() * bpt : 1);
-    if (!ids.empty())
+    if (!ids.empty()) {
+        std::vector<uint32_t> ord(ids.size());
+        for (size_t k = 0; k < ord.size(); k++) ord[k] = (uint32_t)k;
         RT_CUDA(cudaMemcpyAsync(c->d_tile_ids.p, ids.data(), ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(cudaMemcpyAsync(c->d_tile_ids0.p, ids.data(), ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(cudaMemcpyAsync(c->d_tile_ord.p, ord.data(), ord.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(cudaStreamSynchronize(c->stream));      // `ord` and `ids` are pageable host memory
+    }
     if (!pool.empty())
         RT_CUDA(cudaMemcpyAsync(c->d_pool_ids.p, pool.data(), pool.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     RT_CUDA(cudaStreamSynchronize(c->stream));
@@ -1531,6 +1582,7 @@ FrameDev frame_dev(rt_ctx* c, const rt_render_params* p) {
     f.n_tiles_owned = L.n_tiles_owned;
     f.n_local_pix = L.n_tiles_owned * (uint32_t)f.tile_pix;
     f.tile_ids = c->d_tile_ids.p;
+    f.tile_ord = c->d_tile_ord.p;
     f.pool_ids = c->d_pool_ids.p;
     f.n_pool_blocks = L.n_pool_tiles * ((uint32_t)f.tile_pix / 32u);
     f.stolen_map = c->d_stolen_map.p;
@@ -1997,11 +2049,12 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         RT_CUDA(cudaGetLastError());
         launches++;
     }
-    // re-sort after the first two frames of a layout and then every 8th frame (the one-CTA sort costs
-    // ~50 us; costs keep accumulating as maxima in between); it runs after the last kernel that indexes
+    // heavy tiles first in the frames that follow: re-sorted after the first two frames of a layout and then every
+    // RT_TILE_SORT_EVERY-th frame (costs accumulate as maxima in between); it runs after the last kernel that indexes
     // pixels through tile_ids
-    if (f.tile_cost && (c->frames_in_layout < 2 || c->frames_in_layout % 8 == 0)) {
-        k_sort_tiles<<<1, 1024, 0, st>>>(c->d_tile_ids.p, c->d_tile_cost.p, f.n_tiles_owned, c->tile_bucket_bits);
+    if (f.tile_cost && (c->frames_in_layout < 2 || c->frames_in_layout % (uint32_t)c->tile_sort_every == 0)) {
+        k_sort_tiles<<<1, 1024, 0, st>>>(c->d_tile_ids.p, c->d_tile_ord.p, c->d_tile_ids0.p, c->d_tile_cost.p, f.n_tiles_owned,
+                                         c->tile_bucket_bits);
         RT_CUDA(cudaGetLastError());
         launches++;
     }
