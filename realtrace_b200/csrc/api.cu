@@ -75,6 +75,7 @@ static rt_ctx* make_ctx(int device) {
         env_int("RT_TILE_BUCKET_BITS", 0, 8, c->tile_bucket_bits);
         env_int("RT_TILE_SORT_EVERY", 1, 1024, c->tile_sort_every);
         env_int("RT_PATH_KERNEL", 0, 1, c->path_kernel);
+        env_int("RT_PATH_SHARE", 0, 1, c->path_share);
         env_int("RT_TILE_FEEDBACK", 0, 1, c->tile_feedback);
         env_int("RT_REFILL_PRIMARY_FUSED", 1, 32, c->refill_primary_fused);
         env_int("RT_LOOP_PRIMARY", 0, 1024, c->loop_primary);

@@ -1085,6 +1085,7 @@ struct PathArgs {
     int refill_min;
     int loop_style;
     uint32_t brute;
+    int share;                // parked rays are handed to idle lanes of the warp (RT_PATH_SHARE)
 };
 
 template <bool COUNT, bool WIDE = false>
@@ -1112,7 +1113,9 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
     wc.nodes = wc.tris = wcs.nodes = wcs.tris = 0;
     hit.t = nh.t = RT_FLT_MAX; hit.prim = nh.prim = RT_MISS; hit.beta = hit.gamma = nh.beta = nh.gamma = 0.0f;
 
+    bool spawned = false;                     // the current hit's children are parked already (a.share)
     auto start_nearest = [&]() {              // (ro, rd) is the lane's current ray
+        spawned = false;
         bool finite = rd.x == rd.x && rd.y == rd.y && rd.z == rd.z;
         r = prep_ray(ro, rd);
         hit.t = RT_FLT_MAX; hit.prim = RT_MISS; hit.beta = hit.gamma = 0.0f;
@@ -1132,6 +1135,17 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
         stk.clear();
         node = (use_bvh && sd.x == sd.x && sd.y == sd.y && sd.z == sd.z) ? 0 : RT_DONE;
         n_shadow++;
+    };
+    auto park = [&](const ShadeChild& ch) {   // a child of the lane's current ray (pix, w) waits on the lane's stack
+        if (psp < RT_PATH_STACK) {
+            f3 cw = w * ch.w;
+            pend[3 * psp] = make_float4(ch.o.x, ch.o.y, ch.o.z, __uint_as_float(pix));
+            pend[3 * psp + 1] = make_float4(ch.d.x, ch.d.y, ch.d.z, __int_as_float(ch.level));
+            pend[3 * psp + 2] = make_float4(cw.x, cw.y, cw.z, 0.0f);
+            psp++;
+        } else {
+            pend_overflow = true;
+        }
     };
     auto next_ray = [&]() {                   // current ray is finished: continue with a parked one or go idle
         if (psp > 0) {
@@ -1162,6 +1176,39 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
                 w = mk3(q2);
                 psp = 0;
                 start_nearest();
+            }
+        }
+        // ---- parked rays are shared inside the warp: the k-th idle lane takes the OLDEST parked ray (the root of the
+        // largest pending subtree) of the k-th lane that has one, so that no lane walks a whole dielectric subtree
+        // alone while its neighbours have nothing to do.  Shuffles only: no queue, no atomics, no polling; pixel sums
+        // are order-independent (32.32 fixed point), so frames do not change.
+        if (a.share) {
+            const uint32_t idle = __ballot_sync(FULL, !active);
+            const uint32_t donors = __ballot_sync(FULL, active && psp > 0);
+            if (idle && donors) {
+                const int pairs = min(__popc(idle), __popc(donors));
+                const int my_idle = __popc(idle & lt);
+                const bool give = active && psp > 0 && __popc(donors & lt) < pairs;
+                const bool take = !active && my_idle < pairs;
+                float4 g0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), g1 = g0, g2 = g0;
+                if (give) {
+                    g0 = pend[0]; g1 = pend[1]; g2 = pend[2];
+                    psp--;
+                    if (psp > 0) { pend[0] = pend[3 * psp]; pend[1] = pend[3 * psp + 1]; pend[2] = pend[3 * psp + 2]; }
+                }
+                const int src = take ? (int)__fns(donors, 0, my_idle + 1) : lane;
+                g0.x = __shfl_sync(FULL, g0.x, src); g0.y = __shfl_sync(FULL, g0.y, src); g0.z = __shfl_sync(FULL, g0.z, src);
+                g0.w = __shfl_sync(FULL, g0.w, src);
+                g1.x = __shfl_sync(FULL, g1.x, src); g1.y = __shfl_sync(FULL, g1.y, src); g1.z = __shfl_sync(FULL, g1.z, src);
+                g1.w = __shfl_sync(FULL, g1.w, src);
+                g2.x = __shfl_sync(FULL, g2.x, src); g2.y = __shfl_sync(FULL, g2.y, src); g2.z = __shfl_sync(FULL, g2.z, src);
+                if (take) {
+                    ro = mk3(g0); pix = __float_as_uint(g0.w);
+                    rd = mk3(g1); level = __float_as_int(g1.w);
+                    w = mk3(g2);
+                    psp = 0;
+                    start_nearest();
+                }
             }
         }
         if (!__any_sync(FULL, active)) {
@@ -1207,6 +1254,16 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
                     float4 m1 = __ldg(a.s.materials + 3 * mat + 1);
                     if (!(m1.z > 0.0f && m1.w > 0.0f)) {           // dielectrics discard the local colour
                         P = fma3(rd, hit.t, ro);
+                        if (a.share) {
+                            // The mirror child needs the hit, not its shading: it is parked NOW, so that an idle lane
+                            // can walk it while this lane walks the hit's shadow rays (a path's chain of dependent
+                            // traversals shrinks from depth x (1 + lights) to depth + lights).
+                            ShadeOut eo;
+                            auto lit = [](f3, f3) -> bool { return false; };
+                            shade_hit(a.s, ro, rd, level, nh, a.max_depth, lit, eo);
+                            for (int k = 0; k < eo.n_children; k++) park(eo.child[k]);
+                            spawned = true;
+                        }
                         phase = 0;
                         start_shadow(0);
                         shade_now = false;
@@ -1219,18 +1276,8 @@ __global__ void __launch_bounds__(TRAV_TPB) k_paths(const __grid_constant__ Path
                 auto occluded = [&](f3, f3) -> bool { bool o2 = ((occl_mask >> li) & 1u) != 0; li++; return o2; };
                 shade_hit(a.s, ro, rd, level, nh, a.max_depth, occluded, out);
                 accumulate<false>(a.accum, pix, w * (out.local + out.bg_weight * bg));
-                if (out.n_children == 2) {                         // park the second child
-                    if (psp < RT_PATH_STACK) {
-                        const ShadeChild& c1 = out.child[1];
-                        f3 cw = w * c1.w;
-                        pend[3 * psp] = make_float4(c1.o.x, c1.o.y, c1.o.z, __uint_as_float(pix));
-                        pend[3 * psp + 1] = make_float4(c1.d.x, c1.d.y, c1.d.z, __int_as_float(c1.level));
-                        pend[3 * psp + 2] = make_float4(cw.x, cw.y, cw.z, 0.0f);
-                        psp++;
-                    } else {
-                        pend_overflow = true;
-                    }
-                }
+                if (spawned) out.n_children = 0;                   // its children were parked when the hit was found
+                if (out.n_children == 2) park(out.child[1]);       // park the second child
                 if (out.n_children >= 1) {
                     const ShadeChild& c0 = out.child[0];
                     ro = c0.o; rd = c0.d; w = w * c0.w; level = c0.level;
@@ -1746,6 +1793,7 @@ void launch_paths(rt_ctx* c, int slot, int cur, int max_depth, uint32_t brute, b
     pa.refill_min = c->refill_queue;
     pa.loop_style = c->loop_queue;
     pa.brute = brute;
+    pa.share = c->path_share;
     if (pa.s.nodes4) {
         if (count) k_paths<true, true><<<c->path_wide_blocks, TRAV_TPB, 0, c->stream>>>(pa);
         else k_paths<false, true><<<c->path_wide_blocks, TRAV_TPB, 0, c->stream>>>(pa);

@@ -173,6 +173,7 @@ struct rt_ctx {
     TileLayout layout;
     DevBuf<uint32_t> d_tile_ids, d_pool_ids, d_stolen_map, d_tile_cost;
     DevBuf<uint32_t> d_tile_ids0, d_tile_ord;   // the canonical (ascending) tile list; ordinal of the tile at each position of d_tile_ids
+    int path_share = 1;                    // k_paths: parked rays go to idle lanes of the warp (RT_PATH_SHARE)
     int tile_sort_every = 8;               // RT_TILE_SORT_EVERY: the order is renewed after the first two frames of a layout, then every k-th
     bool tile_cost_valid = false;
     uint32_t frames_in_layout = 0;
