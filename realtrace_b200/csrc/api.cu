@@ -835,8 +835,7 @@ int rt_debug_sort_pairs(rt_ctx* ctx, uint64_t* keys, uint32_t* values, uint32_t 
         ctx->d_vals[0].reserve(n);
         RT_CUDA(cudaMemcpyAsync(ctx->d_keys[0].p, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         RT_CUDA(cudaMemcpyAsync(ctx->d_vals[0].p, values, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        int passes = 0;
-        rt_sort_pairs_device(ctx, n, &passes);
+        rt_sort_pairs_device(ctx, n);
         RT_CUDA(cudaMemcpyAsync(keys, ctx->d_keys[ctx->sorted_buf].p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         RT_CUDA(cudaMemcpyAsync(values, ctx->d_vals[ctx->sorted_buf].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         RT_CUDA(cudaStreamSynchronize(st));

@@ -66,14 +66,23 @@ __global__ void __launch_bounds__(TPB) k_scene_bounds(const float* __restrict__ 
             chi[k] = fmaxf(chi[k], __shfl_xor_sync(0xffffffffu, chi[k], o));
         }
     }
-    if ((threadIdx.x & 31) == 0) {
+    // one set of 12 atomics per CTA (one per warp serialised 113 k same-address atomics at 1 M triangles: 78 us)
+    __shared__ float red[TPB / 32][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            atomicMin(&bounds[k], ord_encode(lo[k]));
-            atomicMax(&bounds[3 + k], ord_encode(hi[k]));
-            atomicMin(&bounds[6 + k], ord_encode(clo[k]));
-            atomicMax(&bounds[9 + k], ord_encode(chi[k]));
+            red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; red[warp][6 + k] = clo[k]; red[warp][9 + k] = chi[k];
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const int k = threadIdx.x;
+        const bool is_min = (k % 6) < 3;
+        float r = red[0][k];
+#pragma unroll
+        for (int w = 1; w < TPB / 32; w++) r = is_min ? fminf(r, red[w][k]) : fmaxf(r, red[w][k]);
+        if (is_min) atomicMin(&bounds[k], ord_encode(r)); else atomicMax(&bounds[k], ord_encode(r));
     }
 }
 
@@ -197,11 +206,15 @@ __global__ void __launch_bounds__(TPB) k_refit(const float* __restrict__ v, cons
     Aabb bx = tri_aabb(a, b, c);
     box_lo[(n - 1) + k] = make_float4(bx.lo.x, bx.lo.y, bx.lo.z, 0.0f);
     box_hi[(n - 1) + k] = make_float4(bx.hi.x, bx.hi.y, bx.hi.z, 0.0f);
+    // A node whose leaf range lies inside this CTA's 256 leaves is finished by two threads of this CTA: a
+    // CTA-scope fence orders their box stores.  Only nodes that span CTAs (well under 1 % of them) pay for the
+    // GPU-scope fence (MEMBAR.SC.GPU + L1 invalidate), which used to be issued on every level by every thread.
+    const int cta_lo = blockIdx.x * TPB, cta_hi = min(cta_lo + TPB, n) - 1;
     int cur = leaf_parent[k];
     while (cur >= 0) {
-        __threadfence();
-        if (atomicAdd(&visit[cur], 1u) == 0u) return;   // first arriver leaves; the sibling finishes the node
         KarrasNode nd = kn[cur];
+        if (nd.first >= cta_lo && nd.last <= cta_hi) __threadfence_block(); else __threadfence();
+        if (atomicAdd(&visit[cur], 1u) == 0u) return;   // first arriver leaves; the sibling finishes the node
         int li = nd.left < 0 ? (n - 1) + ~nd.left : nd.left;
         int ri = nd.right < 0 ? (n - 1) + ~nd.right : nd.right;
         float4 l0 = __ldcg(box_lo + li), l1 = __ldcg(box_hi + li);
@@ -428,9 +441,7 @@ void rt_build_bvh(rt_ctx* c, bool refit_only) {
         c->n_large = h_large;
         c->n_bvh = n - h_large;
 
-        int passes = 0;
-        rt_sort_pairs_device(c, n, &passes);
-        c->build_stats.sort_passes = (uint32_t)passes;
+        rt_sort_pairs_device(c, n);
         if (c->n_bvh >= 2) {
             k_karras<<<blocks_for(c->n_bvh - 1), TPB, 0, st>>>(c->d_keys[c->sorted_buf].p, (int)c->n_bvh, c->d_karras.p,
                                                               c->d_leaf_parent.p, c->d_node_parent.p);
@@ -441,6 +452,7 @@ void rt_build_bvh(rt_ctx* c, bool refit_only) {
     RT_CUDA(cudaEventRecord(c->ev[5], st));
     RT_CUDA(cudaEventSynchronize(c->ev[5]));
     RT_CUDA(cudaEventElapsedTime(&c->build_stats.ms_build, c->ev[4], c->ev[5]));
+    c->build_stats.sort_passes = n >= 2 ? (uint32_t)rt_sort_passes_done(c) : 0u;
     c->build_stats.n_triangles = c->n_bvh;
     c->build_stats.leaf_size = (uint32_t)c->leaf_size;
     c->build_stats.n_large_triangles = c->n_large;

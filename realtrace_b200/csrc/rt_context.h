@@ -237,7 +237,8 @@ struct rt_ctx {
 
 // ---- entry points implemented across the .cu files ------------------------------------------------
 void rt_build_bvh(rt_ctx* c, bool refit_only);                      // bvh_build.cu
-void rt_sort_pairs_device(rt_ctx* c, uint32_t n, int* sort_passes); // radix_sort.cu: d_keys[0]/d_vals[0] -> sorted_buf
+void rt_sort_pairs_device(rt_ctx* c, uint32_t n);   // radix_sort.cu: d_keys[0]/d_vals[0] -> sorted_buf; only enqueues
+int rt_sort_passes_done(rt_ctx* c);                  // passes of the last sort that moved keys (synchronises)
 void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p, void* rgb_dev,
                      const rt_aux_out* aux_dev, rt_frame_stats* stats);   // render.cu
 void rt_query_rays(rt_ctx* c, const float* rays_host, uint32_t n, int max_depth, uint32_t flags, bool shade,
