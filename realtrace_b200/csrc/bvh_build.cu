@@ -326,10 +326,16 @@ static void upload_static_scene(rt_ctx* c) {
     RT_CUDA(cudaStreamSynchronize(st));       // m, l, a are locals
 }
 
+// The 4-wide view serves k_paths (latency-bound bounce paths; mode 1, only when something reflects), every fused
+// walk (mode 2), or the heaviest tiles of a multi-GPU share (want_nodes4, set by the first frame that asks).
+static bool wants_wide_view(const rt_ctx* c) {
+    return (c->wide_bvh == 1 && c->has_reflective) || c->wide_bvh >= 2 || c->want_nodes4;
+}
+
 static void publish_scene(rt_ctx* c) {
     SceneDev& s = c->scene;
     s.nodes = c->d_nodes.p;
-    s.nodes4 = (((c->wide_bvh == 1 && c->has_reflective) || c->wide_bvh >= 2) && c->n_bvh >= 1) ? c->d_nodes4.p : nullptr;
+    s.nodes4 = (wants_wide_view(c) && c->n_bvh >= 1) ? c->d_nodes4.p : nullptr;
     s.tris = c->d_tris.p;
     s.tri_rgb = c->h_tri_rgb.empty() ? nullptr : c->d_tri_rgb.p;
     s.analytic = c->d_analytic.p;
@@ -350,6 +356,16 @@ static void launch_scene_bounds(rt_ctx* c) {
     if (bb > c->sm_count * 8) bb = c->sm_count * 8;
     k_scene_bounds<<<bb, TPB, 0, st>>>(c->d_tri_v.p, n, c->d_bounds.p);
     RT_CUDA(cudaGetLastError());
+}
+
+static void launch_collapse4(rt_ctx* c) {
+    uint32_t nb = c->n_bvh;
+    if (nb < 1) return;
+    int nn = nb >= 2 ? (int)nb - 1 : 1;
+    c->d_nodes4.reserve(RT_NODE4_FLOAT4S * (size_t)nn);
+    k_collapse4<<<blocks_for((uint32_t)nn), TPB, 0, c->stream>>>(c->d_nodes.p, nn, c->d_nodes4.p);
+    RT_CUDA(cudaGetLastError());
+    c->launch_total++;
 }
 
 static void run_refit(rt_ctx* c, bool new_vertices) {
@@ -382,15 +398,14 @@ static void run_refit(rt_ctx* c, bool new_vertices) {
         RT_CUDA(cudaGetLastError());
         c->launch_total++;
     }
-    // the 4-wide view serves k_paths (latency-bound bounce paths; mode 1, only built when something reflects)
-    // or every fused walk (mode 2)
-    if (((c->wide_bvh == 1 && c->has_reflective) || c->wide_bvh >= 2) && nb >= 1) {
-        int nn = nb >= 2 ? (int)nb - 1 : 1;
-        c->d_nodes4.reserve(RT_NODE4_FLOAT4S * (size_t)nn);
-        k_collapse4<<<blocks_for((uint32_t)nn), TPB, 0, st>>>(c->d_nodes.p, nn, c->d_nodes4.p);
-        RT_CUDA(cudaGetLastError());
-        c->launch_total++;
-    }
+    if (wants_wide_view(c)) launch_collapse4(c);
+}
+
+void rt_ensure_nodes4(rt_ctx* c) {
+    c->want_nodes4 = true;
+    if (c->scene.nodes4 || c->n_bvh < 1) return;
+    launch_collapse4(c);
+    publish_scene(c);
 }
 
 void rt_build_bvh(rt_ctx* c, bool refit_only) {

@@ -132,6 +132,8 @@ struct FrameDev {
     uint32_t* steal_cursor;                // system-scope cursor of this frame, nullptr = no stealing
     uint32_t* tile_cost;                   // per owned tile: clocks its warps spent this frame (feedback for the
                                            // heavy-tiles-first order of the next frame), nullptr = off
+    uint32_t n_wide_pix;                   // batches below this local pixel index (the heaviest tiles of the order) walk
+                                           // the 4-wide view (traverse_body<WIDE = 2>); 0 = none
 };
 
 // (tile, 8x4 block, lane) -> frame pixel; lane = x%8 + 8*(y%4).
@@ -357,12 +359,20 @@ __device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uin
 // WIDE = 1: walk the 4-wide view of the tree (SceneDev::nodes4); a template parameter so that the binary walk
 // keeps its register budget.  (A hybrid that moved a ray to the wide view after 32 steps was measured in round 2:
 // it removes the kernel's tail but costs the bulk 20 % at 80 registers — profiles/r2_tuning.md — and was deleted.)
+// WIDE = 2 (whole-batch refill only): both walks, chosen per 32-pixel batch.  The batches of the tiles at the head of the
+// heavy-tiles-first order walk the wide view, everything else the binary tree.  The end of a rank's share of a multi-GPU
+// frame is ONE batch whose longest ray is a chain of ~240 dependent steps; on the wide view the same ray takes ~40 %
+// fewer, and the few hundred batches that walk it do not cost the bulk its cheaper binary step.  The choice is
+// warp-uniform and fixed for the batch, so each walk keeps its own loop (no per-step branch, unlike the hybrid).
 // SHADE (fused primary rays, whole-batch refill): the hit is not queued for k_shade either.  A lane keeps its
 // hit and occlusion bits until the warp's 32-pixel batch is done, then the warp shades all its hits together
 // (World::shade_ray, world.cpp:32-111, same shade_hit as k_shade), writes the pixels and queues the bounce
 // rays.  One kernel per primary wave: no hit queue traffic, no second launch, no second tail.
 #ifndef RT_DENSE_MIN_BLOCKS
 #define RT_DENSE_MIN_BLOCKS 9           // k_frame / k_frame_push for large shares: 56 registers, 9 CTAs per SM
+#endif
+#ifndef RT_FRAME_WIDE
+#define RT_FRAME_WIDE 2                 // k_frame / k_frame_push: 2 = heavy batches walk the wide view, 0 = binary walk only
 #endif
 #ifndef RT_SHADE_FUSED_MIN_BLOCKS
 #define RT_SHADE_FUSED_MIN_BLOCKS 7     // SHADE: hold the kernel to the traversal loop's 72 registers (the once-per-batch shading spills)
@@ -374,7 +384,8 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
     constexpr bool ANY = MODE == MODE_SHADOW;
     static_assert(!(FUSE && ANY), "FUSE applies to the nearest-hit modes");
     static_assert(!WIDE || FUSE, "the wide walk is instantiated for the fused kernels only");
-    static_assert(WIDE >= 0 && WIDE <= 1, "WIDE: 0 binary walk, 1 4-wide view");
+    static_assert(WIDE >= 0 && WIDE <= 2, "WIDE: 0 binary walk, 1 4-wide view, 2 chosen per batch");
+    static_assert(WIDE != 2 || MODE == MODE_PRIMARY, "the per-batch choice needs whole batches of primary rays");
     static_assert(!SHADE || (FUSE && MODE == MODE_PRIMARY), "in-kernel shading is for the fused primary wave");
     const unsigned FULL = 0xffffffffu;
     uint32_t claimed = 0;
@@ -400,6 +411,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
     uint32_t steal_left = 0, steal_slot = 0;
     uint32_t batch_tile = 0xffffffffu;
     long long batch_t0 = 0;
+    bool wide_now = false;                 // WIDE == 2: the current batch walks the 4-wide view (warp-uniform)
     uint32_t item = 0, pix = 0;
     int pi = 0, pj = 0;
     f3 w = mk3(1, 1, 1);
@@ -439,7 +451,13 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
         }
         if (batch_tile == 0xffffffffu) return;
         // charge its duration to the tile
-        if (a.f.tile_cost && lane == 0) atomicMax(a.f.tile_cost + __ldg(a.f.tile_ord + batch_tile), (uint32_t)((clock64() - batch_t0) >> 6));
+        if (a.f.tile_cost && lane == 0) {
+            uint32_t cost = (uint32_t)((clock64() - batch_t0) >> 6);
+            // a batch that walked the wide view is charged what the binary walk would have taken (about 3/2), so that a
+            // heavy tile does not drop out of the head of the order because it was treated as heavy
+            if (WIDE == 2 && wide_now) cost += cost >> 1;
+            atomicMax(a.f.tile_cost + __ldg(a.f.tile_ord + batch_tile), cost);
+        }
         batch_tile = 0xffffffffu;
     };
 
@@ -466,6 +484,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
                 batch_tile = base / (uint32_t)a.f.tile_pix;
                 batch_t0 = clock64();
             }
+            if (WIDE == 2) wide_now = need == FULL && base < a.f.n_wide_pix;
             if (base + (uint32_t)cnt >= n) exhausted = true;
             if (base < n) claimed += min((uint32_t)cnt, n - base);
             my = base + __popc(need & lt);
@@ -489,6 +508,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
                 if (steal_left == 0) steal_done = true;
             }
             if (steal_left) {
+                if (WIDE == 2) wide_now = false;
                 my = a.f.n_local_pix + steal_slot * 32u + (uint32_t)lane;
                 have = true;
                 steal_slot++;
@@ -563,7 +583,12 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
         const bool any = FUSE ? phase >= 0 : ANY;
         WorkCount* wcp = COUNT ? (any ? &wcs : &wc) : nullptr;
         if (active) {
-            if (a.loop_style == 0) {
+            if (WIDE == 2 && wide_now) {
+                // a heavy batch: the same walk on the 4-wide view (its own loop: the binary loop below keeps its code)
+                const int iters = a.loop_style == 0 ? 64 : a.loop_style;
+                for (int it = 0; it < iters && node != RT_DONE; it++)
+                    node = bvh4_step_unified(a.s, r, hit, node, stk, any, found, &overflow, wcp);
+            } else if (a.loop_style == 0) {
                 while (rt_is_internal(node)) {
                     if (COUNT) wcp->nodes++;
                     node = WIDE == 1
@@ -865,7 +890,7 @@ __global__ void __launch_bounds__(TRAV_TPB, MINB) k_frame(const __grid_constant_
         __threadfence_system();
     }
     // ---- phase 1
-    traverse_body<MODE_PRIMARY, COUNT, true, 0, false>(a.t, nullptr);
+    traverse_body<MODE_PRIMARY, COUNT, true, RT_FRAME_WIDE, false>(a.t, nullptr);
     stamp(1);
     if (a.phase1_only) return;
     // every hit of the frame is in the queue once all CTAs are here
@@ -1037,7 +1062,7 @@ __global__ void __launch_bounds__(TRAV_TPB, MINB) k_frame_push(const __grid_cons
         }
     }
     stamp(2);
-    traverse_body<MODE_PRIMARY, COUNT, true, 0, true>(a.t, s_pdir);
+    traverse_body<MODE_PRIMARY, COUNT, true, RT_FRAME_WIDE, true>(a.t, s_pdir);
     stamp(1);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1634,6 +1659,7 @@ FrameDev frame_dev(rt_ctx* c, const rt_render_params* p) {
     f.n_pool_blocks = L.n_pool_tiles * ((uint32_t)f.tile_pix / 32u);
     f.stolen_map = c->d_stolen_map.p;
     f.tile_cost = nullptr;
+    f.n_wide_pix = 0;
     if (c->tile_feedback && L.n_tiles_owned > 1 && L.n_tiles_owned <= RT_SORT_TILES_MAX && c->refill_primary == 32 &&
         (!c->fuse_shadow || c->refill_primary_fused == 32)) {
         c->d_tile_cost.reserve(L.n_tiles_owned);
@@ -1997,6 +2023,15 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         ta.hits = c->d_hits.p; ta.hitq = c->d_hitq.p; ta.occl = c->d_occl.p;
         ta.refill_min = c->refill_primary_fused;
         ta.loop_style = c->loop_primary;
+        // the tiles at the head of the heavy-tiles-first order walk the 4-wide view (traverse_body<WIDE = 2>): needs a
+        // cost-sorted order (from the second frame of a layout on) and whole-batch refill; the view is built on first use
+        ta.f.n_wide_pix = 0;
+        if (RT_FRAME_WIDE == 2 && f.tile_cost && c->frames_in_layout >= 1 && ta.refill_min == 32 && !ta.brute &&
+            (c->wide_heavy == 2 || (c->wide_heavy == 1 && f.world > 1)) && c->n_bvh >= 1) {
+            rt_ensure_nodes4(c);
+            ta.s = c->scene;
+            ta.f.n_wide_pix = ((f.n_tiles_owned + (uint32_t)c->wide_heavy_div - 1) / (uint32_t)c->wide_heavy_div) * (uint32_t)f.tile_pix;
+        }
         fa.t = ta;
         fa.max_depth = p->max_depth;
         static const bool fk_split = getenv("RT_FK_SPLIT") != nullptr;

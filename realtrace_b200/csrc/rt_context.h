@@ -157,6 +157,10 @@ struct rt_ctx {
     DevBuf<uint32_t> d_tri_mat, d_tri_obj;
     DevBuf<float4> d_tri_rgb, d_tris, d_nodes, d_nodes4, d_box_lo, d_box_hi, d_materials, d_lights;
     int wide_bvh = 1;                      // 4-wide collapse of the tree: 0 off, 1 for k_paths (bounce paths), 2 everywhere (RT_WIDE_BVH)
+    int wide_heavy = 1;                    // RT_WIDE_HEAVY: the heaviest tiles of a share walk the 4-wide view (k_frame / k_frame_push):
+                                           // 0 never, 1 shares of a multi-rank frame, 2 every frame with a cost-sorted tile order
+    int wide_heavy_div = 64;               // RT_WIDE_HEAVY_DIV: ... the first n_tiles_owned / div tiles of the heavy-tiles-first order
+    bool want_nodes4 = false;              // the 4-wide view is kept current for the heavy tiles (set by the first frame that wants it)
     DevBuf<AnalyticPrim> d_analytic;
     DevBuf<uint64_t> d_keys[2];
     DevBuf<uint32_t> d_vals[2];
@@ -238,6 +242,7 @@ struct rt_ctx {
 // ---- entry points implemented across the .cu files ------------------------------------------------
 void rt_build_bvh(rt_ctx* c, bool refit_only);                      // bvh_build.cu
 void rt_sort_pairs_device(rt_ctx* c, uint32_t n);   // radix_sort.cu: d_keys[0]/d_vals[0] -> sorted_buf; only enqueues
+void rt_ensure_nodes4(rt_ctx* c);                    // bvh_build.cu: builds the 4-wide view now if the scene has none (enqueues)
 int rt_sort_passes_done(rt_ctx* c);                  // passes of the last sort that moved keys (synchronises)
 void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p, void* rgb_dev,
                      const rt_aux_out* aux_dev, rt_frame_stats* stats);   // render.cu

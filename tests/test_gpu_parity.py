@@ -413,6 +413,58 @@ def test_work_order_feedback_never_changes_a_pixel(name):
         assert np.array_equal(got[y0:y0 + 16, x0:x0 + 32], first[y0:y0 + 16, x0:x0 + 32]), t
 
 
+@pytest.mark.parametrize("name", ["synth_small_d1", "analytic_stock_d1", "one_triangle", "two_triangles",
+                                  "degenerate_and_duplicate_triangles", "coincident_centroids"])
+@pytest.mark.parametrize("div", [1, 3])
+def test_heavy_tiles_on_the_wide_view_never_change_a_pixel(name, div, monkeypatch):
+    """RT_WIDE_HEAVY: the batches of the heaviest tiles (the first 1/div of the cost-sorted order) walk the 4-wide view
+    of the tree inside the same launch, the others the binary tree.  Both views index the same nodes and tie-break
+    equal distances by object order, so frames, first-hit ids and distances are those of the binary walk — for the
+    whole frame (k_frame) and for a logical rank's share pushed into a shared frame (k_frame_push)."""
+    import torch
+    if name in EDGE_CASES:
+        scene, cam, depth = build_edge_case(name)
+    else:
+        scene, cam, depth, _ = build_case(name)
+    if name == "analytic_stock_d1":            # bounce-free variant of the stock scene: the one-launch frame needs kr = 0
+        scene.materials["kr"] = 0.0
+        scene.materials["kt"] = 0.0
+    cam.width, cam.height = 328, 203
+    monkeypatch.setenv("RT_WIDE_HEAVY", "0")
+    ref_ctx = make_ctx(scene)
+    ref = ref_ctx.render(cam, depth, aux=True)
+    ref_ctx.close()
+    monkeypatch.setenv("RT_WIDE_HEAVY", "2")
+    monkeypatch.setenv("RT_WIDE_HEAVY_DIV", str(div))
+    ctx = make_ctx(scene)
+    for k in range(4):                         # frame 0 runs in spatial order (binary walk only), then the sorted order
+        got = ctx.render(cam, depth, tile=(32, 16), aux=True)
+        assert np.array_equal(got[0], ref[0]), k
+        assert np.array_equal(got[1], ref[1]), k
+        assert np.array_equal(got[2], ref[2]), k
+        assert got[3]["rays_primary"] == cam.width * cam.height
+    # a logical rank's share through rt_render_push (rank 1 of 2; the frame lives on this GPU)
+    world, rank, tile = 2, 1, (32, 16)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+    frame = torch.zeros(cam.width * cam.height * 3, dtype=torch.uint8, device="cuda")
+    sync_ptr, _ = ctx.shared_buffer_create(1024)
+    _, owned, tb = api.tile_layout(cam.width, cam.height, tile[0], tile[1], rank, world)
+    packed = torch.zeros(max(owned * tb, 1), dtype=torch.uint8, device="cuda")
+    cs = api.camera_struct(cam)
+    params = api.Context._params(depth, tile=tile, rank=rank, world=world, flags=api.FLAG_PACKED_TILES)
+    tx, ty = (cam.width + tile[0] - 1) // tile[0], (cam.height + tile[1] - 1) // tile[1]
+    for k in range(4):
+        frame.fill_(0x5a)
+        ctx.peer_sync(sync_ptr, 0, world, k, 0)
+        ctx.render_push(cs, params, packed.data_ptr(), frame.data_ptr(), sync_ptr, k)
+        ctx.synchronize()
+        got = frame.cpu().numpy().reshape(cam.height, cam.width, 3)
+        for t in range(rank, tx * ty, world):
+            x0, y0 = (t % tx) * tile[0], (t // tx) * tile[1]
+            assert np.array_equal(got[y0:y0 + tile[1], x0:x0 + tile[0]], ref[0][y0:y0 + tile[1], x0:x0 + tile[0]]), (k, t)
+    ctx.close()
+
+
 @pytest.mark.parametrize("name,tile", [("synth_small_d1", (0, 0)), ("synth_small_d1", (32, 16)), ("synth_small_d1", (8, 4)),
                                        ("blubmixed_d5", (0, 0))])
 def test_render_push_one_call_per_rank(name, tile):
