@@ -70,6 +70,7 @@ static rt_ctx* make_ctx(int device) {
         env_int("RT_WIDE_BVH", 0, 2, c->wide_bvh);
         env_int("RT_WIDE_HEAVY", 0, 2, c->wide_heavy);
         env_int("RT_WIDE_HEAVY_DIV", 1, 65536, c->wide_heavy_div);
+        env_int("RT_WIDE_AFTER_BURSTS", 0, 1024, c->wide_after_bursts);
         env_int("RT_FUSE_SHADOW", 0, 1, c->fuse_shadow);
         env_int("RT_FUSE_SHADE", 0, 2, c->fuse_shade);
         env_int("RT_FRAME_KERNEL", 0, 2, c->frame_kernel);

@@ -134,6 +134,8 @@ struct FrameDev {
                                            // heavy-tiles-first order of the next frame), nullptr = off
     uint32_t n_wide_pix;                   // batches below this local pixel index (the heaviest tiles of the order) walk
                                            // the 4-wide view (traverse_body<WIDE = 2>); 0 = none
+    uint32_t wide_after_bursts;            // ... and any batch moves to it once it has run this many bursts of
+                                           // loop_style steps (a long batch the order did not predict); 0 = never
 };
 
 // (tile, 8x4 block, lane) -> frame pixel; lane = x%8 + 8*(y%4).
@@ -412,6 +414,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
     uint32_t batch_tile = 0xffffffffu;
     long long batch_t0 = 0;
     bool wide_now = false;                 // WIDE == 2: the current batch walks the 4-wide view (warp-uniform)
+    uint32_t bursts = 0;                   // WIDE == 2: traversal bursts the current batch has run (warp-uniform)
     uint32_t item = 0, pix = 0;
     int pi = 0, pj = 0;
     f3 w = mk3(1, 1, 1);
@@ -484,7 +487,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
                 batch_tile = base / (uint32_t)a.f.tile_pix;
                 batch_t0 = clock64();
             }
-            if (WIDE == 2) wide_now = need == FULL && base < a.f.n_wide_pix;
+            if (WIDE == 2) { wide_now = need == FULL && base < a.f.n_wide_pix; bursts = 0; }
             if (base + (uint32_t)cnt >= n) exhausted = true;
             if (base < n) claimed += min((uint32_t)cnt, n - base);
             my = base + __popc(need & lt);
@@ -508,7 +511,7 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
                 if (steal_left == 0) steal_done = true;
             }
             if (steal_left) {
-                if (WIDE == 2) wide_now = false;
+                if (WIDE == 2) { wide_now = false; bursts = 0; }
                 my = a.f.n_local_pix + steal_slot * 32u + (uint32_t)lane;
                 have = true;
                 steal_slot++;
@@ -582,6 +585,10 @@ __device__ __forceinline__ uint32_t traverse_body(const TravArgs& a, float* s_pd
         // ---- traversal of the lanes that own a ray
         const bool any = FUSE ? phase >= 0 : ANY;
         WorkCount* wcp = COUNT ? (any ? &wcs : &wc) : nullptr;
+        // a batch that is still running after wide_after_bursts bursts is a long one the order did not announce (a moving
+        // camera, the first frames of a layout): it continues on the wide view — both views index the same nodes and
+        // leaves, so the lanes' stacks and current nodes carry over
+        if (WIDE == 2 && a.f.wide_after_bursts && bursts++ >= a.f.wide_after_bursts) wide_now = true;
         if (active) {
             if (WIDE == 2 && wide_now) {
                 // a heavy batch: the same walk on the 4-wide view (its own loop: the binary loop below keeps its code)
@@ -1660,6 +1667,7 @@ FrameDev frame_dev(rt_ctx* c, const rt_render_params* p) {
     f.stolen_map = c->d_stolen_map.p;
     f.tile_cost = nullptr;
     f.n_wide_pix = 0;
+    f.wide_after_bursts = 0;
     if (c->tile_feedback && L.n_tiles_owned > 1 && L.n_tiles_owned <= RT_SORT_TILES_MAX && c->refill_primary == 32 &&
         (!c->fuse_shadow || c->refill_primary_fused == 32)) {
         c->d_tile_cost.reserve(L.n_tiles_owned);
@@ -2031,6 +2039,14 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
             rt_ensure_nodes4(c);
             ta.s = c->scene;
             ta.f.n_wide_pix = ((f.n_tiles_owned + (uint32_t)c->wide_heavy_div - 1) / (uint32_t)c->wide_heavy_div) * (uint32_t)f.tile_pix;
+        }
+        // long batches the order did not announce move to the wide view after a few bursts (no order needed)
+        ta.f.wide_after_bursts = 0;
+        if (RT_FRAME_WIDE == 2 && c->wide_after_bursts > 0 && ta.refill_min == 32 && !ta.brute && ta.loop_style > 0 &&
+            (c->wide_heavy == 2 || (c->wide_heavy == 1 && f.world > 1)) && c->n_bvh >= 1) {
+            rt_ensure_nodes4(c);
+            ta.s = c->scene;
+            ta.f.wide_after_bursts = (uint32_t)c->wide_after_bursts;
         }
         fa.t = ta;
         fa.max_depth = p->max_depth;

@@ -160,6 +160,8 @@ struct rt_ctx {
     int wide_heavy = 1;                    // RT_WIDE_HEAVY: the heaviest tiles of a share walk the 4-wide view (k_frame / k_frame_push):
                                            // 0 never, 1 shares of a multi-rank frame, 2 every frame with a cost-sorted tile order
     int wide_heavy_div = 64;               // RT_WIDE_HEAVY_DIV: ... the first n_tiles_owned / div tiles of the heavy-tiles-first order
+    int wide_after_bursts = 0;             // RT_WIDE_AFTER_BURSTS: ... and any batch still running after this many bursts of RT_LOOP_PRIMARY
+                                           // steps continues on the wide view (0 = off)
     bool want_nodes4 = false;              // the 4-wide view is kept current for the heavy tiles (set by the first frame that wants it)
     DevBuf<AnalyticPrim> d_analytic;
     DevBuf<uint64_t> d_keys[2];

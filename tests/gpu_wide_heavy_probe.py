@@ -14,14 +14,15 @@ sys.path.insert(0, ROOT)
 
 SETTINGS = [
     {"RT_WIDE_HEAVY": "0"},
-    {"RT_WIDE_HEAVY": "1", "RT_WIDE_HEAVY_DIV": "32"},
-    {"RT_WIDE_HEAVY": "1", "RT_WIDE_HEAVY_DIV": "8"},
-    {"RT_WIDE_HEAVY": "1", "RT_WIDE_HEAVY_DIV": "128"},
-    {"RT_WIDE_HEAVY": "0", "RT_DENSE_MIN_PIXELS": "0"},
-    {"RT_WIDE_HEAVY": "1", "RT_WIDE_HEAVY_DIV": "32", "RT_DENSE_MIN_PIXELS": "0"},
-    {"RT_WIDE_HEAVY": "1", "RT_WIDE_HEAVY_DIV": "8", "RT_DENSE_MIN_PIXELS": "0"},
-    {"RT_WIDE_HEAVY": "1", "RT_WIDE_HEAVY_DIV": "128", "RT_DENSE_MIN_PIXELS": "0"},
+    {"RT_WIDE_HEAVY": "1", "RT_WIDE_AFTER_BURSTS": "0"},
+    {"RT_WIDE_HEAVY": "1", "RT_WIDE_AFTER_BURSTS": "1"},
+    {"RT_WIDE_HEAVY": "1", "RT_WIDE_AFTER_BURSTS": "2"},
+    {"RT_WIDE_HEAVY": "1", "RT_WIDE_AFTER_BURSTS": "1", "RT_WIDE_HEAVY_DIV": "65536"},
+    {"RT_WIDE_HEAVY": "1", "RT_WIDE_AFTER_BURSTS": "1", "RT_LOOP_PRIMARY": "32"},
+    {"RT_WIDE_HEAVY": "1", "RT_WIDE_AFTER_BURSTS": "1", "RT_DENSE_MIN_PIXELS": "0"},
 ]
+if os.environ.get("PROBE_SETTINGS"):
+    SETTINGS = [json.loads(a) for a in os.environ["PROBE_SETTINGS"].split(";")]
 if os.environ.get("PROBE_HEAD"):
     SETTINGS.insert(0, {"RT_LIB_PATH": os.path.join(ROOT, "realtrace_b200", "librt_variant_head.so")})
 RANKS = [int(x) for x in os.environ.get("PROBE_RANKS", "0,7").split(",")]

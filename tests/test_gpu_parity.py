@@ -415,10 +415,11 @@ def test_work_order_feedback_never_changes_a_pixel(name):
 
 @pytest.mark.parametrize("name", ["synth_small_d1", "analytic_stock_d1", "one_triangle", "two_triangles",
                                   "degenerate_and_duplicate_triangles", "coincident_centroids"])
-@pytest.mark.parametrize("div", [1, 3])
+@pytest.mark.parametrize("div", [1, 3, 0])
 def test_heavy_tiles_on_the_wide_view_never_change_a_pixel(name, div, monkeypatch):
     """RT_WIDE_HEAVY: the batches of the heaviest tiles (the first 1/div of the cost-sorted order) walk the 4-wide view
-    of the tree inside the same launch, the others the binary tree.  Both views index the same nodes and tie-break
+    of the tree inside the same launch, the others the binary tree; div = 0: batches change to the wide view mid-walk
+    (RT_WIDE_AFTER_BURSTS).  Both views index the same nodes and tie-break
     equal distances by object order, so frames, first-hit ids and distances are those of the binary walk — for the
     whole frame (k_frame) and for a logical rank's share pushed into a shared frame (k_frame_push)."""
     import torch
@@ -435,7 +436,15 @@ def test_heavy_tiles_on_the_wide_view_never_change_a_pixel(name, div, monkeypatc
     ref = ref_ctx.render(cam, depth, aux=True)
     ref_ctx.close()
     monkeypatch.setenv("RT_WIDE_HEAVY", "2")
-    monkeypatch.setenv("RT_WIDE_HEAVY_DIV", str(div))
+    if div:
+        monkeypatch.setenv("RT_WIDE_HEAVY_DIV", str(div))
+        monkeypatch.setenv("RT_WIDE_AFTER_BURSTS", "0")
+    else:
+        # no tile starts on the wide view; every batch moves to it after 2 bursts of 4 steps, i.e. nearly every ray
+        # changes views in the middle of its walk (stack and current node carry over)
+        monkeypatch.setenv("RT_WIDE_HEAVY_DIV", "65536")
+        monkeypatch.setenv("RT_WIDE_AFTER_BURSTS", "2")
+        monkeypatch.setenv("RT_LOOP_PRIMARY", "4")
     ctx = make_ctx(scene)
     for k in range(4):                         # frame 0 runs in spatial order (binary walk only), then the sorted order
         got = ctx.render(cam, depth, tile=(32, 16), aux=True)
@@ -688,9 +697,11 @@ def build_overflow_case():
     return s, scenes.close_camera(96, 64), 120
 
 
-def test_render_without_stats_reports_kernel_errors():
-    """rt_render(stats = NULL) must look at the device error word too: a dielectric hall of mirrors at depth 30
-    overflows the per-lane stack of parked rays in k_paths."""
+def test_render_without_stats_reports_kernel_errors(monkeypatch):
+    """rt_render(stats = NULL) must look at the device error word too: a dielectric hall of mirrors at depth 120
+    overflows the per-lane stack of parked rays in k_paths.  (With RT_PATH_SHARE=1 the idle lanes of the warp take
+    the oldest parked rays and this scene no longer overflows, so the hand-over is switched off here.)"""
+    monkeypatch.setenv("RT_PATH_SHARE", "0")
     scene, cam, depth = build_overflow_case()
     ctx = make_ctx(scene)
     rgb = np.zeros((cam.height, cam.width, 3), np.uint8)
