@@ -68,6 +68,7 @@ static rt_ctx* make_ctx(int device) {
         env_int("RT_REFILL_SHADOW", 1, 32, c->refill_shadow);
         env_int("RT_BLOCKS_PER_SM", 1, 32, c->blocks_per_sm);
         env_int("RT_WIDE_BVH", 0, 2, c->wide_bvh);
+        env_int("RT_MULTI_THREADS", 0, 2, c->mg_threads);
         env_int("RT_WIDE_HEAVY", 0, 2, c->wide_heavy);
         env_int("RT_WIDE_HEAVY_DIV", 1, 65536, c->wide_heavy_div);
         env_int("RT_WIDE_AFTER_BURSTS", 0, 1024, c->wide_after_bursts);
@@ -217,6 +218,7 @@ int rt_device_count(rt_ctx* ctx, int32_t* n) {
 
 int rt_destroy(rt_ctx* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    rt_multi_pool_stop(ctx);
     for (rt_ctx* k : ctx->kids) {
         cudaSetDevice(k->device);
         cudaDeviceSynchronize();

@@ -18,8 +18,11 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <condition_variable>
 #include <cstring>
 #include <ctime>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #include "rt_context.h"
@@ -63,6 +66,105 @@ std::vector<rt_ctx*> ranks_of(rt_ctx* c) {
 }
 
 }  // namespace
+
+// ---- one enqueue thread per extra device --------------------------------------------------------------------
+// A frame of an n-device context is ~8 runtime calls per rank for the kernels and ~5 + its granules for the copy to the
+// host: 0.117 ms of the caller's time per frame at 8 GPUs when one thread issues them all.  Rank r's calls are independent
+// of the other ranks' (own device, own streams), so with RT_MULTI_THREADS rank 0's are issued by the caller and every other
+// rank's by a thread of its own; the caller returns when all of them have been enqueued (0.062 ms at 8 GPUs).  Measured on
+// 8 x B200 (profiles/r2_tuning.md section 18) the pipelined frame rate does not change — it is bound by the frame's way into
+// host memory, not by the enqueue — so the default is 0 (one thread); 1 = threads from four devices on, 2 = always.
+struct RtRankPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable go, done;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+    const std::function<void(int)>* job = nullptr;
+    std::vector<RtError> errs;
+};
+
+static void rank_pool_worker(RtRankPool* p, int r, int device) {
+    cudaSetDevice(device);
+    uint64_t seen = 0;
+    for (;;) {
+        const std::function<void(int)>* job;
+        {
+            std::unique_lock<std::mutex> lk(p->m);
+            p->go.wait(lk, [&] { return p->stop || p->gen != seen; });
+            if (p->stop) return;
+            seen = p->gen;
+            job = p->job;
+        }
+        RtError err{RT_OK, ""};
+        try {
+            (*job)(r);
+        } catch (const RtError& e) {
+            err = e;
+        } catch (const std::exception& e) {
+            err = RtError{RT_ERR_CUDA, e.what()};
+        }
+        {
+            std::lock_guard<std::mutex> lk(p->m);
+            p->errs[r] = err;
+            if (--p->pending == 0) p->done.notify_one();
+        }
+    }
+}
+
+// job(r) for every rank: rank 0 on the calling thread, the others on their threads (or all on the caller without a
+// pool).  Returns when every job has returned; rethrows the lowest rank's error.
+static void run_on_ranks(rt_ctx* c, const std::function<void(int)>& job) {
+    const int n = 1 + (int)c->kids.size();
+    // (the two wake-ups of a frame cost what two ranks' calls cost: worth it from four devices on; 2 = always)
+    if (n == 1 || !c->mg_threads || (c->mg_threads == 1 && n < 4)) {
+        for (int r = 0; r < n; r++) job(r);
+        return;
+    }
+    if (!c->mg_pool) {
+        RtRankPool* p = new RtRankPool;
+        p->errs.assign(n, RtError{RT_OK, ""});
+        for (int r = 1; r < n; r++) p->th.emplace_back(rank_pool_worker, p, r, c->kids[r - 1]->device);
+        c->mg_pool = p;
+    }
+    RtRankPool* p = c->mg_pool;
+    {
+        std::lock_guard<std::mutex> lk(p->m);
+        for (auto& e : p->errs) e = RtError{RT_OK, ""};
+        p->job = &job;
+        p->pending = n - 1;
+        p->gen++;
+    }
+    p->go.notify_all();
+    RtError mine{RT_OK, ""};
+    try {
+        job(0);
+    } catch (const RtError& e) {
+        mine = e;
+    }
+    {
+        std::unique_lock<std::mutex> lk(p->m);
+        p->done.wait(lk, [&] { return p->pending == 0; });
+        p->job = nullptr;
+    }
+    if (mine.code != RT_OK) throw mine;
+    for (auto& e : p->errs)
+        if (e.code != RT_OK) throw e;
+}
+
+void rt_multi_pool_stop(rt_ctx* c) {
+    RtRankPool* p = c->mg_pool;
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->m);
+        p->stop = true;
+    }
+    p->go.notify_all();
+    for (auto& t : p->th) t.join();
+    delete p;
+    c->mg_pool = nullptr;
+}
 
 // ---- the striped frame ------------------------------------------------------------------------------------
 void rt_frame_release(rt_ctx* c, rt_ctx::SharedFrame& f) {
@@ -176,6 +278,12 @@ void rt_multi_attach(rt_ctx* c, const std::vector<int>& devices, rt_ctx* (*make_
 // LBVH build on every device at once (the build synchronises with the host several times; one helper thread per
 // extra device keeps the builds concurrent).
 void rt_multi_build(rt_ctx* c, bool refit_only) {
+    // every rank renders a share: the heaviest tiles will walk the 4-wide view (RT_WIDE_HEAVY), so build it with the
+    // tree instead of inside the second frame
+    if (!c->kids.empty() && c->wide_heavy >= 1) {
+        c->want_nodes4 = true;
+        for (rt_ctx* k : c->kids) k->want_nodes4 = true;
+    }
     std::vector<RtError> errs(c->kids.size(), RtError{RT_OK, ""});
     std::vector<std::thread> th;
     for (size_t i = 0; i < c->kids.size(); i++) {
@@ -222,17 +330,18 @@ void rt_multi_enqueue_frame(rt_ctx* c, const rt_camera* cam, const rt_render_par
     }
     const uint32_t k = c->mg_frame++;
     static const bool trace = getenv("RT_TRACE_HOST") != nullptr;
-    for (int r = 0; r < n; r++) {
+    run_on_ranks(c, [&](int r) {
         rt_ctx* x = ranks[r];
         timespec ts0;
         if (trace) clock_gettime(CLOCK_MONOTONIC, &ts0);
         RT_CUDA(cudaSetDevice(x->device));
-        q.rank = r;
+        rt_render_params qr = q;
+        qr.rank = r;
         uint32_t total, owned, tb;
-        rt_tile_layout(cam->width, cam->height, q.tile_w, q.tile_h, r, n, &total, &owned, &tb);
+        rt_tile_layout(cam->width, cam->height, qr.tile_w, qr.tile_h, r, n, &total, &owned, &tb);
         x->d_packed.reserve((size_t)(owned ? owned : 1) * tb);
         if (r == 0) RT_CUDA(cudaEventRecord(c->mg_ev[0], x->stream));
-        rt_push_frame(x, cam, &q, x->d_packed.p, frame_dev, c->mg_sync, k, aux_dev);
+        rt_push_frame(x, cam, &qr, x->d_packed.p, frame_dev, c->mg_sync, k, aux_dev);
         if (r == 0) RT_CUDA(cudaEventRecord(c->mg_ev[1], x->stream));
         if (trace) {
             timespec ts1;
@@ -240,7 +349,7 @@ void rt_multi_enqueue_frame(rt_ctx* c, const rt_camera* cam, const rt_render_par
             fprintf(stderr, "[rt host] frame %u rank %d enqueued in %.3f ms\n", k, r,
                     (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
         }
-    }
+    });
     RT_CUDA(cudaSetDevice(c->device));
 }
 
@@ -285,7 +394,8 @@ void rt_frame_download_async(rt_ctx* c, const rt_ctx::SharedFrame& f, uint8_t* h
                              cudaEvent_t* done, uint32_t* h_sticky) {
     std::vector<rt_ctx*> ranks = ranks_of(c);
     const int n = (int)ranks.size();
-    for (int r = 0; r < n; r++) {
+    // (`ready` has been recorded by the caller: every rank's wait refers to that record)
+    run_on_ranks(c, [&](int r) {
         rt_ctx* x = ranks[r];
         RT_CUDA(cudaSetDevice(x->device));
         RT_CUDA(cudaStreamWaitEvent(x->copy_stream, ready, 0));
@@ -303,6 +413,6 @@ void rt_frame_download_async(rt_ctx* c, const rt_ctx::SharedFrame& f, uint8_t* h
         // word is final
         RT_CUDA(cudaMemcpyAsync(h_sticky + r, x->d_sticky.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, x->copy_stream));
         RT_CUDA(cudaEventRecord(done[r], x->copy_stream));
-    }
+    });
     RT_CUDA(cudaSetDevice(c->device));
 }

@@ -108,6 +108,8 @@ struct rt_ctx {
     std::vector<rt_ctx*> kids;
     rt_ctx* parent = nullptr;
     void* mg_sync = nullptr;               // handshake words in rank 0's memory (rt_peer_sync layout), mapped by every rank
+    struct RtRankPool* mg_pool = nullptr;  // one enqueue thread per extra device (multi_device.cu), created by the first frame
+    int mg_threads = 0;                    // RT_MULTI_THREADS: 0 = the caller's thread issues every rank's calls (default: measured equal), 1 = threads from 4 devices on, 2 = always
     uint32_t mg_frame = 0;                 // frames rendered through the multi-device path (handshake slot counter)
     cudaEvent_t mg_ev[2] = {};
     std::vector<void*> host_registered;    // caller buffers page-locked on first use by rt_render_enqueue (unregistered at destroy)
@@ -244,6 +246,7 @@ struct rt_ctx {
 // ---- entry points implemented across the .cu files ------------------------------------------------
 void rt_build_bvh(rt_ctx* c, bool refit_only);                      // bvh_build.cu
 void rt_sort_pairs_device(rt_ctx* c, uint32_t n);   // radix_sort.cu: d_keys[0]/d_vals[0] -> sorted_buf; only enqueues
+void rt_multi_pool_stop(rt_ctx* c);                  // multi_device.cu: joins the per-rank enqueue threads
 void rt_ensure_nodes4(rt_ctx* c);                    // bvh_build.cu: builds the 4-wide view now if the scene has none (enqueues)
 int rt_sort_passes_done(rt_ctx* c);                  // passes of the last sort that moved keys (synchronises)
 void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p, void* rgb_dev,

@@ -69,8 +69,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--child":
         child(sys.argv[2])
     else:
-        for name in ("synth1m", "blub4k"):
-            for v in ({}, {"RT_NO_VMM": "1"}, {"RT_FRAME_KERNEL": "0"}, {"RT_FRAME_KERNEL": "0", "RT_NO_VMM": "1"}):
+        names = os.environ.get("PROBE_WORKLOADS", "synth1m,blub4k").split(",")
+        variants = ({}, {"RT_NO_VMM": "1"}, {"RT_FRAME_KERNEL": "0"}, {"RT_FRAME_KERNEL": "0", "RT_NO_VMM": "1"})
+        if os.environ.get("PROBE_ENVS"):
+            variants = [json.loads(a) for a in os.environ["PROBE_ENVS"].split(";")]
+        for name in names:
+            for v in variants:
                 env = dict(os.environ)
                 env.update(v)
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", name], env=env, capture_output=True,
