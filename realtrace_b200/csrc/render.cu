@@ -376,6 +376,10 @@ __device__ __forceinline__ bool shade_batch(const TravArgs& a, bool pending, uin
 #ifndef RT_FRAME_WIDE
 #define RT_FRAME_WIDE 2                 // k_frame / k_frame_push: 2 = heavy batches walk the wide view, 0 = binary walk only
 #endif
+// Both walks are compiled into the 72-register build only (small shares: that is where one straggler batch ends the
+// launch).  In the 56-register build the second loop's registers push per-burst state into local memory: measured 5 % on
+// the whole 4K frame (1.081 -> 1.137 ms) with the wide walk never taken, and a 1/8 share does not gain from it there.
+__host__ __device__ constexpr int frame_wide_mode(int minb) { return minb >= RT_DENSE_MIN_BLOCKS ? 0 : RT_FRAME_WIDE; }
 #ifndef RT_SHADE_FUSED_MIN_BLOCKS
 #define RT_SHADE_FUSED_MIN_BLOCKS 7     // SHADE: hold the kernel to the traversal loop's 72 registers (the once-per-batch shading spills)
 #endif
@@ -897,7 +901,7 @@ __global__ void __launch_bounds__(TRAV_TPB, MINB) k_frame(const __grid_constant_
         __threadfence_system();
     }
     // ---- phase 1
-    traverse_body<MODE_PRIMARY, COUNT, true, RT_FRAME_WIDE, false>(a.t, nullptr);
+    traverse_body<MODE_PRIMARY, COUNT, true, frame_wide_mode(MINB), false>(a.t, nullptr);
     stamp(1);
     if (a.phase1_only) return;
     // every hit of the frame is in the queue once all CTAs are here
@@ -1069,7 +1073,7 @@ __global__ void __launch_bounds__(TRAV_TPB, MINB) k_frame_push(const __grid_cons
         }
     }
     stamp(2);
-    traverse_body<MODE_PRIMARY, COUNT, true, RT_FRAME_WIDE, true>(a.t, s_pdir);
+    traverse_body<MODE_PRIMARY, COUNT, true, frame_wide_mode(MINB), true>(a.t, s_pdir);
     stamp(1);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -2033,8 +2037,9 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         ta.loop_style = c->loop_primary;
         // the tiles at the head of the heavy-tiles-first order walk the 4-wide view (traverse_body<WIDE = 2>): needs a
         // cost-sorted order (from the second frame of a layout on) and whole-batch refill; the view is built on first use
+        const bool dense = (long long)f.n_local_pix >= c->dense_min_pixels;
         ta.f.n_wide_pix = 0;
-        if (RT_FRAME_WIDE == 2 && f.tile_cost && c->frames_in_layout >= 1 && ta.refill_min == 32 && !ta.brute &&
+        if (RT_FRAME_WIDE == 2 && !dense && f.tile_cost && c->frames_in_layout >= 1 && ta.refill_min == 32 && !ta.brute &&
             (c->wide_heavy == 2 || (c->wide_heavy == 1 && f.world > 1)) && c->n_bvh >= 1) {
             rt_ensure_nodes4(c);
             ta.s = c->scene;
@@ -2042,7 +2047,7 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         }
         // long batches the order did not announce move to the wide view after a few bursts (no order needed)
         ta.f.wide_after_bursts = 0;
-        if (RT_FRAME_WIDE == 2 && c->wide_after_bursts > 0 && ta.refill_min == 32 && !ta.brute && ta.loop_style > 0 &&
+        if (RT_FRAME_WIDE == 2 && !dense && c->wide_after_bursts > 0 && ta.refill_min == 32 && !ta.brute && ta.loop_style > 0 &&
             (c->wide_heavy == 2 || (c->wide_heavy == 1 && f.world > 1)) && c->n_bvh >= 1) {
             rt_ensure_nodes4(c);
             ta.s = c->scene;
@@ -2056,7 +2061,6 @@ void rt_render_frame(rt_ctx* c, const rt_camera* cam, const rt_render_params* p,
         fa.y.zero_words = zero_next;
         fa.y.n_zero_words = (uint32_t)(sizeof(FrameKernelCounters) / sizeof(uint32_t));
         // large shares run the 9-CTAs-per-SM build of the kernel, small ones the 7-CTA build (see k_frame)
-        const bool dense = (long long)f.n_local_pix >= c->dense_min_pixels;
         const int fk_blocks = dense ? c->frame_blocks_dense : c->frame_blocks;
         const int fkp_blocks = dense ? c->frame_push_blocks_dense : c->frame_push_blocks;
         if (p->flags & RT_FLAG_WARP_TIMES) {
