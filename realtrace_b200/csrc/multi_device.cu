@@ -21,6 +21,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <ctime>
+#include <exception>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -104,6 +105,8 @@ static void rank_pool_worker(RtRankPool* p, int r, int device) {
             err = e;
         } catch (const std::exception& e) {
             err = RtError{RT_ERR_CUDA, e.what()};
+        } catch (...) {
+            err = RtError{RT_ERR_CUDA, "unknown exception on a rank's enqueue thread"};
         }
         {
             std::lock_guard<std::mutex> lk(p->m);
@@ -137,18 +140,18 @@ static void run_on_ranks(rt_ctx* c, const std::function<void(int)>& job) {
         p->gen++;
     }
     p->go.notify_all();
-    RtError mine{RT_OK, ""};
+    std::exception_ptr mine;                   // whatever rank 0's job throws: the others still refer to `job`, wait first
     try {
         job(0);
-    } catch (const RtError& e) {
-        mine = e;
+    } catch (...) {
+        mine = std::current_exception();
     }
     {
         std::unique_lock<std::mutex> lk(p->m);
         p->done.wait(lk, [&] { return p->pending == 0; });
         p->job = nullptr;
     }
-    if (mine.code != RT_OK) throw mine;
+    if (mine) std::rethrow_exception(mine);
     for (auto& e : p->errs)
         if (e.code != RT_OK) throw e;
 }
